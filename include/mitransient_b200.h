@@ -1,0 +1,248 @@
+/*
+ * mitransient_b200.h -- C ABI of the B200-native transient path-tracing hot path.
+ *
+ * This is the drop-in boundary for the ONE path this repository accelerates:
+ * mitransient's per-bounce transient path-tracing wavefront plus the scatter-add of
+ * per-path radiance into the (y, x, time) film histogram.  Every entry point cites the
+ * reference interface (file:line under the mitransient source tree) it replaces.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; pointers + sizes only.
+ *  - every function returns 0 on success or a negative TrStatus; the message of the last
+ *    failure on the calling thread is available from tr_last_error().
+ *  - "device" pointers are CUDA device pointers on the CURRENT device of the calling
+ *    thread; "host" pointers are ordinary host memory.  Output buffers are always
+ *    allocated by the caller (PyTorch on the host side); the library only owns the
+ *    opaque TrScene handle.
+ *  - all work is enqueued on the caller-supplied cudaStream_t (passed as void*).  No hidden
+ *    device synchronisation, except where a function is documented as synchronous.
+ *  - film layout is the reference's:  film[y][x][t][c]  (row-major, channel innermost;
+ *    mitransient/render/transient_image_block.py:63-68,142-144).
+ */
+#ifndef MITRANSIENT_B200_H
+#define MITRANSIENT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TR_ABI_VERSION 3
+
+/* ------------------------------------------------------------------ status codes */
+typedef enum TrStatus {
+    TR_OK = 0,
+    TR_ERR_INVALID_ARGUMENT = -1, /* bad pointer / size / enum value                         */
+    TR_ERR_UNSUPPORTED = -2,      /* combination the reference rejects, or not built here    */
+    TR_ERR_CUDA = -3,             /* a CUDA runtime call failed (text in tr_last_error)      */
+    TR_ERR_NO_DEVICE = -4,        /* no sm_100 device visible: the product has NO CPU path   */
+    TR_ERR_OUT_OF_MEMORY = -5
+} TrStatus;
+
+/* ------------------------------------------------------------------ scene description
+ * A flat restatement of what mi.load_dict()/XML hands to the integrator: geometry as a
+ * triangle soup grouped into shapes, a BSDF table, an emitter table, one sensor and its
+ * film (mitransient/utils.py:78-220 is the benchmark scene expressed this way).           */
+
+enum { TR_SHAPE_MESH = 0, TR_SHAPE_RECTANGLE = 1 };
+enum { TR_SHAPE_FLAG_SENSOR = 1 };       /* the shape carrying the nlos_capture_meter      */
+
+typedef struct TrShapeDesc {
+    int32_t type;        /* TR_SHAPE_*: rectangle = Mitsuba `rectangle` (2 triangles for ray
+                            intersection, to_world-based uniform sampling); mesh = obj/ply/cube */
+    int32_t bsdf;        /* index into TrSceneDesc.bsdfs                                    */
+    int32_t emitter;     /* index into TrSceneDesc.emitters (area light) or -1              */
+    int32_t flags;       /* TR_SHAPE_FLAG_*                                                 */
+    int32_t interior_medium; /* index into media or -1 (transient_prbvolpath)              */
+    int32_t exterior_medium; /* index into media or -1                                     */
+    uint32_t tri_begin;  /* first triangle of this shape in tri_verts                       */
+    uint32_t tri_count;
+    float to_world[12];  /* row-major 3x4 affine; meaningful for rectangles                 */
+} TrShapeDesc;
+
+enum { TR_BSDF_DIFFUSE = 0, TR_BSDF_NULL = 1 };
+enum { TR_BSDF_FLAG_TWOSIDED = 1 };
+
+typedef struct TrBsdfDesc {
+    int32_t type;        /* TR_BSDF_*                                                       */
+    int32_t flags;       /* TR_BSDF_FLAG_*                                                  */
+    float reflectance[3];
+    float _pad[3];
+} TrBsdfDesc;
+
+enum { TR_EMITTER_AREA = 0, TR_EMITTER_PROJECTOR = 1 };
+
+typedef struct TrEmitterDesc {
+    int32_t type;        /* TR_EMITTER_*                                                    */
+    int32_t shape;       /* area: index of the emitting shape; projector: -1                */
+    float radiance[3];   /* area: radiance; projector: irradiance                           */
+    float fov_x;         /* projector: horizontal field of view, degrees                    */
+    float to_world[12];  /* projector: row-major 3x4 affine (origin + orientation)          */
+    float _pad[2];
+} TrEmitterDesc;
+
+typedef struct TrMediumDesc { /* homogeneous medium + Henyey-Greenstein phase function      */
+    float sigma_t[3];
+    float albedo[3];
+    float g;
+    float scale;
+} TrMediumDesc;
+
+enum { TR_SENSOR_PERSPECTIVE = 0, TR_SENSOR_NLOS_CAPTURE_METER = 1 };
+
+typedef struct TrSensorDesc {
+    int32_t type;           /* TR_SENSOR_*                                                  */
+    int32_t shape;          /* nlos_capture_meter: index of the relay-wall shape            */
+    float to_world[12];     /* perspective: camera-to-world, row-major 3x4                  */
+    float sample_to_camera[16]; /* perspective: inverse of Mitsuba's perspective_projection */
+    float near_clip, far_clip;
+    float origin[3];        /* nlos_capture_meter: sensor_origin
+                               (mitransient/sensors/nloscapturemeter.py:100-102)            */
+    int32_t medium;         /* index of the medium the sensor sits in, or -1                */
+} TrSensorDesc;
+
+typedef struct TrFilmDesc {  /* mitransient/films/transient_hdr_film.py:114-121             */
+    uint32_t width, height;
+    uint32_t temporal_bins;
+    float start_opl;
+    float bin_width_opl;
+} TrFilmDesc;
+
+typedef struct TrSceneDesc {
+    uint32_t abi_version;          /* must be TR_ABI_VERSION                                */
+    uint32_t n_tris;
+    const float *tri_verts;        /* host, [n_tris][3 vertices][xyz], world space          */
+    uint32_t n_shapes;
+    const TrShapeDesc *shapes;     /* host                                                  */
+    uint32_t n_bsdfs;
+    const TrBsdfDesc *bsdfs;       /* host                                                  */
+    uint32_t n_emitters;
+    const TrEmitterDesc *emitters; /* host                                                  */
+    uint32_t n_media;
+    const TrMediumDesc *media;     /* host (may be NULL when n_media == 0)                  */
+    TrSensorDesc sensor;
+    TrFilmDesc film;
+} TrSceneDesc;
+
+/* ------------------------------------------------------------------ render parameters
+ * Integrator properties keep the reference's names and defaults
+ * (mitransient/integrators/common.py:22-30, transientpath.py:43-86,
+ *  transientnlospath.py:201-249).                                                         */
+
+enum { TR_INTEGRATOR_TRANSIENT_PATH = 0,
+       TR_INTEGRATOR_TRANSIENT_NLOS_PATH = 1,
+       TR_INTEGRATOR_TRANSIENT_PRBVOLPATH = 2 };
+
+enum { TR_FLAG_CAMERA_UNWARP = 1,          /* common.py:25                                  */
+       TR_FLAG_DISCARD_DIRECT_LIGHT = 2,   /* common.py:27                                  */
+       TR_FLAG_HIDE_EMITTERS = 4,          /* transientpath.py:161-163                      */
+       /* transient_nlos_path only (transientnlospath.py:201-249): */
+       TR_FLAG_NLOS_LASER_SAMPLING = 8,
+       TR_FLAG_NLOS_HG_SAMPLING = 16,
+       TR_FLAG_NLOS_HG_SAMPLING_DO_RROULETTE = 32,
+       TR_FLAG_NLOS_HG_SAMPLING_INCLUDES_RELAY_WALL = 64,
+       TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES = 128,
+       TR_FLAG_DISCARD_DIRECT_PATHS = 256 };
+
+enum { TR_CAPTURE_SINGLE = 0, TR_CAPTURE_CONFOCAL = 1, TR_CAPTURE_EXHAUSTIVE = 2 };
+
+typedef struct TrRenderParams {
+    int32_t integrator;     /* TR_INTEGRATOR_*                                              */
+    uint32_t max_depth;     /* 0xffffffff == unbounded (reference: max_depth = -1)          */
+    uint32_t rr_depth;
+    uint32_t flags;         /* TR_FLAG_*                                                    */
+    uint32_t spp;           /* samples per pixel of THIS pass                               */
+    uint32_t total_spp;     /* sum over passes; deposits are scaled by 1/total_spp
+                               (mitransient/integrators/common.py:150-155,173)              */
+    uint32_t seed;          /* sampler seed of this pass (common.py:52,72)                  */
+    /* pixel-tile sharding: tiles of tile_size x tile_size pixels are dealt
+       round-robin; this call renders the tiles t with t % world == rank.  world == 1
+       renders everything.  RNG streams are indexed by the GLOBAL sample index, so the
+       film does not depend on `world`.                                                    */
+    uint32_t tile_size;
+    uint32_t rank, world;
+    int32_t film_channels;  /* layout of `film` passed to tr_render: 4 = raw RGBW
+                               (develop(raw=True)), 3 = developed RGB                      */
+    int32_t accumulate;     /* 0: owned pixels are overwritten; 1: added to (multi-pass)    */
+    /* transient_nlos_path */
+    int32_t capture_type;   /* TR_CAPTURE_*                                                 */
+    int32_t filter_depth;   /* -1 = off                                                     */
+    float laser_target[3];  /* `single` capture: illuminated relay-wall point (set by the
+                               host, cf. transientnlospath.py:328-336)                      */
+    uint32_t _reserved[4];
+} TrRenderParams;
+
+/* Exact work counters; identical integers are produced by the CPU oracle, which makes
+ * them a bit-exact parity check on the integer/index side of the path.                   */
+typedef struct TrCounters {
+    uint64_t paths;             /* camera paths started                                     */
+    uint64_t vertices;          /* N_v: loop iterations executed (live path vertices)       */
+    uint64_t deposits;          /* non-zero deposits offered to the film                    */
+    uint64_t deposits_in_range; /* ... that passed the [start, start + T*bw) mask           */
+    uint64_t bin_checksum;      /* sum over in-range deposits of (pixel_index * T + bin)    */
+    uint64_t shadow_rays;       /* visibility tests issued                                  */
+    uint64_t reserved[2];
+} TrCounters;
+
+typedef struct TrScene TrScene; /* opaque: device copy of the scene + BVH                   */
+
+/* One recorded deposit = the arguments of TransientHDRFilm.add_transient_data
+ * (mitransient/films/transient_hdr_film.py:250-276) after the 1/spp pre-scale.           */
+typedef struct TrDeposit {
+    float x, y;     /* splatting position (integer valued for the box filter)               */
+    float opl;      /* optical path length ("distance")                                     */
+    float r, g, b;  /* spec * sample_scale * ray_weight                                     */
+} TrDeposit;
+
+/* ------------------------------------------------------------------ entry points */
+
+/* Library / device probe.  Returns TR_OK iff an sm_100 class device is current.           */
+int tr_device_check(void);
+int tr_abi_version(void);
+const char *tr_last_error(void);
+
+/* Upload a scene, build its BVH.  Replaces mi.load_dict()'s hand-off of shapes / bsdfs /
+ * emitters / sensor / film to the integrator (scene services called from
+ * mitransient/integrators/transientpath.py:134-231).                                      */
+int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene);
+void tr_scene_destroy(TrScene *scene);
+/* bytes of the packed scene blob, number of BVH nodes (introspection for tests)           */
+int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_tris);
+
+/* THE hot path.  Replaces TransientADIntegrator.render's per-pass body
+ * (mitransient/integrators/common.py:157-206): sample_rays -> TransientPath.sample
+ * (transientpath.py:88-326) / TransientNLOSPath.sample (transientnlospath.py:673-927)
+ * -> add_transient_data (transient_hdr_film.py:250-276) -> TransientImageBlock.put_/accum
+ * (transient_image_block.py:103-151,79-81), plus the steady-image splat.
+ *   film     device, float[H][W][T][film_channels]
+ *   steady   device, float[H][W][3]   (mean of L over total_spp), may be NULL
+ *   counters device, TrCounters accumulated with atomics, may be NULL
+ * Asynchronous on `stream`.                                                               */
+int tr_render(const TrScene *scene, const TrRenderParams *params,
+              float *film, float *steady, TrCounters *counters, void *stream);
+
+/* Same, but film / steady are HOST buffers (pinned or pageable): the film is rendered in
+ * row bands on the device and copied out band by band so the device->host copy of band i
+ * overlaps the rendering of band i+1.  Synchronous (returns when the host buffers are
+ * complete).  This is what mi.render() returns on a CPU variant.                          */
+int tr_render_to_host(const TrScene *scene, const TrRenderParams *params,
+                      float *film_host, float *steady_host, TrCounters *counters_host,
+                      void *stream);
+
+/* K4 on its own: TransientImageBlock.put_ for a stream of deposits
+ * (transient_hdr_film.py:263-276 + transient_image_block.py:130-149).  `deposits` is a
+ * device array; film is device float[H][W][T][channels], accumulated into (not cleared). */
+int tr_film_scatter_add(float *film, const TrFilmDesc *film_desc, int32_t channels,
+                        const TrDeposit *deposits, uint64_t n_deposits, void *stream);
+
+/* TransientHDRFilm.develop_transient_ (transient_hdr_film.py:220-248): drop the weight
+ * channel, dividing by it where it is non-zero.  in: float[n_bins][in_channels] with the
+ * weight last; out: float[n_bins][in_channels-1].                                         */
+int tr_film_develop(const float *film_raw, float *out, uint64_t n_bins, int32_t in_channels,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MITRANSIENT_B200_H */

@@ -1,0 +1,41 @@
+"""mitransient_b200 -- B200-native transient path tracing behind mitransient's plugin surface.
+
+Usage mirrors the reference (examples/transient/0-render_cbox_diffuse.ipynb)::
+
+    import mitransient_b200 as mitr
+    scene = mitr.load_dict(mitr.cornell_box())
+    steady, transient = mitr.render(scene, spp=256, seed=0)      # (H,W,3), (H,W,T,3) CUDA tensors
+
+All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in
+``include/mitransient_b200.h``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from . import _abi
+from . import films, integrators, sensors            # registers the plugins
+from ._lib import TransientError, lib_path
+from .films.transient_hdr_film import TransientHDRFilm
+from .integrators.common import TransientADIntegrator
+from .integrators.transientpath import TransientPath
+from .plugins import register_film, register_integrator, register_sensor
+from .scene import Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
+from .sensors.nloscapturemeter import NLOSCaptureMeter
+from .transforms import ScalarTransform4f
+from .utils import cornell_box, cornell_box_config, speed_of_light
+
+__version__ = "0.1.0"
+
+
+def render(scene: Scene, params=None, sensor=0, seed: int = 0, spp: int = 0, **kwargs):
+    """``mi.render`` for transient scenes: ``scene.integrator().render(scene, sensor, seed, spp)``.
+    Returns ``(steady, transient)`` like the reference (mitransient/integrators/common.py:212-213)."""
+    integrator = scene.integrator()
+    if integrator is None:
+        raise ValueError("the scene has no integrator")
+    return integrator.render(scene, sensor=sensor, seed=seed, spp=spp, **kwargs)
+
+
+def set_variant(*names):
+    """Accepted for source compatibility with ``mi.set_variant``; this build has exactly one variant
+    (CUDA, RGB, fp32)."""
+    return "cuda_rgb"

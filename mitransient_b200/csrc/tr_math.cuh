@@ -1,0 +1,127 @@
+// Device-side maths for the transient path tracer (sm_100a).
+//
+// ARITHMETIC CONTRACT (DESIGN.md "Arithmetic contract"): IEEE fp32, compiled with -fmad=false so
+// nothing is contracted implicitly; every fused multiply-add is spelled fmaf() here.  Division
+// and sqrt are the correctly rounded ones (nvcc defaults -prec-div=true -prec-sqrt=true, no
+// --use_fast_math).  The CPU oracle follows the same contract by specification, which makes the
+// walk of every path bit-identical between the two; only the order of additions into a film
+// bin differs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tr {
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+__device__ __forceinline__ V3 fma3(V3 a, float s, V3 c) { return v3(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z)); }
+__device__ __forceinline__ V3 normalize(V3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }
+__device__ __forceinline__ float max3(V3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+__device__ __forceinline__ float mulsign(float a, float b) {
+    return __uint_as_float(__float_as_uint(a) ^ (__float_as_uint(b) & 0x80000000u));
+}
+__device__ __forceinline__ V3 xyz(float4 v) { return v3(v.x, v.y, v.z); }
+
+#define TR_PI 3.14159265358979323846f
+#define TR_INV_PI 0.31830988618379067154f
+#define TR_RAY_EPSILON 8.940696716308594e-05f
+#define TR_SHADOW_EPSILON 8.940696716308594e-04f
+#define TR_FLT_MAX 3.402823466e+38f
+
+// Cephes single-precision sincos (same polynomial as the oracle).
+__device__ __forceinline__ void sincos_cephes(float x, float *s_out, float *c_out) {
+    float xa = fabsf(x);
+    int j = (int) (xa * 1.2732395447351628f);
+    j = (j + 1) & ~1;
+    float y = (float) j;
+    float z = fmaf(y, -0.78515625f, xa);
+    z = fmaf(y, -2.4187564849853515625e-4f, z);
+    z = fmaf(y, -3.77489497744594108e-8f, z);
+    float z2 = z * z;
+    float sp = fmaf(z2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, z2, -1.6666654611e-1f);
+    sp = fmaf(sp * z2, z, z);
+    float cp = fmaf(z2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, z2, 4.166664568298827e-2f);
+    cp = fmaf(cp * z2, z2, fmaf(z2, -0.5f, 1.0f));
+    bool swap = (j & 2) != 0;
+    float s = swap ? cp : sp, c = swap ? sp : cp;
+    if (j & 4) s = -s;
+    if ((j + 2) & 4) c = -c;
+    if (x < 0.0f) s = -s;
+    *s_out = s; *c_out = c;
+}
+
+// Mitsuba `independent` sampler: PCG32 per lane seeded through TEA from (seed, lane index).
+struct Pcg32 {
+    uint64_t state, inc;
+    __device__ __forceinline__ void advance() { state = state * 0x5851f42d4c957f2dULL + inc; }
+    __device__ __forceinline__ uint32_t next_u32() {
+        uint64_t old = state;
+        advance();
+        uint32_t xorshifted = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t) (old >> 59u);
+        return __funnelshift_r(xorshifted, xorshifted, rot);  // rotate right
+    }
+    __device__ __forceinline__ float next_1d() {
+        return __uint_as_float((next_u32() >> 9) | 0x3f800000u) - 1.0f;
+    }
+    __device__ __forceinline__ void seed(uint64_t initstate, uint64_t initseq) {
+        state = 0; inc = (initseq << 1) | 1u; advance(); state += initstate; advance();
+    }
+};
+__device__ __forceinline__ void sample_tea_32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    *o0 = v0; *o1 = v1;
+}
+
+__device__ __forceinline__ V3 square_to_cosine_hemisphere(float sx, float sy) {
+    float x = fmaf(2.0f, sx, -1.0f), y = fmaf(2.0f, sy, -1.0f);
+    bool is_zero = (x == 0.0f) && (y == 0.0f);
+    bool q13 = fabsf(x) < fabsf(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = 0.25f * TR_PI * rp * (1.0f / r);
+    if (q13) phi = 0.5f * TR_PI - phi;
+    if (is_zero) phi = 0.0f;
+    float s, c; sincos_cephes(phi, &s, &c);
+    float px = r * c, py = r * s;
+    float z2 = 1.0f - fmaf(py, py, px * px);
+    return v3(px, py, sqrtf(fmaxf(z2, 0.0f)));
+}
+
+__device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) {
+    float a2 = pdf_a * pdf_a, b2 = pdf_b * pdf_b;
+    float w = a2 / (a2 + b2);
+    return isfinite(w) ? w : 0.0f;
+}
+
+// Duff et al. orthonormal basis (Mitsuba coordinate_system); returns s, t = cross(n, s) is done by the caller.
+__device__ __forceinline__ V3 coordinate_system_s(V3 n) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -(1.0f / (sign + n.z));
+    float b = n.x * n.y * a;
+    return v3(mulsign(n.x * n.x * a, n.z) + 1.0f, mulsign(b, n.z), mulsign(-n.x, n.z));
+}
+
+__device__ __forceinline__ V3 offset_p(V3 p, V3 n, V3 dir) {
+    float mag = (1.0f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z))) * TR_RAY_EPSILON;
+    mag = mulsign(mag, dot(n, dir));
+    return fma3(n, mag, p);
+}
+
+}  // namespace tr

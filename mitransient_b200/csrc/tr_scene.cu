@@ -1,0 +1,299 @@
+// Host side of the scene: validation, per-triangle precomputation, BVH build, blob packing,
+// upload.  Replaces what Mitsuba's Scene / Shape constructors + Embree/OptiX acceleration build do
+// for the integrator (scene services used at mitransient/integrators/transientpath.py:134-231).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "tr_common.h"
+#include "tr_scene.h"
+
+namespace tr {
+namespace {
+
+struct H3 { float x, y, z; };
+inline H3 h3(float x, float y, float z) { return H3{x, y, z}; }
+inline H3 operator-(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline H3 operator*(H3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline float hdot(H3 a, H3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+inline H3 hcross(H3 a, H3 b) {
+    return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))};
+}
+inline H3 hxf_vector(const float *m, H3 v) {
+    return h3(fmaf(m[0], v.x, fmaf(m[1], v.y, m[2] * v.z)), fmaf(m[4], v.x, fmaf(m[5], v.y, m[6] * v.z)),
+              fmaf(m[8], v.x, fmaf(m[9], v.y, m[10] * v.z)));
+}
+
+struct BuildTri { float lo[3], hi[3], c[3]; uint32_t idx; };
+struct BuildNode { float lo[3], hi[3]; int left = -1, right = -1; uint32_t first = 0, count = 0; };
+
+constexpr uint32_t kLeafSize = 2;
+
+int build_rec(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32_t begin, uint32_t end) {
+    BuildNode nd;
+    float clo[3], chi[3];
+    for (int a = 0; a < 3; ++a) { nd.lo[a] = clo[a] = INFINITY; nd.hi[a] = chi[a] = -INFINITY; }
+    for (uint32_t i = begin; i < end; ++i)
+        for (int a = 0; a < 3; ++a) {
+            nd.lo[a] = std::min(nd.lo[a], tris[i].lo[a]); nd.hi[a] = std::max(nd.hi[a], tris[i].hi[a]);
+            clo[a] = std::min(clo[a], tris[i].c[a]); chi[a] = std::max(chi[a], tris[i].c[a]);
+        }
+    int me = (int) nodes.size();
+    nodes.push_back(nd);
+    uint32_t n = end - begin;
+    int axis = 0;
+    for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+    if (n <= kLeafSize || !(chi[axis] - clo[axis] > 0.0f)) {
+        if (n > 15) {  // degenerate cluster (identical centroids): split by index so leaves stay <= 15
+            uint32_t mid = begin + n / 2;
+            int l = build_rec(nodes, tris, begin, mid), r = build_rec(nodes, tris, mid, end);
+            nodes[me].left = l; nodes[me].right = r;
+            return me;
+        }
+        nodes[me].first = begin; nodes[me].count = n;
+        return me;
+    }
+    uint32_t mid = begin + n / 2;
+    std::nth_element(tris.begin() + begin, tris.begin() + mid, tris.begin() + end,
+                     [axis](const BuildTri &a, const BuildTri &b) {
+                         return a.c[axis] < b.c[axis] || (a.c[axis] == b.c[axis] && a.idx < b.idx);
+                     });
+    int l = build_rec(nodes, tris, begin, mid);
+    int r = build_rec(nodes, tris, mid, end);
+    nodes[me].left = l; nodes[me].right = r;
+    return me;
+}
+
+inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+}  // namespace
+
+bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
+    if (!desc) { err = "scene descriptor is NULL"; return false; }
+    if (desc->abi_version != TR_ABI_VERSION) { err = "TrSceneDesc.abi_version does not match this library"; return false; }
+    if (desc->n_tris == 0 || !desc->tri_verts) { err = "scene has no triangles"; return false; }
+    if (desc->n_shapes == 0 || !desc->shapes) { err = "scene has no shapes"; return false; }
+    if (desc->n_bsdfs == 0 || !desc->bsdfs) { err = "scene has no bsdfs"; return false; }
+    if (desc->n_emitters && !desc->emitters) { err = "emitters pointer is NULL"; return false; }
+    if (desc->n_tris >= (1u << 28)) { err = "too many triangles"; return false; }
+    const TrFilmDesc &f = desc->film;
+    if (f.width == 0 || f.height == 0 || f.temporal_bins == 0) { err = "film has a zero dimension"; return false; }
+    if (!(f.bin_width_opl > 0.0f)) { err = "bin_width_opl must be > 0"; return false; }
+    if ((uint64_t) f.width * f.height >= (1ull << 31)) { err = "film too large"; return false; }
+
+    const uint32_t nt = desc->n_tris, ns = desc->n_shapes;
+    std::vector<uint32_t> tri_shape(nt, 0xffffffffu);
+    for (uint32_t s = 0; s < ns; ++s) {
+        const TrShapeDesc &sd = desc->shapes[s];
+        if ((uint64_t) sd.tri_begin + sd.tri_count > nt) { err = "shape triangle range out of bounds"; return false; }
+        if (sd.bsdf < 0 || (uint32_t) sd.bsdf >= desc->n_bsdfs) { err = "shape bsdf index out of range"; return false; }
+        if (sd.emitter >= (int32_t) desc->n_emitters) { err = "shape emitter index out of range"; return false; }
+        if (sd.type == TR_SHAPE_RECTANGLE && sd.tri_count != 2) { err = "a rectangle must have exactly 2 triangles"; return false; }
+        for (uint32_t k = 0; k < sd.tri_count; ++k) tri_shape[sd.tri_begin + k] = s;
+    }
+    for (uint32_t i = 0; i < nt; ++i)
+        if (tri_shape[i] == 0xffffffffu) { err = "triangle not covered by any shape"; return false; }
+
+    // ---- per-triangle data (same arithmetic as the oracle's build_scene)
+    std::vector<DevTri> tris(nt);
+    std::vector<float> tri_area(nt);
+    std::vector<BuildTri> btris(nt);
+    float slo[3] = {INFINITY, INFINITY, INFINITY}, shi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < nt; ++i) {
+        const float *v = desc->tri_verts + 9 * (size_t) i;
+        for (int k = 0; k < 9; ++k) if (!std::isfinite(v[k])) { err = "non-finite vertex"; return false; }
+        H3 p0 = h3(v[0], v[1], v[2]);
+        H3 e1 = h3(v[3], v[4], v[5]) - p0, e2 = h3(v[6], v[7], v[8]) - p0;
+        H3 c = hcross(e1, e2);
+        float len = sqrtf(hdot(c, c));
+        H3 n = c * (1.0f / len);
+        DevTri &t = tris[i];
+        t.p0[0] = p0.x; t.p0[1] = p0.y; t.p0[2] = p0.z; t.shape = tri_shape[i];
+        t.e1[0] = e1.x; t.e1[1] = e1.y; t.e1[2] = e1.z; t.prim = i;
+        t.e2[0] = e2.x; t.e2[1] = e2.y; t.e2[2] = e2.z; t._r0 = 0;
+        t.n[0] = n.x; t.n[1] = n.y; t.n[2] = n.z; t._r1 = 0;
+        tri_area[i] = 0.5f * len;
+        BuildTri &b = btris[i];
+        b.idx = i;
+        for (int a = 0; a < 3; ++a) {
+            float x0 = v[a], x1 = v[3 + a], x2 = v[6 + a];
+            b.lo[a] = std::min(x0, std::min(x1, x2)); b.hi[a] = std::max(x0, std::max(x1, x2));
+            b.c[a] = (b.lo[a] + b.hi[a]) * 0.5f;
+            slo[a] = std::min(slo[a], b.lo[a]); shi[a] = std::max(shi[a], b.hi[a]);
+        }
+    }
+
+    // ---- BVH (median split, pre-order threaded).  Boxes are padded so that the fp32 slab test is
+    // conservative w.r.t. the triangle test: culling never changes the result.
+    std::vector<BuildNode> bnodes;
+    bnodes.reserve(2 * nt);
+    build_rec(bnodes, btris, 0, nt);
+    float extent = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
+    float absmax = 0.0f;
+    for (int a = 0; a < 3; ++a) absmax = std::max(absmax, std::max(std::fabs(slo[a]), std::fabs(shi[a])));
+    const float pad = 1e-4f * std::max(extent, absmax) + 1e-6f;
+    // pre-order layout == construction order of build_rec (node pushed before its children, left first)
+    const uint32_t nn = (uint32_t) bnodes.size();
+    std::vector<DevNode> nodes(nn);
+    // skip pointers: next node in pre-order that is not a descendant
+    std::vector<uint32_t> skip(nn, nn);
+    {
+        struct Item { int node; uint32_t skip; };
+        std::vector<Item> st; st.push_back({0, nn});
+        while (!st.empty()) {
+            Item it = st.back(); st.pop_back();
+            skip[it.node] = it.skip;
+            const BuildNode &b = bnodes[it.node];
+            if (b.left >= 0) { st.push_back({b.left, (uint32_t) b.right}); st.push_back({b.right, it.skip}); }
+        }
+    }
+    std::vector<DevTri> tris_sorted(nt);
+    for (uint32_t i = 0; i < nt; ++i) tris_sorted[i] = tris[btris[i].idx];
+    std::vector<uint32_t> orig_to_sorted(nt);
+    for (uint32_t i = 0; i < nt; ++i) orig_to_sorted[btris[i].idx] = i;
+    for (uint32_t i = 0; i < nn; ++i) {
+        const BuildNode &b = bnodes[i];
+        for (int a = 0; a < 3; ++a) { nodes[i].lo[a] = b.lo[a] - pad; nodes[i].hi[a] = b.hi[a] + pad; }
+        nodes[i].skip = skip[i];
+        nodes[i].leaf = b.count ? ((b.first << 4) | b.count) : 0u;
+    }
+
+    // ---- shapes (+ sampling tables for meshes)
+    std::vector<DevShape> shapes(ns);
+    std::vector<unsigned char> sampling;  // per mesh shape: pmf[n] | cdf[n] | sorted tri index[n]
+    for (uint32_t s = 0; s < ns; ++s) {
+        const TrShapeDesc &sd = desc->shapes[s];
+        DevShape &d = shapes[s];
+        memset(&d, 0, sizeof(d));
+        d.type = sd.type; d.bsdf = sd.bsdf; d.emitter = sd.emitter; d.flags = sd.flags;
+        d.tri_begin_orig = sd.tri_begin; d.tri_count = sd.tri_count;
+        d.interior_medium = sd.interior_medium; d.exterior_medium = sd.exterior_medium;
+        memcpy(d.to_world, sd.to_world, sizeof(d.to_world));
+        double acc = 0.0;
+        std::vector<float> pmf(sd.tri_count), cdf(sd.tri_count);
+        for (uint32_t k = 0; k < sd.tri_count; ++k) {
+            float a = tri_area[sd.tri_begin + k];
+            acc += (double) a; pmf[k] = a; cdf[k] = (float) acc;
+        }
+        d.area_sum = (float) acc; d.area_norm = (float) (1.0 / acc);
+        if (!(acc > 0.0)) { err = "shape with zero surface area"; return false; }
+        if (sd.type == TR_SHAPE_RECTANGLE) {
+            H3 dpdu = hxf_vector(sd.to_world, h3(2.0f, 0.0f, 0.0f));
+            H3 dpdv = hxf_vector(sd.to_world, h3(0.0f, 2.0f, 0.0f));
+            H3 c = hcross(dpdu, dpdv);
+            d.inv_area = 1.0f / sqrtf(hdot(c, c));
+            const DevTri &t0 = tris[sd.tri_begin];
+            H3 n = h3(t0.n[0], t0.n[1], t0.n[2]);
+            float dd = hdot(n, dpdu);
+            H3 sv = h3(fmaf(-n.x, dd, dpdu.x), fmaf(-n.y, dd, dpdu.y), fmaf(-n.z, dd, dpdu.z));
+            float inv = 1.0f / sqrtf(hdot(sv, sv));
+            d.n[0] = n.x; d.n[1] = n.y; d.n[2] = n.z;
+            d.s[0] = sv.x * inv; d.s[1] = sv.y * inv; d.s[2] = sv.z * inv;
+            d.samp_off = 0;
+        } else {
+            d.inv_area = d.area_norm;
+            d.samp_off = (uint32_t) sampling.size();  // relative for now, fixed up below
+            size_t base = sampling.size();
+            sampling.resize(base + (size_t) sd.tri_count * 12);
+            memcpy(&sampling[base], pmf.data(), sd.tri_count * 4);
+            memcpy(&sampling[base + sd.tri_count * 4], cdf.data(), sd.tri_count * 4);
+            uint32_t *ti = (uint32_t *) &sampling[base + sd.tri_count * 8];
+            for (uint32_t k = 0; k < sd.tri_count; ++k) ti[k] = orig_to_sorted[sd.tri_begin + k];
+        }
+    }
+
+    std::vector<DevBsdf> bsdfs(desc->n_bsdfs);
+    for (uint32_t i = 0; i < desc->n_bsdfs; ++i) {
+        memset(&bsdfs[i], 0, sizeof(DevBsdf));
+        bsdfs[i].type = desc->bsdfs[i].type; bsdfs[i].flags = desc->bsdfs[i].flags;
+        if (bsdfs[i].type != TR_BSDF_DIFFUSE && bsdfs[i].type != TR_BSDF_NULL) { err = "unknown bsdf type"; return false; }
+        for (int c = 0; c < 3; ++c) bsdfs[i].r[c] = desc->bsdfs[i].reflectance[c];
+    }
+    std::vector<DevEmitter> emitters(std::max(1u, desc->n_emitters));
+    memset(emitters.data(), 0, emitters.size() * sizeof(DevEmitter));
+    uint32_t n_area = 0;
+    for (uint32_t i = 0; i < desc->n_emitters; ++i) {
+        const TrEmitterDesc &e = desc->emitters[i];
+        emitters[i].type = e.type; emitters[i].shape = e.shape; emitters[i].fov_x = e.fov_x;
+        for (int c = 0; c < 3; ++c) emitters[i].radiance[c] = e.radiance[c];
+        memcpy(emitters[i].to_world, e.to_world, sizeof(e.to_world));
+        if (e.type == TR_EMITTER_AREA) {
+            if (e.shape < 0 || (uint32_t) e.shape >= ns) { err = "area emitter without a valid shape"; return false; }
+            if (desc->shapes[e.shape].emitter != (int32_t) i) { err = "area emitter / shape cross reference mismatch"; return false; }
+            n_area++;
+        } else if (e.type != TR_EMITTER_PROJECTOR) { err = "unknown emitter type"; return false; }
+    }
+    std::vector<DevMedium> media(std::max(1u, desc->n_media));
+    memset(media.data(), 0, media.size() * sizeof(DevMedium));
+    for (uint32_t i = 0; i < desc->n_media; ++i) {
+        for (int c = 0; c < 3; ++c) { media[i].sigma_t[c] = desc->media[i].sigma_t[c]; media[i].albedo[c] = desc->media[i].albedo[c]; }
+        media[i].g = desc->media[i].g; media[i].scale = desc->media[i].scale;
+    }
+
+    // ---- blob
+    BlobHeader h; memset(&h, 0, sizeof(h));
+    h.n_tris = nt; h.n_nodes = nn; h.n_shapes = ns; h.n_bsdfs = desc->n_bsdfs; h.n_emitters = desc->n_emitters;
+    h.n_media = desc->n_media; h.n_area_emitters = n_area;
+    uint32_t off = sizeof(BlobHeader);
+    h.off_tris = off; off += nt * (uint32_t) sizeof(DevTri);
+    h.off_nodes = off; off += nn * (uint32_t) sizeof(DevNode);
+    h.off_shapes = off; off += ns * (uint32_t) sizeof(DevShape);
+    h.off_bsdfs = off; off += (uint32_t) (bsdfs.size() * sizeof(DevBsdf));
+    h.off_emitters = off; off += (uint32_t) (emitters.size() * sizeof(DevEmitter));
+    h.off_media = off; off += (uint32_t) (media.size() * sizeof(DevMedium));
+    h.off_sampling = off; off += align16((uint32_t) sampling.size());
+    h.total_bytes = align16(off);
+    for (uint32_t s = 0; s < ns; ++s)
+        if (shapes[s].type != TR_SHAPE_RECTANGLE) shapes[s].samp_off += h.off_sampling;
+    out.blob.assign(h.total_bytes, 0);
+    memcpy(&out.blob[0], &h, sizeof(h));
+    memcpy(&out.blob[h.off_tris], tris_sorted.data(), nt * sizeof(DevTri));
+    memcpy(&out.blob[h.off_nodes], nodes.data(), nn * sizeof(DevNode));
+    memcpy(&out.blob[h.off_shapes], shapes.data(), ns * sizeof(DevShape));
+    memcpy(&out.blob[h.off_bsdfs], bsdfs.data(), bsdfs.size() * sizeof(DevBsdf));
+    memcpy(&out.blob[h.off_emitters], emitters.data(), emitters.size() * sizeof(DevEmitter));
+    memcpy(&out.blob[h.off_media], media.data(), media.size() * sizeof(DevMedium));
+    if (!sampling.empty()) memcpy(&out.blob[h.off_sampling], sampling.data(), sampling.size());
+    out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn; out.n_tris = nt;
+    return true;
+}
+
+}  // namespace tr
+
+extern "C" {
+
+int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene) {
+    if (!out_scene) return tr::fail(TR_ERR_INVALID_ARGUMENT, "out_scene is NULL");
+    *out_scene = nullptr;
+    int rc = tr_device_check();
+    if (rc != TR_OK) return rc;
+    TrScene *s = new (std::nothrow) TrScene();
+    if (!s) return tr::fail(TR_ERR_OUT_OF_MEMORY, "host allocation failed");
+    std::string err;
+    if (!tr::pack_scene(desc, s->impl, err)) { delete s; return tr::fail(TR_ERR_INVALID_ARGUMENT, err); }
+    TR_CUDA_OR(cudaGetDevice(&s->impl.device), { delete s; });
+    TR_CUDA_OR(cudaMalloc(&s->impl.d_blob, s->impl.blob.size()), { delete s; });
+    TR_CUDA_OR(cudaMemcpy(s->impl.d_blob, s->impl.blob.data(), s->impl.blob.size(), cudaMemcpyHostToDevice),
+               { cudaFree(s->impl.d_blob); delete s; });
+    TR_CUDA_OR(cudaMalloc(&s->impl.d_scratch, 4096), { cudaFree(s->impl.d_blob); delete s; });
+    *out_scene = s;
+    return TR_OK;
+}
+
+void tr_scene_destroy(TrScene *scene) {
+    if (!scene) return;
+    if (scene->impl.d_blob) cudaFree(scene->impl.d_blob);
+    if (scene->impl.d_pixels) cudaFree(scene->impl.d_pixels);
+    if (scene->impl.d_scratch) cudaFree(scene->impl.d_scratch);
+    delete scene;
+}
+
+int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_tris) {
+    if (!scene) return tr::fail(TR_ERR_INVALID_ARGUMENT, "scene is NULL");
+    if (blob_bytes) *blob_bytes = scene->impl.blob.size();
+    if (n_nodes) *n_nodes = scene->impl.n_nodes;
+    if (n_tris) *n_tris = scene->impl.n_tris;
+    return TR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Packed device scene ("blob") shared by tr_scene.cu (host packer / BVH builder) and the kernels.
+//
+// The whole scene is ONE contiguous, 16-byte aligned byte blob so that a CTA can stage it into
+// shared memory with a single TMA bulk copy (cp.async.bulk, SASS UBLKCP) when it is small enough
+// (Cornell box: ~7 KB), and read it through the read-only path from global memory otherwise.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mitransient_b200.h"
+
+namespace tr {
+
+struct BlobHeader {            // 64 bytes
+    uint32_t total_bytes;      // multiple of 16
+    uint32_t n_tris, n_nodes, n_shapes, n_bsdfs, n_emitters, n_media;
+    uint32_t off_tris, off_nodes, off_shapes, off_bsdfs, off_emitters, off_media, off_sampling;
+    uint32_t n_area_emitters;  // emitters usable by Scene::sample_emitter_direction
+    uint32_t _pad;
+};
+static_assert(sizeof(BlobHeader) == 64, "BlobHeader must be 64 bytes");
+
+struct DevTri {                // 64 bytes = 4 x float4, BVH leaf order
+    float p0[3]; uint32_t shape;
+    float e1[3]; uint32_t prim;   // original triangle index (tie-break key)
+    float e2[3]; uint32_t _r0;
+    float n[3];  uint32_t _r1;
+};
+static_assert(sizeof(DevTri) == 64, "DevTri must be 64 bytes");
+
+struct DevNode {               // 32 bytes = 2 x float4, pre-order threaded BVH
+    float lo[3]; uint32_t skip;   // node to visit when this one is missed / finished
+    float hi[3]; uint32_t leaf;   // 0 for inner nodes, else (first_tri << 4) | count
+};
+static_assert(sizeof(DevNode) == 32, "DevNode must be 32 bytes");
+
+struct DevShape {              // 128 bytes
+    int32_t type, bsdf, emitter, flags;
+    uint32_t tri_begin_orig, tri_count, samp_off /* byte offset in blob of pmf|cdf|tri index arrays */, _r0;
+    float inv_area, area_sum, area_norm, _r1;
+    float to_world[12];
+    float n[3]; int32_t interior_medium;
+    float s[3]; int32_t exterior_medium;
+};
+static_assert(sizeof(DevShape) == 128, "DevShape must be 128 bytes");
+
+struct DevBsdf { int32_t type, flags; float r[3]; float _pad[3]; };          // 32 bytes
+static_assert(sizeof(DevBsdf) == 32, "DevBsdf must be 32 bytes");
+
+struct DevEmitter {            // 96 bytes
+    int32_t type, shape; float radiance[3]; float fov_x;   // 24
+    float to_world[12];                                    // 72
+    float _pad[6];
+};
+static_assert(sizeof(DevEmitter) == 96, "DevEmitter must be 96 bytes");
+
+struct DevMedium { float sigma_t[3]; float g; float albedo[3]; float scale; };  // 32 bytes
+
+// Host-side packed scene + device copies; this is what the opaque TrScene points to.
+struct SceneImpl {
+    std::vector<unsigned char> blob;     // host copy
+    void *d_blob = nullptr;              // device copy
+    TrSensorDesc sensor;
+    TrFilmDesc film;
+    uint32_t n_nodes = 0, n_tris = 0;
+    int device = -1;
+    // cached owned-pixel list (tile sharding), rebuilt when (tile, rank, world) changes
+    void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;
+    // scratch for counters / work queue
+    void *d_scratch = nullptr;
+};
+
+bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err);
+
+}  // namespace tr
+
+struct TrScene { tr::SceneImpl impl; };

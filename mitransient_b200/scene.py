@@ -1,0 +1,421 @@
+"""Scene ingestion: Mitsuba-style scene dictionaries -> the flat ``TrSceneDesc`` the C ABI takes.
+
+The reference hands ``mi.load_dict(mitr.cornell_box())`` to ``mi.render`` (mitransient/utils.py:78-220,
+examples/transient/0-render_cbox_diffuse.ipynb cell 3).  Mitsuba is not available here, so this module
+understands the subset of the dictionary format the hot path's configurations use and flattens it into
+triangles + shape/bsdf/emitter tables + one sensor/film (include/mitransient_b200.h).
+
+Supported plugin types
+  shapes     rectangle, cube, obj (v / f records; ``l`` records are ignored)
+  bsdfs      diffuse, twosided(diffuse), null, ref
+  emitters   area (nested in a shape), projector (top level; transient_nlos_path's laser)
+  sensors    perspective, nlos_capture_meter (nested in the relay-wall shape)
+  films      transient_hdr_film          samplers   independent          rfilter   box
+  integrators transient_path, transient_nlos_path, transient_prbvolpath
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from . import _abi
+from .transforms import ScalarTransform4f, parse_fov, perspective_projection
+
+
+def ScalarColor3d(*v):
+    """``mi.ScalarColor3d`` stand-in: just a float64 triple."""
+    if len(v) == 1:
+        v = v[0]
+    a = np.asarray(v, dtype=np.float64).reshape(-1)
+    if a.size == 1:
+        a = np.repeat(a, 3)
+    return a
+
+
+ScalarColor3f = ScalarColor3d
+
+
+class Properties(dict):
+    """Dictionary with the ``mi.Properties.get(name, default)`` access pattern the plugins use."""
+
+    def keys_unqueried(self):
+        return [k for k in self.keys() if k not in getattr(self, "_queried", set())]
+
+    def get(self, key, default=None):
+        if not hasattr(self, "_queried"):
+            self._queried = set()
+        self._queried.add(key)
+        return super().get(key, default)
+
+
+# ------------------------------------------------------------------------------------ geometry
+_CUBE_FACES = (  # (origin corner, u edge, v edge) with u x v pointing outwards; corners in [-1,1]^3
+    ((1, -1, -1), (0, 2, 0), (0, 0, 2)),    # +x
+    ((-1, -1, -1), (0, 0, 2), (0, 2, 0)),   # -x
+    ((-1, 1, -1), (0, 0, 2), (2, 0, 0)),    # +y
+    ((-1, -1, -1), (2, 0, 0), (0, 0, 2)),   # -y
+    ((-1, -1, 1), (2, 0, 0), (0, 2, 0)),    # +z
+    ((-1, -1, -1), (0, 2, 0), (2, 0, 0)),   # -z
+)
+
+
+def _cube_triangles() -> np.ndarray:
+    tris = []
+    for o, u, v in _CUBE_FACES:
+        o, u, v = np.array(o, float), np.array(u, float), np.array(v, float)
+        tris.append([o, o + u, o + u + v])
+        tris.append([o, o + u + v, o + v])
+    return np.array(tris, dtype=np.float64)
+
+
+def _rectangle_triangles() -> np.ndarray:
+    v0, v1, v2, v3 = (np.array(p, float) for p in ((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)))
+    return np.array([[v0, v1, v2], [v0, v2, v3]], dtype=np.float64)
+
+
+def load_obj(path: str) -> np.ndarray:
+    """Wavefront OBJ -> float64 [n_tris, 3, 3].  Polygons are fan-triangulated; ``l``, ``vt``, ``vn``, ``o``,
+    ``s`` ... records are ignored (face normals are used, as Mitsuba does for meshes without ``vn``)."""
+    verts: List[List[float]] = []
+    tris: List[List[int]] = []
+    with open(path, "r") as f:
+        for line in f:
+            if line.startswith("v "):
+                p = line.split()
+                verts.append([float(p[1]), float(p[2]), float(p[3])])
+            elif line.startswith("f "):
+                idx = []
+                for tok in line.split()[1:]:
+                    i = int(tok.split("/")[0])
+                    idx.append(i - 1 if i > 0 else len(verts) + i)
+                for k in range(1, len(idx) - 1):
+                    tris.append([idx[0], idx[k], idx[k + 1]])
+    v = np.asarray(verts, dtype=np.float64)
+    t = np.asarray(tris, dtype=np.int64)
+    if t.size == 0:
+        return np.zeros((0, 3, 3))
+    return v[t]
+
+
+def _apply(to_world: ScalarTransform4f, tris: np.ndarray, flip: bool) -> np.ndarray:
+    m = to_world.matrix
+    out = tris @ m[:3, :3].T + m[:3, 3]
+    if (np.linalg.det(m[:3, :3]) < 0) != bool(flip):
+        out = out[:, ::-1, :]  # keep the geometric normal equal to the transformed (inverse-transpose) normal
+    return np.ascontiguousarray(out)
+
+
+def _rgb(v, default=None) -> np.ndarray:
+    if v is None:
+        v = default
+    if isinstance(v, dict):
+        t = v.get("type", "rgb")
+        if t not in ("rgb", "uniform", "spectrum"):
+            raise ValueError(f"unsupported spectrum/texture type {t!r} (only constant rgb values)")
+        v = v.get("value")
+    return ScalarColor3d(v)
+
+
+def _to_transform(v) -> ScalarTransform4f:
+    if v is None:
+        return ScalarTransform4f()
+    if isinstance(v, ScalarTransform4f):
+        return v
+    return ScalarTransform4f(np.asarray(v, dtype=np.float64))
+
+
+# ------------------------------------------------------------------------------------ host-side scene objects
+class Shape:
+    def __init__(self, name, kind, tris, to_world, bsdf_index, flip=False):
+        self.name, self.kind, self.tris, self.to_world = name, kind, tris, to_world
+        self.bsdf_index = bsdf_index
+        self.emitter_index = -1
+        self.is_sensor = False
+        self.interior_medium = -1
+        self.exterior_medium = -1
+        self.flip = flip
+
+    def surface_area(self) -> float:
+        e1 = self.tris[:, 1] - self.tris[:, 0]
+        e2 = self.tris[:, 2] - self.tris[:, 0]
+        return float(0.5 * np.linalg.norm(np.cross(e1, e2), axis=1).sum())
+
+
+class Scene:
+    """What ``mi.load_dict`` returns for our purposes: the parsed plugins + the flattened description."""
+
+    def __init__(self):
+        self.shapes_: List[Shape] = []
+        self.bsdfs_: List[Dict[str, Any]] = []
+        self.emitters_: List[Dict[str, Any]] = []
+        self.media_: List[Dict[str, Any]] = []
+        self.sensors_: List[Any] = []
+        self.integrator_ = None
+        self._handle = None          # device scene (mitransient_b200._lib.DeviceScene)
+        self._handle_key = None
+        self._keepalive: List[Any] = []
+
+    # Mitsuba-like accessors used by the reference's integrators
+    def sensors(self):
+        return self.sensors_
+
+    def integrator(self):
+        return self.integrator_
+
+    def shapes(self):
+        return self.shapes_
+
+    def emitters(self):
+        return self.emitters_
+
+    # -- flattening ----------------------------------------------------------------------
+    def describe(self, sensor) -> _abi.TrSceneDesc:
+        """Build the ctypes ``TrSceneDesc`` for ``sensor`` (arrays are kept alive on ``self``)."""
+        film = sensor.film()
+        tris = [s.tris for s in self.shapes_]
+        tri_verts = np.ascontiguousarray(np.concatenate(tris, axis=0) if tris else np.zeros((0, 3, 3)),
+                                         dtype=np.float32)
+        shapes = (_abi.TrShapeDesc * max(1, len(self.shapes_)))()
+        begin = 0
+        for i, s in enumerate(self.shapes_):
+            d = shapes[i]
+            d.type = _abi.TR_SHAPE_RECTANGLE if s.kind == "rectangle" else _abi.TR_SHAPE_MESH
+            d.bsdf, d.emitter = s.bsdf_index, s.emitter_index
+            d.flags = _abi.TR_SHAPE_FLAG_SENSOR if s.is_sensor else 0
+            d.interior_medium, d.exterior_medium = s.interior_medium, s.exterior_medium
+            d.tri_begin, d.tri_count = begin, len(s.tris)
+            d.to_world[:] = s.to_world.affine3x4().reshape(-1).tolist()
+            begin += len(s.tris)
+        bsdfs = (_abi.TrBsdfDesc * max(1, len(self.bsdfs_)))()
+        for i, b in enumerate(self.bsdfs_):
+            bsdfs[i].type, bsdfs[i].flags = b["type"], b["flags"]
+            bsdfs[i].reflectance[:] = [float(x) for x in b["reflectance"]]
+        emitters = (_abi.TrEmitterDesc * max(1, len(self.emitters_)))()
+        for i, e in enumerate(self.emitters_):
+            emitters[i].type, emitters[i].shape = e["type"], e["shape"]
+            emitters[i].radiance[:] = [float(x) for x in e["radiance"]]
+            emitters[i].fov_x = float(e.get("fov_x", 0.0))
+            emitters[i].to_world[:] = e.get("to_world", ScalarTransform4f()).affine3x4().reshape(-1).tolist()
+        media = (_abi.TrMediumDesc * max(1, len(self.media_)))()
+        for i, m in enumerate(self.media_):
+            media[i].sigma_t[:] = [float(x) for x in m["sigma_t"]]
+            media[i].albedo[:] = [float(x) for x in m["albedo"]]
+            media[i].g, media[i].scale = float(m["g"]), float(m.get("scale", 1.0))
+
+        desc = _abi.TrSceneDesc()
+        desc.abi_version = _abi.TR_ABI_VERSION
+        desc.n_tris = tri_verts.shape[0]
+        desc.tri_verts = tri_verts.ctypes.data_as(C.POINTER(C.c_float))
+        desc.n_shapes, desc.shapes = len(self.shapes_), shapes
+        desc.n_bsdfs, desc.bsdfs = len(self.bsdfs_), bsdfs
+        desc.n_emitters, desc.emitters = len(self.emitters_), emitters
+        desc.n_media, desc.media = len(self.media_), media
+        desc.sensor = sensor.describe(self)
+        desc.film = film.describe()
+        self._keepalive = [tri_verts, shapes, bsdfs, emitters, media]
+        return desc
+
+    def description_key(self, sensor):
+        f = sensor.film()
+        return (id(sensor), f.size(), f.temporal_bins, float(f.start_opl), float(f.bin_width_opl),
+                sensor.state_key())
+
+    def __repr__(self):
+        return (f"Scene[shapes={len(self.shapes_)}, triangles={sum(len(s.tris) for s in self.shapes_)}, "
+                f"bsdfs={len(self.bsdfs_)}, emitters={len(self.emitters_)}, sensors={len(self.sensors_)}]")
+
+
+class PerspectiveSensor:
+    """Mitsuba ``perspective`` sensor (pinhole): parameters only; rays are generated on the device."""
+
+    def __init__(self, props: Properties, film, sampler):
+        self.to_world = _to_transform(props.get("to_world"))
+        self.fov = float(props.get("fov", 45.0))
+        self.fov_axis = props.get("fov_axis", "x")
+        self.near_clip = float(props.get("near_clip", 1e-2))
+        self.far_clip = float(props.get("far_clip", 1e4))
+        props.get("focus_distance")
+        self._film, self._sampler = film, sampler
+        self.medium = -1
+
+    def film(self):
+        return self._film
+
+    def sampler(self):
+        return self._sampler
+
+    def world_transform(self):
+        return self.to_world
+
+    def state_key(self):
+        return ("perspective", self.to_world.matrix.tobytes(), self.fov, self.fov_axis, self.near_clip,
+                self.far_clip)
+
+    def describe(self, scene) -> _abi.TrSensorDesc:
+        w, h = self._film.size()
+        d = _abi.TrSensorDesc()
+        d.type, d.shape = _abi.TR_SENSOR_PERSPECTIVE, -1
+        d.to_world[:] = self.to_world.affine3x4().reshape(-1).tolist()
+        fov_x = parse_fov(self.fov, self.fov_axis, w / h)
+        cam_to_sample = perspective_projection((w, h), self._film.crop_size(), self._film.crop_offset(), fov_x,
+                                               self.near_clip, self.far_clip)
+        d.sample_to_camera[:] = cam_to_sample.inverse().matrix.astype(np.float32).reshape(-1).tolist()
+        d.near_clip, d.far_clip = self.near_clip, self.far_clip
+        d.medium = self.medium
+        return d
+
+
+class IndependentSampler:
+    def __init__(self, props: Properties):
+        self._sample_count = int(props.get("sample_count", 4))
+        self.base_seed = int(props.get("seed", 0))
+
+    def sample_count(self):
+        return self._sample_count
+
+    def set_sample_count(self, spp):
+        self._sample_count = int(spp)
+
+    def clone(self):
+        c = IndependentSampler(Properties())
+        c._sample_count, c.base_seed = self._sample_count, self.base_seed
+        return c
+
+
+# ------------------------------------------------------------------------------------ load_dict
+def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
+    """``mi.load_dict`` for the supported subset.  Returns a :class:`Scene` for ``type == 'scene'`` and the
+    plugin object for a film / integrator / sensor dictionary."""
+    from . import plugins  # late import: plugins registers the mitransient classes
+
+    t = d.get("type")
+    if t != "scene":
+        return plugins.instantiate(d)
+
+    scene = Scene()
+    named_bsdf: Dict[str, int] = {}
+    named_medium: Dict[str, int] = {}
+
+    def add_bsdf(spec) -> int:
+        if isinstance(spec, dict) and spec.get("type") == "ref":
+            rid = spec["id"]
+            if rid not in named_bsdf:
+                if rid in d and isinstance(d[rid], dict):
+                    named_bsdf[rid] = add_bsdf(d[rid])
+                else:
+                    raise ValueError(f"unresolved bsdf reference {rid!r}")
+            return named_bsdf[rid]
+        flags = 0
+        bt = spec.get("type")
+        if bt == "twosided":
+            inner = spec.get("bsdf") or next(v for k, v in spec.items() if isinstance(v, dict))
+            if isinstance(inner, dict) and inner.get("type") == "ref":
+                inner = d[inner["id"]]
+            flags |= _abi.TR_BSDF_FLAG_TWOSIDED
+            spec, bt = inner, inner.get("type")
+        if bt == "diffuse":
+            entry = {"type": _abi.TR_BSDF_DIFFUSE, "flags": flags, "reflectance": _rgb(spec.get("reflectance"), 0.5)}
+        elif bt == "null":
+            entry = {"type": _abi.TR_BSDF_NULL, "flags": flags, "reflectance": ScalarColor3d(0.0)}
+        else:
+            raise ValueError(f"unsupported bsdf type {bt!r} (supported: diffuse, twosided(diffuse), null)")
+        scene.bsdfs_.append(entry)
+        return len(scene.bsdfs_) - 1
+
+    def add_medium(spec) -> int:
+        if isinstance(spec, dict) and spec.get("type") == "ref":
+            rid = spec["id"]
+            if rid not in named_medium:
+                named_medium[rid] = add_medium(d[rid])
+            return named_medium[rid]
+        if spec.get("type") != "homogeneous":
+            raise ValueError(f"unsupported medium type {spec.get('type')!r} (supported: homogeneous)")
+        scale = float(spec.get("scale", 1.0))
+        phase = spec.get("phase", {"type": "isotropic"})
+        g = float(phase.get("g", 0.0)) if phase.get("type") == "hg" else 0.0
+        if phase.get("type") not in ("hg", "isotropic"):
+            raise ValueError(f"unsupported phase function {phase.get('type')!r}")
+        scene.media_.append({"sigma_t": _rgb(spec.get("sigma_t"), 1.0), "albedo": _rgb(spec.get("albedo"), 0.75),
+                             "g": g, "scale": scale})
+        return len(scene.media_) - 1
+
+    default_bsdf = None
+    # first pass: named bsdfs / media keep their dictionary order (ids are the dict keys)
+    for key, val in d.items():
+        if isinstance(val, dict) and val.get("type") in ("diffuse", "twosided", "null"):
+            named_bsdf[key] = add_bsdf(val)
+        elif isinstance(val, dict) and val.get("type") == "homogeneous":
+            named_medium[key] = add_medium(val)
+
+    for key, val in d.items():
+        if not isinstance(val, dict):
+            continue
+        t = val.get("type")
+        if t in ("rectangle", "cube", "obj"):
+            to_world = _to_transform(val.get("to_world"))
+            flip = bool(val.get("flip_normals", False))
+            if t == "rectangle":
+                base = _rectangle_triangles()
+            elif t == "cube":
+                base = _cube_triangles()
+            else:
+                fn = val["filename"]
+                if not os.path.isabs(fn) and base_dir:
+                    fn = os.path.join(base_dir, fn)
+                base = load_obj(fn)
+            bspec = val.get("bsdf")
+            if bspec is None:
+                bspec = next((v for k, v in val.items() if isinstance(v, dict) and
+                              v.get("type") in ("diffuse", "twosided", "null", "ref") and k not in
+                              ("interior", "exterior")), None)
+            if bspec is None:
+                if default_bsdf is None:
+                    default_bsdf = add_bsdf({"type": "diffuse"})
+                bidx = default_bsdf
+            else:
+                bidx = add_bsdf(bspec)
+            shape = Shape(key, t, _apply(to_world, base, flip), to_world, bidx, flip)
+            if "interior" in val:
+                shape.interior_medium = add_medium(val["interior"])
+            if "exterior" in val:
+                shape.exterior_medium = add_medium(val["exterior"])
+            scene.shapes_.append(shape)
+            sidx = len(scene.shapes_) - 1
+            em = val.get("emitter")
+            if em is not None:
+                if em.get("type") != "area":
+                    raise ValueError(f"unsupported shape emitter {em.get('type')!r} (supported: area)")
+                scene.emitters_.append({"type": _abi.TR_EMITTER_AREA, "shape": sidx,
+                                        "radiance": _rgb(em.get("radiance"), 1.0)})
+                shape.emitter_index = len(scene.emitters_) - 1
+            se = val.get("sensor")
+            if se is not None:
+                if se.get("type") != "nlos_capture_meter":
+                    raise ValueError("only nlos_capture_meter sensors can be attached to a shape")
+                shape.is_sensor = True
+                sensor = plugins.instantiate(se)
+                sensor.set_shape(sidx, shape)
+                scene.sensors_.append(sensor)
+        elif t == "projector":
+            to_world = _to_transform(val.get("to_world"))
+            scene.emitters_.append({"type": _abi.TR_EMITTER_PROJECTOR, "shape": -1,
+                                    "radiance": _rgb(val.get("irradiance"), 1.0),
+                                    "fov_x": float(val.get("fov", 45.0)), "to_world": to_world})
+        elif t in ("perspective",):
+            film = plugins.instantiate(val["film"]) if "film" in val else plugins.instantiate(
+                {"type": "transient_hdr_film"})
+            sampler = IndependentSampler(Properties(val.get("sampler", {})))
+            sensor = PerspectiveSensor(Properties(val), film, sampler)
+            if "medium" in val:
+                sensor.medium = add_medium(val["medium"])
+            scene.sensors_.append(sensor)
+        elif t in plugins.INTEGRATORS:
+            scene.integrator_ = plugins.instantiate(val)
+        elif t in ("diffuse", "twosided", "null", "homogeneous", "scene"):
+            pass
+        else:
+            raise ValueError(f"load_dict(): unsupported plugin type {t!r} for key {key!r}")
+    return scene

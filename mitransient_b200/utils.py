@@ -1,0 +1,78 @@
+"""Benchmark scene + small helpers (counterpart of mitransient/utils.py).
+
+``cornell_box()`` returns the same scene *description* as the reference's (mitransient/utils.py:78-220:
+pinhole at z = 3.9, five one-sided diffuse walls, two cubes, a 0.46 x 0.38 area light under the
+ceiling, transient film 256 x 256 x 300 bins over OPL [3.5, 9.5)) so that configurations are expressed
+identically; it is consumed by :func:`mitransient_b200.load_dict`.
+"""
+from __future__ import annotations
+
+from .scene import ScalarColor3d
+from .transforms import ScalarTransform4f as T
+
+speed_of_light = 299792458.0
+"""Speed of light in meters/second"""
+
+_CBOX_ALBEDO = {
+    "white": (0.885809, 0.698859, 0.666422),
+    "green": (0.105421, 0.37798, 0.076425),
+    "red": (0.570068, 0.0430135, 0.0443706),
+}
+_CBOX_LIGHT_RADIANCE = (18.387, 13.9873, 6.75357)
+
+
+def _wall(to_world, bsdf):
+    return {"type": "rectangle", "to_world": to_world, "bsdf": {"type": "ref", "id": bsdf}}
+
+
+def _box(to_world):
+    return {"type": "cube", "to_world": to_world, "bsdf": {"type": "ref", "id": "white"}}
+
+
+def cornell_box():
+    """Dictionary describing the Cornell-box scene for transient rendering."""
+    scene = {
+        "type": "scene",
+        "integrator": {"type": "transient_path", "camera_unwarp": False, "max_depth": 8,
+                       "temporal_filter": "box", "gaussian_stddev": 2.0},
+        "sensor": {
+            "type": "perspective", "fov_axis": "smaller", "near_clip": 0.001, "far_clip": 100.0,
+            "focus_distance": 1000, "fov": 39.3077,
+            "to_world": T().look_at(origin=[0, 0, 3.90], target=[0, 0, 0], up=[0, 1, 0]),
+            "sampler": {"type": "independent", "sample_count": 256},
+            "film": {"type": "transient_hdr_film", "width": 256, "height": 256, "rfilter": {"type": "box"},
+                     "temporal_bins": 300, "start_opl": 3.5, "bin_width_opl": 0.02},
+        },
+    }
+    for name, rgb in _CBOX_ALBEDO.items():
+        scene[name] = {"type": "diffuse", "reflectance": {"type": "rgb", "value": ScalarColor3d(*rgb)}}
+    light = _wall(T().translate([0.0, 0.99, 0.01]).rotate([1, 0, 0], 90).scale([0.23, 0.19, 0.19]), "white")
+    light["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": ScalarColor3d(*_CBOX_LIGHT_RADIANCE)}}
+    scene["light"] = light
+    scene["floor"] = _wall(T().translate([0.0, -1.0, 0.0]).rotate([1, 0, 0], -90), "white")
+    scene["ceiling"] = _wall(T().translate([0.0, 1.0, 0.0]).rotate([1, 0, 0], 90), "white")
+    scene["back"] = _wall(T().translate([0.0, 0.0, -1.0]), "white")
+    scene["green-wall"] = _wall(T().translate([1.0, 0.0, 0.0]).rotate([0, 1, 0], -90), "green")
+    scene["red-wall"] = _wall(T().translate([-1.0, 0.0, 0.0]).rotate([0, 1, 0], 90), "red")
+    scene["small-box"] = _box(T().translate([0.335, -0.7, 0.38]).rotate([0, 1, 0], -17).scale(0.3))
+    scene["large-box"] = _box(T().translate([-0.33, -0.4, -0.28]).rotate([0, 1, 0], 18.25).scale([0.3, 0.61, 0.3]))
+    return scene
+
+
+def cornell_box_config(width, height, temporal_bins, spp, max_depth=8, window=(3.5, 9.5)):
+    """The Cornell box with the film overrides BASELINE.md section 4 uses (same OPL window [3.5, 9.5))."""
+    d = cornell_box()
+    film = d["sensor"]["film"]
+    film["width"], film["height"], film["temporal_bins"] = int(width), int(height), int(temporal_bins)
+    film["start_opl"] = float(window[0])
+    film["bin_width_opl"] = (float(window[1]) - float(window[0])) / int(temporal_bins)
+    d["sensor"]["sampler"]["sample_count"] = int(spp)
+    d["integrator"]["max_depth"] = int(max_depth)
+    return d
+
+
+def indent(obj, amount=2):
+    lines = str(obj).splitlines(keepends=True)
+    if len(lines) <= 1:
+        return "".join(lines)
+    return "".join(line + " " * amount for line in lines)

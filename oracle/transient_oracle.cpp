@@ -1,0 +1,700 @@
+// ===========================================================================================
+//  oracle/transient_oracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+//  A scalar, line-by-line restatement of mitransient's transient path-tracing hot path.  It
+//  is the checker the CUDA kernels are compared against; it is NOT part of the product:
+//  only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+//  may load it.  Nothing under mitransient_b200/ links, imports or calls it.
+//
+//  PARITY STATUS: *unpinned*.  The reference's arithmetic for this path lives in two
+//  third-party, un-vendored dependencies -- mitsuba (pinned >=3.6.0,<3.9.0,
+//  mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the notebooks) -- which are
+//  not installable here (no wheel, no network), and the reference's only test is stale and
+//  shape-only (tests/integration/test_nlos.py:81-118).  So there are no golden vectors to pin
+//  against; the oracle restates the published Mitsuba 3 algorithms and is validated by the
+//  analytic known-answer tests in tests/test_oracle_kat.py.
+//
+//  What is restated (file:line relative to the mitransient tree):
+//    render driver        mitransient/integrators/common.py:122-213   -> oracle_render
+//    sample_rays          mitsuba ADIntegrator.sample_rays [upstream] -> sample_camera_ray
+//    TransientPath.sample mitransient/integrators/transientpath.py:109-326 -> trace_path
+//    add_transient_f      mitransient/integrators/common.py:411-422   -> Film::add_transient
+//    add_transient_data   mitransient/films/transient_hdr_film.py:250-276
+//    put_/accum           mitransient/render/transient_image_block.py:130-149, 79-81
+//    develop              mitransient/films/transient_hdr_film.py:220-248 -> oracle_develop
+//  Upstream (Mitsuba 3 / Dr.Jit) pieces restated from their published source: PCG32 + TEA
+//  seeding of the `independent` sampler, perspective sensor, `diffuse` BSDF, `area` emitter,
+//  Scene::sample_emitter_direction / pdf_emitter_direction, rectangle / mesh position
+//  sampling, SurfaceInteraction::spawn_ray(_to), mis_weight (power heuristic).
+//
+//  ARITHMETIC CONTRACT (shared with the CUDA kernels by *specification*, not by code): all
+//  maths is IEEE fp32, no implicit contraction (-ffp-contract=off); fused multiply-adds are
+//  written out as fmaf() exactly where the contract says so:
+//      dot(a,b)   = fmaf(a.z,b.z, fmaf(a.y,b.y, a.x*b.x))
+//      cross(a,b) = ( fmaf(a.y,b.z, -(a.z*b.y)), fmaf(a.z,b.x, -(a.x*b.z)), fmaf(a.x,b.y, -(a.y*b.x)) )
+//      v / s      = v * (1.0f / s)            normalize(v) = v * (1.0f / sqrtf(dot(v,v)))
+//  sqrt and division are correctly rounded; sin/cos use the Cephes polynomial below.  With
+//  the same PCG32 streams the GPU then walks bit-identical paths; only the order of the fp32
+//  additions into a film bin differs.
+// ===========================================================================================
+#include "../include/mitransient_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------ vectors
+struct V3 { float x, y, z; };
+inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline float dot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+inline V3 cross(V3 a, V3 b) {
+    return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))};
+}
+inline V3 fma3(V3 a, float s, V3 c) { return {fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z)}; }
+inline V3 normalize(V3 a) { float inv = 1.0f / sqrtf(dot(a, a)); return a * inv; }
+inline float max3(V3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+inline float mulsign(float a, float b) {  // a with the sign of b multiplied in (drjit mulsign)
+    uint32_t ua, ub; memcpy(&ua, &a, 4); memcpy(&ub, &b, 4);
+    ua ^= (ub & 0x80000000u); float r; memcpy(&r, &ua, 4); return r;
+}
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kInvPi = 0.31830988618379067154f;
+constexpr float kRayEpsilon = 8.940696716308594e-05f;     // Mitsuba math::RayEpsilon<float> = 2^-24 * 1500
+constexpr float kShadowEpsilon = 8.940696716308594e-04f;  // RayEpsilon * 10
+constexpr float kInf = std::numeric_limits<float>::infinity();
+
+// Cephes single-precision sincos (the polynomial Dr.Jit uses), valid for |x| < 8192.
+inline void sincos_cephes(float x, float *s_out, float *c_out) {
+    float xa = fabsf(x);
+    int j = (int) (xa * 1.2732395447351628f);  // 4/pi
+    j = (j + 1) & ~1;
+    float y = (float) j;
+    // Cody-Waite range reduction
+    float z = fmaf(y, -0.78515625f, xa);
+    z = fmaf(y, -2.4187564849853515625e-4f, z);
+    z = fmaf(y, -3.77489497744594108e-8f, z);
+    float z2 = z * z;
+    float sp = fmaf(z2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, z2, -1.6666654611e-1f);
+    sp = fmaf(sp * z2, z, z);
+    float cp = fmaf(z2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, z2, 4.166664568298827e-2f);
+    cp = fmaf(cp * z2, z2, fmaf(z2, -0.5f, 1.0f));
+    bool swap = (j & 2) != 0;
+    float s = swap ? cp : sp, c = swap ? sp : cp;
+    if (j & 4) s = -s;
+    if ((j + 2) & 4) c = -c;
+    if (x < 0.0f) s = -s;
+    *s_out = s; *c_out = c;
+}
+
+// ------------------------------------------------------------------------------ sampler
+// Mitsuba `independent` sampler: one PCG32 per lane, seeded through the Tiny Encryption
+// Algorithm from (seed, lane index) [upstream: Sampler::seed, sample_tea_32, drjit PCG32].
+struct Pcg32 {
+    uint64_t state, inc;
+    void seed(uint64_t initstate, uint64_t initseq) {
+        state = 0; inc = (initseq << 1) | 1u; next_u32(); state += initstate; next_u32();
+    }
+    uint32_t next_u32() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t) (old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    float next_1d() {
+        uint32_t u = (next_u32() >> 9) | 0x3f800000u; float f; memcpy(&f, &u, 4); return f - 1.0f;
+    }
+};
+inline void sample_tea_32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) {
+    uint32_t sum = 0;
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    *o0 = v0; *o1 = v1;
+}
+
+// ------------------------------------------------------------------------------ scene
+struct Tri { V3 p0, e1, e2, n, s, t; uint32_t shape; };
+struct Shape {
+    TrShapeDesc d;
+    float inv_area;            // 1 / surface area
+    V3 n;                      // rectangle: frame normal
+    std::vector<float> pmf;    // mesh: triangle areas (unnormalised pmf)
+    std::vector<float> cdf;    // mesh: running triangle-area sums (float, accumulated in double)
+    float area_sum, area_norm; // DiscreteDistribution m_sum / m_normalization
+};
+struct Scene {
+    std::vector<Tri> tris;
+    std::vector<Shape> shapes;
+    std::vector<TrBsdfDesc> bsdfs;
+    std::vector<TrEmitterDesc> emitters;
+    TrSensorDesc sensor;
+    TrFilmDesc film;
+};
+
+// Duff et al. branchless orthonormal basis (Mitsuba coordinate_system).
+inline void coordinate_system(V3 n, V3 *s, V3 *t) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -(1.0f / (sign + n.z));
+    float b = n.x * n.y * a;
+    *s = v3(mulsign(n.x * n.x * a, n.z) + 1.0f, mulsign(b, n.z), mulsign(-n.x, n.z));
+    *t = v3(b, fmaf(n.y, n.y * a, sign), -n.y);
+}
+
+inline V3 xf_point(const float *m, float x, float y, float z) {  // row-major 3x4 affine
+    return v3(fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3]))),
+              fmaf(m[4], x, fmaf(m[5], y, fmaf(m[6], z, m[7]))),
+              fmaf(m[8], x, fmaf(m[9], y, fmaf(m[10], z, m[11]))));
+}
+inline V3 xf_vector(const float *m, V3 v) {
+    return v3(fmaf(m[0], v.x, fmaf(m[1], v.y, m[2] * v.z)),
+              fmaf(m[4], v.x, fmaf(m[5], v.y, m[6] * v.z)),
+              fmaf(m[8], v.x, fmaf(m[9], v.y, m[10] * v.z)));
+}
+
+bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
+    if (!desc || desc->abi_version != TR_ABI_VERSION) { err = "bad scene descriptor / ABI version"; return false; }
+    sc.sensor = desc->sensor; sc.film = desc->film;
+    sc.bsdfs.assign(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
+    sc.emitters.assign(desc->emitters, desc->emitters + desc->n_emitters);
+    sc.tris.resize(desc->n_tris);
+    sc.shapes.resize(desc->n_shapes);
+    for (uint32_t si = 0; si < desc->n_shapes; ++si) {
+        Shape &sh = sc.shapes[si];
+        sh.d = desc->shapes[si];
+        if (sh.d.tri_begin + sh.d.tri_count > desc->n_tris) { err = "shape triangle range out of bounds"; return false; }
+        double area_acc = 0.0;
+        sh.cdf.clear(); sh.pmf.clear();
+        for (uint32_t k = 0; k < sh.d.tri_count; ++k) {
+            uint32_t ti = sh.d.tri_begin + k;
+            const float *v = desc->tri_verts + 9 * (size_t) ti;
+            Tri &t = sc.tris[ti];
+            t.p0 = v3(v[0], v[1], v[2]);
+            t.e1 = v3(v[3], v[4], v[5]) - t.p0;
+            t.e2 = v3(v[6], v[7], v[8]) - t.p0;
+            V3 c = cross(t.e1, t.e2);
+            float len = sqrtf(dot(c, c));
+            t.n = c * (1.0f / len);
+            t.shape = si;
+            float area = 0.5f * len;
+            area_acc += (double) area;
+            sh.pmf.push_back(area);
+            sh.cdf.push_back((float) area_acc);
+            if (sh.d.type == TR_SHAPE_RECTANGLE) {
+                // Rectangle: tangent from dp_du = to_world * (2,0,0), Gram-Schmidt against n
+                // (Mitsuba SurfaceInteraction::initialize_sh_frame).
+                V3 dpdu = xf_vector(sh.d.to_world, v3(2.0f, 0.0f, 0.0f));
+                float d = dot(t.n, dpdu);
+                t.s = normalize(v3(fmaf(-t.n.x, d, dpdu.x), fmaf(-t.n.y, d, dpdu.y), fmaf(-t.n.z, d, dpdu.z)));
+            } else {
+                V3 tt; coordinate_system(t.n, &t.s, &tt);
+            }
+            t.t = cross(t.n, t.s);
+        }
+        sh.area_sum = (float) area_acc;
+        sh.area_norm = (float) (1.0 / area_acc);
+        if (sh.d.type == TR_SHAPE_RECTANGLE) {
+            V3 dpdu = xf_vector(sh.d.to_world, v3(2.0f, 0.0f, 0.0f));
+            V3 dpdv = xf_vector(sh.d.to_world, v3(0.0f, 2.0f, 0.0f));
+            V3 c = cross(dpdu, dpdv);
+            sh.inv_area = 1.0f / sqrtf(dot(c, c));
+            sh.n = sh.d.tri_count ? sc.tris[sh.d.tri_begin].n : v3(0, 0, 1);
+        } else {
+            sh.inv_area = sh.area_norm;
+            sh.n = v3(0, 0, 0);
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------ rays
+struct Ray { V3 o, d; float maxt; };
+struct Hit {
+    bool valid; float t; V3 p, n, s, tt; uint32_t shape, prim;
+};
+
+// Moeller-Trumbore as in Mitsuba's Mesh::ray_intersect_triangle.
+inline bool tri_test(const Tri &tr, const Ray &r, float *t_out, float *u_out, float *v_out) {
+    V3 pvec = cross(r.d, tr.e2);
+    float det = dot(tr.e1, pvec);
+    float inv_det = 1.0f / det;
+    V3 tvec = r.o - tr.p0;
+    float u = dot(tvec, pvec) * inv_det;
+    V3 qvec = cross(tvec, tr.e1);
+    float v = dot(r.d, qvec) * inv_det;
+    float t = dot(tr.e2, qvec) * inv_det;
+    bool ok = (u >= 0.0f) && (v >= 0.0f) && (u + v <= 1.0f) && (t >= 0.0f) && (t <= r.maxt);
+    *t_out = t; *u_out = u; *v_out = v;
+    return ok;
+}
+
+Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: closest hit, brute force
+    Hit h; h.valid = false; h.t = kInf; h.prim = 0xffffffffu; h.shape = 0;
+    float bu = 0, bv = 0;
+    for (uint32_t i = 0; i < sc.tris.size(); ++i) {
+        float t, u, v;
+        if (tri_test(sc.tris[i], r, &t, &u, &v) && t < h.t) {  // ascending index + strict '<' == lowest index wins ties
+            h.valid = true; h.t = t; h.prim = i; bu = u; bv = v;
+        }
+    }
+    if (h.valid) {
+        const Tri &tr = sc.tris[h.prim];
+        h.p = fma3(tr.e2, bv, fma3(tr.e1, bu, tr.p0));
+        h.n = tr.n; h.s = tr.s; h.tt = tr.t; h.shape = tr.shape;
+    } else {
+        h.p = v3(0, 0, 0); h.n = v3(0, 0, 0); h.s = h.tt = v3(0, 0, 0);
+    }
+    return h;
+}
+
+bool ray_test(const Scene &sc, const Ray &r) {  // scene.ray_test: any hit
+    for (uint32_t i = 0; i < sc.tris.size(); ++i) {
+        float t, u, v;
+        if (tri_test(sc.tris[i], r, &t, &u, &v)) return true;
+    }
+    return false;
+}
+
+// SurfaceInteraction::offset_p / spawn_ray / spawn_ray_to [upstream interaction.h]
+inline V3 offset_p(V3 p, V3 n, V3 dir) {
+    float mag = (1.0f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z))) * kRayEpsilon;
+    mag = mulsign(mag, dot(n, dir));
+    return fma3(n, mag, p);
+}
+inline Ray spawn_ray(V3 p, V3 n, V3 d) { return Ray{offset_p(p, n, d), d, std::numeric_limits<float>::max()}; }
+inline Ray spawn_ray_to(V3 p, V3 n, V3 target) {
+    V3 o = offset_p(p, n, target - p);
+    V3 d = target - o;
+    float dist = sqrtf(dot(d, d));
+    d = d * (1.0f / dist);
+    return Ray{o, d, dist * (1.0f - kShadowEpsilon)};
+}
+
+// ------------------------------------------------------------------------------ warps
+inline void square_to_uniform_disk_concentric(float sx, float sy, float *ox, float *oy) {
+    float x = fmaf(2.0f, sx, -1.0f), y = fmaf(2.0f, sy, -1.0f);
+    bool is_zero = (x == 0.0f) && (y == 0.0f);
+    bool quadrant_1_or_3 = fabsf(x) < fabsf(y);
+    float r = quadrant_1_or_3 ? y : x, rp = quadrant_1_or_3 ? x : y;
+    float phi = 0.25f * kPi * rp * (1.0f / r);
+    if (quadrant_1_or_3) phi = 0.5f * kPi - phi;
+    if (is_zero) phi = 0.0f;
+    float s, c; sincos_cephes(phi, &s, &c);
+    *ox = r * c; *oy = r * s;
+}
+inline V3 square_to_cosine_hemisphere(float sx, float sy) {
+    float px, py; square_to_uniform_disk_concentric(sx, sy, &px, &py);
+    float z2 = 1.0f - fmaf(py, py, px * px);
+    float z = sqrtf(fmaxf(z2, 0.0f));  // safe_sqrt
+    return v3(px, py, z);
+}
+
+inline float mis_weight(float pdf_a, float pdf_b) {  // mitsuba.ad.integrators.common.mis_weight
+    float a2 = pdf_a * pdf_a, b2 = pdf_b * pdf_b;
+    float w = a2 / (a2 + b2);
+    return std::isfinite(w) ? w : 0.0f;
+}
+
+// ------------------------------------------------------------------------------ emitters
+struct DirectionSample { V3 p, n, d; float dist, pdf; bool delta; };
+
+// Shape::sample_position for the two shape kinds [upstream rectangle.cpp / mesh.cpp]
+inline void shape_sample_position(const Scene &sc, const Shape &sh, float u0, float u1, V3 *p, V3 *n, float *pdf) {
+    if (sh.d.type == TR_SHAPE_RECTANGLE) {
+        *p = xf_point(sh.d.to_world, fmaf(u0, 2.0f, -1.0f), fmaf(u1, 2.0f, -1.0f), 0.0f);
+        *n = sh.n; *pdf = sh.inv_area;
+    } else {
+        // Mesh::sample_position: face by area CDF reusing sample.y, uniform triangle warp
+        float value = u1 * sh.area_sum;
+        uint32_t lo = 0, hi = sh.d.tri_count ? sh.d.tri_count - 1 : 0;  // first idx with cdf[idx] >= value
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sh.cdf[mid] < value) lo = mid + 1; else hi = mid; }
+        uint32_t idx = lo;
+        float cdf_prev = idx ? sh.cdf[idx - 1] : 0.0f;
+        float pmf = sh.pmf[idx] * sh.area_norm;
+        float u1r = (u1 - cdf_prev * sh.area_norm) / pmf;
+        const Tri &tr = sc.tris[sh.d.tri_begin + idx];
+        float t = sqrtf(fmaxf(1.0f - u0, 0.0f));
+        float b0 = 1.0f - t, b1 = t * u1r;
+        *p = fma3(tr.e1, b0, fma3(tr.e2, b1, tr.p0));
+        *n = tr.n; *pdf = sh.area_norm;
+    }
+}
+
+// Emitter(area)::sample_direction -> Shape::sample_direction (area pdf -> solid angle).
+// Returns the (unoccluded) weight radiance / pdf, or 0.
+inline V3 area_sample_direction(const Scene &sc, const TrEmitterDesc &em, V3 ref_p, float u0, float u1, DirectionSample *ds) {
+    const Shape &sh = sc.shapes[em.shape];
+    shape_sample_position(sc, sh, u0, u1, &ds->p, &ds->n, &ds->pdf);
+    V3 d = ds->p - ref_p;
+    float dist2 = dot(d, d);
+    ds->dist = sqrtf(dist2);
+    ds->d = d * (1.0f / ds->dist);
+    float dp = fabsf(dot(ds->d, ds->n));
+    float x = dist2 / dp;
+    ds->pdf *= std::isfinite(x) ? x : 0.0f;
+    ds->delta = false;
+    bool active = (dot(ds->d, ds->n) < 0.0f) && (ds->pdf != 0.0f);
+    if (!active) return v3(0, 0, 0);
+    float inv = 1.0f / ds->pdf;
+    return v3(em.radiance[0], em.radiance[1], em.radiance[2]) * inv;
+}
+
+// Scene::pdf_emitter_direction for an area emitter hit by BSDF sampling.
+inline float area_pdf_direction(const Scene &sc, const TrEmitterDesc &em, V3 d, V3 n_light, float dist) {
+    float dp = dot(d, n_light);
+    if (!(dp < 0.0f)) return 0.0f;
+    const Shape &sh = sc.shapes[em.shape];
+    float adp = fabsf(dp);
+    float pdf = sh.inv_area * (adp != 0.0f ? (dist * dist) / adp : 0.0f);
+    return pdf;
+}
+
+// ------------------------------------------------------------------------------ film
+struct Film {
+    const TrFilmDesc &fd; float *data; int C;
+    TrCounters *cnt; std::vector<TrDeposit> *log;
+    // add_transient_f + add_transient_data + put_ (box filter path)
+    inline void add_transient(float px, float py, V3 spec, float distance, float sample_scale, float ray_weight) {
+        V3 value = (spec * sample_scale) * ray_weight;
+        if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) return;  // x + 0 == x: skipping is exact
+        cnt->deposits++;
+        if (log) log->push_back(TrDeposit{px, py, distance, value.x, value.y, value.z});
+        float pos_distance = (distance - fd.start_opl) / fd.bin_width_opl;
+        bool mask = (pos_distance >= 0.0f) && (pos_distance < (float) fd.temporal_bins);
+        if (!mask) return;
+        uint32_t x = (uint32_t) floorf(px), y = (uint32_t) floorf(py), z = (uint32_t) floorf(pos_distance);
+        if (!(x < fd.width && y < fd.height && z < fd.temporal_bins)) return;
+        uint64_t pix = (uint64_t) y * fd.width + x;
+        uint64_t index = (pix * fd.temporal_bins + z) * (uint64_t) C;
+        data[index + 0] += value.x; data[index + 1] += value.y; data[index + 2] += value.z;
+        // channel 3 (W) receives alpha = 0.0 in the reference (transient_image_block.py:99,148): no-op
+        cnt->deposits_in_range++;
+        cnt->bin_checksum += pix * fd.temporal_bins + z;
+    }
+};
+
+// ------------------------------------------------------------------------------ sensor
+inline Ray sample_camera_ray(const Scene &sc, uint32_t px, uint32_t py, float jx, float jy) {
+    // ADIntegrator.sample_rays + perspective.sample_ray [upstream]
+    const TrSensorDesc &se = sc.sensor;
+    float fx = (float) px + jx, fy = (float) py + jy;
+    float sx = fx * (1.0f / (float) sc.film.width), sy = fy * (1.0f / (float) sc.film.height);
+    const float *m = se.sample_to_camera;
+    float cx = fmaf(m[0], sx, fmaf(m[1], sy, m[3]));
+    float cy = fmaf(m[4], sx, fmaf(m[5], sy, m[7]));
+    float cz = fmaf(m[8], sx, fmaf(m[9], sy, m[11]));
+    float cw = fmaf(m[12], sx, fmaf(m[13], sy, m[15]));
+    float iw = 1.0f / cw;
+    V3 d = normalize(v3(cx * iw, cy * iw, cz * iw));
+    V3 dw = xf_vector(se.to_world, d);
+    float inv_z = 1.0f / d.z;
+    float near_t = se.near_clip * inv_z, far_t = se.far_clip * inv_z;
+    V3 o = v3(se.to_world[3], se.to_world[7], se.to_world[11]);
+    o = fma3(dw, near_t, o);
+    return Ray{o, dw, far_t - near_t};
+}
+
+// ------------------------------------------------------------------------------ transient_path
+// mitransient/integrators/transientpath.py:109-326 (primal branch).  Returns L.
+V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
+                        float px, float py, float sample_scale, float ray_weight, Film &film) {
+    const bool camera_unwarp = (rp.flags & TR_FLAG_CAMERA_UNWARP) != 0;
+    const bool discard_direct_light = (rp.flags & TR_FLAG_DISCARD_DIRECT_LIGHT) != 0;
+    const uint32_t n_em = (uint32_t) sc.emitters.size();
+
+    uint32_t depth = 0;                       // :119
+    V3 L = v3(0, 0, 0);                       // :120
+    V3 beta = v3(1, 1, 1);                    // utils.py:12 (unpolarized beta_init)
+    float eta = 1.0f;                         // :125
+    bool active = true;                       // :126
+    float distance = 0.0f;                    // :127
+    V3 prev_p = v3(0, 0, 0);                  // prev_si = zeros  :130
+    float prev_bsdf_pdf = 1.0f;               // :131
+    bool prev_bsdf_delta = true;              // :132
+
+    if (camera_unwarp) {                      // :134-139
+        Hit h0 = ray_intersect(sc, ray);
+        if (h0.valid) distance = -h0.t;
+    }
+
+    for (uint32_t it = 0; active && it < rp.max_depth; ++it) {   // :141-143 (max_iterations = max_depth)
+        film.cnt->vertices++;
+        bool active_next = active;
+        Hit si = ray_intersect(sc, ray);                          // :150-152
+        distance += si.t * eta;                                   // :155 (inf on a miss)
+
+        // ---------------- direct emission :159-181
+        V3 Le = v3(0, 0, 0);
+        if (si.valid) {
+            const Shape &sh = sc.shapes[si.shape];
+            if (sh.d.emitter >= 0) {
+                const TrEmitterDesc &em = sc.emitters[sh.d.emitter];
+                V3 rel = si.p - prev_p;                           // DirectionSample3f(scene, si, prev_si)
+                float dist = sqrtf(dot(rel, rel));
+                V3 dsd = rel * (1.0f / dist);
+                float em_pdf = 0.0f;
+                if (!prev_bsdf_delta) {
+                    em_pdf = area_pdf_direction(sc, em, dsd, si.n, dist);
+                    if (n_em > 1) em_pdf *= 1.0f / (float) n_em;  // Scene::pdf_emitter
+                }
+                float mis = mis_weight(prev_bsdf_pdf, em_pdf);    // :169-172
+                float cos_i = -dot(ray.d, si.n);                  // Frame3f::cos_theta(si.wi)
+                if (cos_i > 0.0f && !discard_direct_light)        // area.eval: front side only  :175-177
+                    Le = (beta * mis) * v3(em.radiance[0], em.radiance[1], em.radiance[2]);
+            }
+        }
+        film.add_transient(px, py, Le, distance, sample_scale, ray_weight);   // :180-181
+
+        // ---------------- emitter sampling :186-219
+        active_next = active_next && (depth + 1 < rp.max_depth) && si.valid;  // :186
+        const TrBsdfDesc *bsdf = si.valid ? &sc.bsdfs[sc.shapes[si.shape].d.bsdf] : nullptr;
+        bool smooth = bsdf && bsdf->type == TR_BSDF_DIFFUSE;
+        bool active_em = active_next && smooth;                               // :189-190
+
+        float u0 = rng.next_1d(), u1 = rng.next_1d();                         // sampler.next_2d()  :194
+        V3 Lr_dir = v3(0, 0, 0);
+        float cos_i = si.valid ? -dot(ray.d, si.n) : 0.0f;
+        bool back = cos_i < 0.0f;
+        bool twosided = bsdf && (bsdf->flags & TR_BSDF_FLAG_TWOSIDED);
+        float cos_i_eff = (twosided && back) ? -cos_i : cos_i;
+        float ds_dist = 0.0f;
+        if (active_em && n_em > 0) {
+            // Scene::sample_emitter_direction: uniform emitter choice with sample reuse
+            uint32_t ei = 0; float emw = 1.0f, pdf_pick = 1.0f;
+            if (n_em > 1) {
+                float fi = u0 * (float) n_em;
+                ei = (uint32_t) fi; if (ei > n_em - 1) ei = n_em - 1;
+                u0 = fi - (float) ei; emw = (float) n_em; pdf_pick = 1.0f / (float) n_em;
+            }
+            const TrEmitterDesc &em = sc.emitters[ei];
+            DirectionSample ds;
+            V3 em_weight = area_sample_direction(sc, em, si.p, u0, u1, &ds);
+            ds.pdf *= pdf_pick; em_weight = em_weight * emw;
+            ds_dist = ds.dist;
+            bool nz = (em_weight.x != 0.0f || em_weight.y != 0.0f || em_weight.z != 0.0f);
+            if (ds.pdf != 0.0f && nz) {
+                // bsdf.eval_pdf :208-211 (diffuse: R/pi * cos_o; pdf = cos_o/pi; needs both cosines > 0)
+                float cos_o = dot(ds.d, si.n);
+                float cos_o_eff = (twosided && back) ? -cos_o : cos_o;
+                if (cos_i_eff > 0.0f && cos_o_eff > 0.0f) {
+                    film.cnt->shadow_rays++;
+                    bool occluded = ray_test(sc, spawn_ray_to(si.p, si.n, ds.p));
+                    if (!occluded) {
+                        V3 R = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+                        V3 bsdf_val = (R * kInvPi) * cos_o_eff;
+                        float bsdf_pdf = kInvPi * cos_o_eff;
+                        float mis_em = ds.delta ? 1.0f : mis_weight(ds.pdf, bsdf_pdf);  // :212-213
+                        Lr_dir = ((beta * mis_em) * bsdf_val) * em_weight;              // :214
+                    }
+                }
+            }
+        }
+        film.add_transient(px, py, Lr_dir, distance + ds_dist * eta, sample_scale, ray_weight);  // :217-219
+
+        // ---------------- BSDF sampling :223-228
+        float s1 = rng.next_1d(); (void) s1;                       // sampler.next_1d() (unused by diffuse)
+        float s2x = rng.next_1d(), s2y = rng.next_1d();            // sampler.next_2d()
+        V3 bsdf_weight = v3(0, 0, 0); float bs_pdf = 0.0f; V3 wo_world = v3(0, 0, 0);
+        if (active_next && smooth) {
+            V3 wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs_pdf = kInvPi * wo.z;
+            if (cos_i_eff > 0.0f && bs_pdf > 0.0f)
+                bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            if (twosided && back) wo.z = -wo.z;
+            wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));   // si.to_world(wo)
+        }
+
+        // ---------------- update loop variables :231-241
+        L = L + Le + Lr_dir;                                       // :231
+        if (si.valid) ray = spawn_ray(si.p, si.n, wo_world);       // :232
+        // eta *= bs.eta (== 1 for diffuse)                        // :233
+        beta = beta * bsdf_weight;                                 // :234
+        prev_p = si.p; prev_bsdf_pdf = bs_pdf; prev_bsdf_delta = false;   // :238-241
+
+        // ---------------- stopping criterion :246-258
+        float beta_max = max3(beta);
+        active_next = active_next && (beta_max != 0.0f);           // :247
+        float rr_prob = fminf(beta_max * (eta * eta), 0.95f);      // :251
+        active_next = active_next && (rr_prob > 0.0f);             // :252
+        bool rr_active = depth >= rp.rr_depth;                     // :255
+        if (rr_active) { float r = (rr_prob > 0.0f) ? (1.0f / rr_prob) : 0.0f; beta = beta * r; }  // :256
+        bool rr_continue = rng.next_1d() < rr_prob;                // :257
+        active_next = active_next && (!rr_active || rr_continue);  // :258
+
+        if (si.valid) depth += 1;                                  // :319
+        active = active_next;                                      // :320
+    }
+    return L;
+}
+
+struct RenderJob {
+    const Scene *sc; const TrRenderParams *rp; float *film; float *steady; int C;
+    std::atomic<uint32_t> next_row{0};
+    std::mutex mu; TrCounters total{}; std::vector<TrDeposit> *log = nullptr; uint64_t log_cap = 0;
+};
+
+inline bool pixel_owned(const TrRenderParams &rp, uint32_t W, uint32_t x, uint32_t y) {
+    if (rp.world <= 1) return true;
+    uint32_t ts = rp.tile_size ? rp.tile_size : 32;
+    uint32_t tiles_x = (W + ts - 1) / ts;
+    uint32_t tile = (y / ts) * tiles_x + (x / ts);
+    return tile % rp.world == rp.rank;
+}
+
+void render_rows(RenderJob *job) {
+    const Scene &sc = *job->sc; const TrRenderParams &rp = *job->rp;
+    const uint32_t W = sc.film.width, H = sc.film.height;
+    TrCounters cnt{}; std::vector<TrDeposit> local_log;
+    Film film{sc.film, job->film, job->C, &cnt, job->log ? &local_log : nullptr};
+    const float sample_scale = 1.0f / (float) rp.total_spp;        // common.py:173
+    for (;;) {
+        uint32_t y = job->next_row.fetch_add(1);
+        if (y >= H) break;
+        for (uint32_t x = 0; x < W; ++x) {
+            if (!pixel_owned(rp, W, x, y)) continue;
+            V3 Lsum = v3(0, 0, 0);
+            for (uint32_t s = 0; s < rp.spp; ++s) {
+                // lane index of this sample in the reference's wavefront (idx // spp == pixel)
+                uint32_t idx = (y * W + x) * rp.spp + s;
+                uint32_t v0, v1; sample_tea_32(rp.seed, idx, &v0, &v1);
+                Pcg32 rng; rng.seed(v0, v1);
+                float jx = rng.next_1d(), jy = rng.next_1d();      // pos_f = pos + sampler.next_2d()
+                Ray ray = sample_camera_ray(sc, x, y, jx, jy);
+                cnt.paths++;
+                V3 L = trace_transient_path(sc, rp, rng, ray, (float) x, (float) y, sample_scale, 1.0f, film);
+                Lsum = Lsum + L;                                   // steady block.put (weight 1)  common.py:196-203
+            }
+            if (job->steady) {
+                float *o = job->steady + 3 * ((size_t) y * W + x);
+                float inv = 1.0f / (float) rp.total_spp;
+                if (rp.accumulate) { o[0] += Lsum.x * inv; o[1] += Lsum.y * inv; o[2] += Lsum.z * inv; }
+                else { o[0] = Lsum.x * inv; o[1] = Lsum.y * inv; o[2] = Lsum.z * inv; }
+            }
+        }
+    }
+    std::lock_guard<std::mutex> g(job->mu);
+    job->total.paths += cnt.paths; job->total.vertices += cnt.vertices; job->total.deposits += cnt.deposits;
+    job->total.deposits_in_range += cnt.deposits_in_range; job->total.bin_checksum += cnt.bin_checksum;
+    job->total.shadow_rays += cnt.shadow_rays;
+    if (job->log) for (auto &d : local_log) if (job->log->size() < job->log_cap) job->log->push_back(d);
+}
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char *oracle_last_error(void) { return g_err.c_str(); }
+
+// Render into host buffers.  film: float[H][W][T][film_channels] (NOT cleared unless
+// params->accumulate == 0, in which case owned pixels' columns are zeroed first).
+// deposit_log (optional): receives up to log_capacity deposits in thread-completion order;
+// *n_logged gets the count.  n_threads <= 0 -> hardware concurrency.
+int oracle_render(const TrSceneDesc *desc, const TrRenderParams *params, float *film, float *steady,
+                  TrCounters *counters, int n_threads, TrDeposit *deposit_log, uint64_t log_capacity,
+                  uint64_t *n_logged) {
+    Scene sc; std::string err;
+    if (!params || !film) { g_err = "null argument"; return TR_ERR_INVALID_ARGUMENT; }
+    if (!build_scene(desc, sc, err)) { g_err = err; return TR_ERR_INVALID_ARGUMENT; }
+    if (params->integrator != TR_INTEGRATOR_TRANSIENT_PATH) { g_err = "oracle: integrator not implemented"; return TR_ERR_UNSUPPORTED; }
+    if (sc.sensor.type != TR_SENSOR_PERSPECTIVE) { g_err = "oracle: transient_path needs a perspective sensor"; return TR_ERR_UNSUPPORTED; }
+    if (params->film_channels != 3 && params->film_channels != 4) { g_err = "film_channels must be 3 or 4"; return TR_ERR_INVALID_ARGUMENT; }
+    if (params->spp == 0 || params->total_spp == 0) { g_err = "spp must be > 0"; return TR_ERR_INVALID_ARGUMENT; }
+    const uint32_t W = sc.film.width, H = sc.film.height, T = sc.film.temporal_bins;
+    const int C = params->film_channels;
+    if (!params->accumulate) {
+        for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x)
+            if (pixel_owned(*params, W, x, y))
+                memset(film + ((size_t) y * W + x) * T * C, 0, sizeof(float) * (size_t) T * C);
+    }
+    RenderJob job; job.sc = &sc; job.rp = params; job.film = film; job.steady = steady; job.C = C;
+    std::vector<TrDeposit> log;
+    if (deposit_log && log_capacity) { job.log = &log; job.log_cap = log_capacity; log.reserve((size_t) std::min<uint64_t>(log_capacity, 1u << 22)); }
+    int nt = n_threads > 0 ? n_threads : (int) std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; ++i) th.emplace_back(render_rows, &job);
+    for (auto &t : th) t.join();
+    if (counters) *counters = job.total;
+    if (deposit_log) { memcpy(deposit_log, log.data(), log.size() * sizeof(TrDeposit)); if (n_logged) *n_logged = log.size(); }
+    return TR_OK;
+}
+
+// TransientImageBlock.put_ for a recorded deposit stream (sequential fp32 adds, stream order).
+int oracle_film_scatter_add(float *film, const TrFilmDesc *fd, int channels, const TrDeposit *dep, uint64_t n) {
+    if (!film || !fd || !dep) { g_err = "null argument"; return TR_ERR_INVALID_ARGUMENT; }
+    TrCounters cnt{};
+    Film f{*fd, film, channels, &cnt, nullptr};
+    for (uint64_t i = 0; i < n; ++i)
+        f.add_transient(dep[i].x, dep[i].y, v3(dep[i].r, dep[i].g, dep[i].b), dep[i].opl, 1.0f, 1.0f);
+    return TR_OK;
+}
+
+// TransientHDRFilm.develop_transient_ (transient_hdr_film.py:220-248)
+int oracle_film_develop(const float *raw, float *out, uint64_t n_bins, int in_channels) {
+    if (!raw || !out || in_channels < 2) { g_err = "bad argument"; return TR_ERR_INVALID_ARGUMENT; }
+    int oc = in_channels - 1;
+    for (uint64_t i = 0; i < n_bins; ++i) {
+        float w = raw[i * in_channels + in_channels - 1];
+        float div = (w == 0.0f) ? 1.0f : w;
+        for (int c = 0; c < oc; ++c) out[i * oc + c] = raw[i * in_channels + c] / div;
+    }
+    return TR_OK;
+}
+
+// ---- small probes used by the known-answer tests ---------------------------------------
+void oracle_pcg32(uint64_t initstate, uint64_t initseq, uint32_t *out, int n) {
+    Pcg32 r; r.seed(initstate, initseq);
+    for (int i = 0; i < n; ++i) out[i] = r.next_u32();
+}
+void oracle_tea32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) { sample_tea_32(v0, v1, o0, o1); }
+void oracle_sampler_floats(uint32_t seed, uint32_t lane, float *out, int n) {
+    uint32_t v0, v1; sample_tea_32(seed, lane, &v0, &v1);
+    Pcg32 r; r.seed(v0, v1);
+    for (int i = 0; i < n; ++i) out[i] = r.next_1d();
+}
+void oracle_sincos(float x, float *s, float *c) { sincos_cephes(x, s, c); }
+void oracle_cosine_hemisphere(float u0, float u1, float *xyz) {
+    V3 w = square_to_cosine_hemisphere(u0, u1); xyz[0] = w.x; xyz[1] = w.y; xyz[2] = w.z;
+}
+// camera ray for pixel (px,py) with jitter (jx,jy): o[3], d[3], maxt
+int oracle_camera_ray(const TrSceneDesc *desc, uint32_t px, uint32_t py, float jx, float jy, float *o, float *d, float *maxt) {
+    Scene sc; std::string err;
+    if (!build_scene(desc, sc, err)) { g_err = err; return TR_ERR_INVALID_ARGUMENT; }
+    Ray r = sample_camera_ray(sc, px, py, jx, jy);
+    o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; d[0] = r.d.x; d[1] = r.d.y; d[2] = r.d.z; *maxt = r.maxt;
+    return TR_OK;
+}
+// closest hit of an arbitrary ray: returns 1 on hit; out = t, p[3], n[3], shape, prim
+int oracle_ray_intersect(const TrSceneDesc *desc, const float *o, const float *d, float maxt, float *out_t, float *out_p,
+                         float *out_n, uint32_t *out_shape, uint32_t *out_prim) {
+    Scene sc; std::string err;
+    if (!build_scene(desc, sc, err)) { g_err = err; return TR_ERR_INVALID_ARGUMENT; }
+    Hit h = ray_intersect(sc, Ray{v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), maxt});
+    if (!h.valid) return 0;
+    *out_t = h.t; out_p[0] = h.p.x; out_p[1] = h.p.y; out_p[2] = h.p.z;
+    out_n[0] = h.n.x; out_n[1] = h.n.y; out_n[2] = h.n.z; *out_shape = h.shape; *out_prim = h.prim;
+    return 1;
+}
+
+}  // extern "C"
