@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 3
+#define TR_ABI_VERSION 4
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -41,23 +41,31 @@ typedef enum TrStatus {
 } TrStatus;
 
 /* ------------------------------------------------------------------ scene description
- * A flat restatement of what mi.load_dict()/XML hands to the integrator: geometry as a
- * triangle soup grouped into shapes, a BSDF table, an emitter table, one sensor and its
- * film (mitransient/utils.py:78-220 is the benchmark scene expressed this way).           */
+ * A flat restatement of what mi.load_dict()/XML hands to the integrator: geometry as a list
+ * of planar primitives (triangles and parallelograms) grouped into shapes, a BSDF table, an
+ * emitter table, one sensor and its film (mitransient/utils.py:78-220 is the benchmark
+ * scene expressed this way).
+ *
+ * A primitive is three vertices (p0, p1, p2).  TR_PRIM_TRIANGLE covers {p0 + u e1 + v e2 :
+ * u, v >= 0, u + v <= 1}; TR_PRIM_QUAD covers the parallelogram {u, v in [0, 1]} whose fourth
+ * corner is p1 + p2 - p0 (Mitsuba's analytic `rectangle`, a cube face, or two coplanar mesh
+ * triangles merged by the loader).  e1 = p1 - p0, e2 = p2 - p0; the geometric normal is
+ * normalize(cross(e1, e2)).                                                                */
+enum { TR_PRIM_TRIANGLE = 0, TR_PRIM_QUAD = 1 };
 
 enum { TR_SHAPE_MESH = 0, TR_SHAPE_RECTANGLE = 1 };
 enum { TR_SHAPE_FLAG_SENSOR = 1 };       /* the shape carrying the nlos_capture_meter      */
 
 typedef struct TrShapeDesc {
-    int32_t type;        /* TR_SHAPE_*: rectangle = Mitsuba `rectangle` (2 triangles for ray
-                            intersection, to_world-based uniform sampling); mesh = obj/ply/cube */
+    int32_t type;        /* TR_SHAPE_*: rectangle = Mitsuba `rectangle` (exactly one quad primitive,
+                            to_world-based uniform sampling); mesh = obj/ply/cube               */
     int32_t bsdf;        /* index into TrSceneDesc.bsdfs                                    */
     int32_t emitter;     /* index into TrSceneDesc.emitters (area light) or -1              */
     int32_t flags;       /* TR_SHAPE_FLAG_*                                                 */
     int32_t interior_medium; /* index into media or -1 (transient_prbvolpath)              */
     int32_t exterior_medium; /* index into media or -1                                     */
-    uint32_t tri_begin;  /* first triangle of this shape in tri_verts                       */
-    uint32_t tri_count;
+    uint32_t prim_begin; /* first primitive of this shape in prim_verts                     */
+    uint32_t prim_count;
     float to_world[12];  /* row-major 3x4 affine; meaningful for rectangles                 */
 } TrShapeDesc;
 
@@ -111,8 +119,9 @@ typedef struct TrFilmDesc {  /* mitransient/films/transient_hdr_film.py:114-121 
 
 typedef struct TrSceneDesc {
     uint32_t abi_version;          /* must be TR_ABI_VERSION                                */
-    uint32_t n_tris;
-    const float *tri_verts;        /* host, [n_tris][3 vertices][xyz], world space          */
+    uint32_t n_prims;
+    const float *prim_verts;       /* host, [n_prims][3 vertices][xyz], world space         */
+    const uint8_t *prim_types;     /* host, [n_prims] TR_PRIM_*                             */
     uint32_t n_shapes;
     const TrShapeDesc *shapes;     /* host                                                  */
     uint32_t n_bsdfs;
@@ -208,7 +217,7 @@ const char *tr_last_error(void);
 int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene);
 void tr_scene_destroy(TrScene *scene);
 /* bytes of the packed scene blob, number of BVH nodes (introspection for tests)           */
-int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_tris);
+int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_prims);
 
 /* THE hot path.  Replaces TransientADIntegrator.render's per-pass body
  * (mitransient/integrators/common.py:157-206): sample_rays -> TransientPath.sample

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 3
+TR_ABI_VERSION = 4
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -13,6 +13,7 @@ TR_ERR_NO_DEVICE = -4
 TR_ERR_OUT_OF_MEMORY = -5
 
 TR_SHAPE_MESH, TR_SHAPE_RECTANGLE = 0, 1
+TR_PRIM_TRIANGLE, TR_PRIM_QUAD = 0, 1
 TR_SHAPE_FLAG_SENSOR = 1
 TR_BSDF_DIFFUSE, TR_BSDF_NULL = 0, 1
 TR_BSDF_FLAG_TWOSIDED = 1
@@ -36,7 +37,7 @@ TR_CAPTURE_SINGLE, TR_CAPTURE_CONFOCAL, TR_CAPTURE_EXHAUSTIVE = 0, 1, 2
 class TrShapeDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("bsdf", C.c_int32), ("emitter", C.c_int32), ("flags", C.c_int32),
                 ("interior_medium", C.c_int32), ("exterior_medium", C.c_int32),
-                ("tri_begin", C.c_uint32), ("tri_count", C.c_uint32), ("to_world", C.c_float * 12)]
+                ("prim_begin", C.c_uint32), ("prim_count", C.c_uint32), ("to_world", C.c_float * 12)]
 
 
 class TrBsdfDesc(C.Structure):
@@ -64,7 +65,8 @@ class TrFilmDesc(C.Structure):
 
 
 class TrSceneDesc(C.Structure):
-    _fields_ = [("abi_version", C.c_uint32), ("n_tris", C.c_uint32), ("tri_verts", C.POINTER(C.c_float)),
+    _fields_ = [("abi_version", C.c_uint32), ("n_prims", C.c_uint32), ("prim_verts", C.POINTER(C.c_float)),
+                ("prim_types", C.POINTER(C.c_uint8)),
                 ("n_shapes", C.c_uint32), ("shapes", C.POINTER(TrShapeDesc)),
                 ("n_bsdfs", C.c_uint32), ("bsdfs", C.POINTER(TrBsdfDesc)),
                 ("n_emitters", C.c_uint32), ("emitters", C.POINTER(TrEmitterDesc)),

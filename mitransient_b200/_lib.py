@@ -89,7 +89,7 @@ class DeviceScene:
     def info(self):
         b, n, t = C.c_uint64(), C.c_uint32(), C.c_uint32()
         check(self._lib.tr_scene_info(self.handle, C.byref(b), C.byref(n), C.byref(t)))
-        return {"blob_bytes": b.value, "bvh_nodes": n.value, "triangles": t.value}
+        return {"blob_bytes": b.value, "bvh_nodes": n.value, "triangles": t.value, "primitives": t.value}
 
     def close(self):
         if getattr(self, "handle", None):

@@ -28,6 +28,7 @@ struct BuildTri { float lo[3], hi[3], c[3]; uint32_t idx; };
 struct BuildNode { float lo[3], hi[3]; int left = -1, right = -1; uint32_t first = 0, count = 0; };
 
 constexpr uint32_t kLeafSize = 2;
+constexpr uint32_t kBruteForceMaxPrims = 64;   // up to this many primitives: no BVH, lock-step loop in the kernel
 
 int build_rec(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32_t begin, uint32_t end) {
     BuildNode nd;
@@ -71,118 +72,137 @@ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     if (!desc) { err = "scene descriptor is NULL"; return false; }
     if (desc->abi_version != TR_ABI_VERSION) { err = "TrSceneDesc.abi_version does not match this library"; return false; }
-    if (desc->n_tris == 0 || !desc->tri_verts) { err = "scene has no triangles"; return false; }
+    if (desc->n_prims == 0 || !desc->prim_verts || !desc->prim_types) { err = "scene has no primitives"; return false; }
     if (desc->n_shapes == 0 || !desc->shapes) { err = "scene has no shapes"; return false; }
     if (desc->n_bsdfs == 0 || !desc->bsdfs) { err = "scene has no bsdfs"; return false; }
     if (desc->n_emitters && !desc->emitters) { err = "emitters pointer is NULL"; return false; }
-    if (desc->n_tris >= (1u << 28)) { err = "too many triangles"; return false; }
+    if (desc->n_prims >= (1u << 26)) { err = "too many primitives"; return false; }
     const TrFilmDesc &f = desc->film;
     if (f.width == 0 || f.height == 0 || f.temporal_bins == 0) { err = "film has a zero dimension"; return false; }
     if (!(f.bin_width_opl > 0.0f)) { err = "bin_width_opl must be > 0"; return false; }
     if ((uint64_t) f.width * f.height >= (1ull << 31)) { err = "film too large"; return false; }
 
-    const uint32_t nt = desc->n_tris, ns = desc->n_shapes;
-    std::vector<uint32_t> tri_shape(nt, 0xffffffffu);
+    const uint32_t np = desc->n_prims, ns = desc->n_shapes;
+    std::vector<uint32_t> prim_shape(np, 0xffffffffu);
     for (uint32_t s = 0; s < ns; ++s) {
         const TrShapeDesc &sd = desc->shapes[s];
-        if ((uint64_t) sd.tri_begin + sd.tri_count > nt) { err = "shape triangle range out of bounds"; return false; }
+        if ((uint64_t) sd.prim_begin + sd.prim_count > np) { err = "shape primitive range out of bounds"; return false; }
+        if (sd.prim_count == 0) { err = "shape without primitives"; return false; }
         if (sd.bsdf < 0 || (uint32_t) sd.bsdf >= desc->n_bsdfs) { err = "shape bsdf index out of range"; return false; }
         if (sd.emitter >= (int32_t) desc->n_emitters) { err = "shape emitter index out of range"; return false; }
-        if (sd.type == TR_SHAPE_RECTANGLE && sd.tri_count != 2) { err = "a rectangle must have exactly 2 triangles"; return false; }
-        for (uint32_t k = 0; k < sd.tri_count; ++k) tri_shape[sd.tri_begin + k] = s;
+        if (sd.type == TR_SHAPE_RECTANGLE && (sd.prim_count != 1 || desc->prim_types[sd.prim_begin] != TR_PRIM_QUAD)) {
+            err = "a rectangle shape must consist of exactly one quad primitive"; return false;
+        }
+        for (uint32_t k = 0; k < sd.prim_count; ++k) prim_shape[sd.prim_begin + k] = s;
     }
-    for (uint32_t i = 0; i < nt; ++i)
-        if (tri_shape[i] == 0xffffffffu) { err = "triangle not covered by any shape"; return false; }
+    for (uint32_t i = 0; i < np; ++i)
+        if (prim_shape[i] == 0xffffffffu) { err = "primitive not covered by any shape"; return false; }
 
-    // ---- per-triangle data (same arithmetic as the oracle's build_scene)
-    std::vector<DevTri> tris(nt);
-    std::vector<float> tri_area(nt);
-    std::vector<BuildTri> btris(nt);
+    // ---- per-primitive data (same arithmetic as the oracle's build_scene)
+    std::vector<DevPrim> prims(np);
+    std::vector<DevGeom> geom(np);
+    std::vector<BuildTri> bprims(np);
     float slo[3] = {INFINITY, INFINITY, INFINITY}, shi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t i = 0; i < nt; ++i) {
-        const float *v = desc->tri_verts + 9 * (size_t) i;
+    for (uint32_t i = 0; i < np; ++i) {
+        const float *v = desc->prim_verts + 9 * (size_t) i;
         for (int k = 0; k < 9; ++k) if (!std::isfinite(v[k])) { err = "non-finite vertex"; return false; }
+        if (desc->prim_types[i] > TR_PRIM_QUAD) { err = "unknown primitive type"; return false; }
+        const bool quad = desc->prim_types[i] == TR_PRIM_QUAD;
         H3 p0 = h3(v[0], v[1], v[2]);
         H3 e1 = h3(v[3], v[4], v[5]) - p0, e2 = h3(v[6], v[7], v[8]) - p0;
-        H3 c = hcross(e1, e2);
-        float len = sqrtf(hdot(c, c));
-        H3 n = c * (1.0f / len);
-        DevTri &t = tris[i];
-        t.p0[0] = p0.x; t.p0[1] = p0.y; t.p0[2] = p0.z; t.shape = tri_shape[i];
-        t.e1[0] = e1.x; t.e1[1] = e1.y; t.e1[2] = e1.z; t.prim = i;
-        t.e2[0] = e2.x; t.e2[1] = e2.y; t.e2[2] = e2.z; t._r0 = 0;
-        t.n[0] = n.x; t.n[1] = n.y; t.n[2] = n.z; t._r1 = 0;
-        tri_area[i] = 0.5f * len;
-        BuildTri &b = btris[i];
+        H3 N = hcross(e1, e2);
+        float nn = hdot(N, N);
+        if (!(nn > 0.0f)) { err = "degenerate primitive (zero area)"; return false; }
+        float inv_nn = 1.0f / nn;
+        float len = sqrtf(nn);
+        H3 n = N * (1.0f / len);
+        H3 a1 = hcross(e2, N) * inv_nn, a2 = hcross(N, e1) * inv_nn;
+        DevPrim &t = prims[i];
+        memset(&t, 0, sizeof(t));
+        t.N[0] = N.x; t.N[1] = N.y; t.N[2] = N.z; t.d0 = hdot(N, p0);
+        t.a1[0] = a1.x; t.a1[1] = a1.y; t.a1[2] = a1.z; t.c1 = hdot(p0, a1);
+        t.a2[0] = a2.x; t.a2[1] = a2.y; t.a2[2] = a2.z; t.c2 = hdot(p0, a2);
+        t.lim = quad ? 3.0f : 1.0f; t.shape = prim_shape[i]; t.prim = i;
+        t.area = quad ? len : 0.5f * len;
+        t.n[0] = n.x; t.n[1] = n.y; t.n[2] = n.z;
+        DevGeom &g = geom[i];
+        memset(&g, 0, sizeof(g));
+        g.p0[0] = p0.x; g.p0[1] = p0.y; g.p0[2] = p0.z; g.quad = quad ? 1u : 0u;
+        g.e1[0] = e1.x; g.e1[1] = e1.y; g.e1[2] = e1.z; g.area = t.area;
+        g.e2[0] = e2.x; g.e2[1] = e2.y; g.e2[2] = e2.z;
+        BuildTri &b = bprims[i];
         b.idx = i;
         for (int a = 0; a < 3; ++a) {
-            float x0 = v[a], x1 = v[3 + a], x2 = v[6 + a];
-            b.lo[a] = std::min(x0, std::min(x1, x2)); b.hi[a] = std::max(x0, std::max(x1, x2));
+            float x0 = v[a], x1 = v[3 + a], x2 = v[6 + a], x3 = quad ? (x1 + x2 - x0) : x0;
+            b.lo[a] = std::min(std::min(x0, x3), std::min(x1, x2)); b.hi[a] = std::max(std::max(x0, x3), std::max(x1, x2));
             b.c[a] = (b.lo[a] + b.hi[a]) * 0.5f;
             slo[a] = std::min(slo[a], b.lo[a]); shi[a] = std::max(shi[a], b.hi[a]);
         }
     }
 
-    // ---- BVH (median split, pre-order threaded).  Boxes are padded so that the fp32 slab test is
-    // conservative w.r.t. the triangle test: culling never changes the result.
-    std::vector<BuildNode> bnodes;
-    bnodes.reserve(2 * nt);
-    build_rec(bnodes, btris, 0, nt);
-    float extent = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
-    float absmax = 0.0f;
-    for (int a = 0; a < 3; ++a) absmax = std::max(absmax, std::max(std::fabs(slo[a]), std::fabs(shi[a])));
-    const float pad = 1e-4f * std::max(extent, absmax) + 1e-6f;
-    // pre-order layout == construction order of build_rec (node pushed before its children, left first)
-    const uint32_t nn = (uint32_t) bnodes.size();
-    std::vector<DevNode> nodes(nn);
-    // skip pointers: next node in pre-order that is not a descendant
-    std::vector<uint32_t> skip(nn, nn);
-    {
-        struct Item { int node; uint32_t skip; };
-        std::vector<Item> st; st.push_back({0, nn});
-        while (!st.empty()) {
-            Item it = st.back(); st.pop_back();
-            skip[it.node] = it.skip;
-            const BuildNode &b = bnodes[it.node];
-            if (b.left >= 0) { st.push_back({b.left, (uint32_t) b.right}); st.push_back({b.right, it.skip}); }
+    // ---- acceleration: none for small scenes (the kernel runs a lock-step loop over all primitives, original
+    // order); otherwise a median-split BVH, pre-order threaded.  Boxes are padded so that the fp32 slab test is
+    // conservative w.r.t. the primitive test: culling never changes the result.
+    std::vector<DevNode> nodes;
+    std::vector<DevPrim> prims_out;
+    uint32_t nn_nodes = 0;
+    if (np <= kBruteForceMaxPrims) {
+        prims_out = prims;
+    } else {
+        std::vector<BuildNode> bnodes;
+        bnodes.reserve(2 * np);
+        build_rec(bnodes, bprims, 0, np);
+        float extent = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
+        float absmax = 0.0f;
+        for (int a = 0; a < 3; ++a) absmax = std::max(absmax, std::max(std::fabs(slo[a]), std::fabs(shi[a])));
+        const float pad = 1e-4f * std::max(extent, absmax) + 1e-6f;
+        nn_nodes = (uint32_t) bnodes.size();
+        nodes.resize(nn_nodes);
+        std::vector<uint32_t> skip(nn_nodes, nn_nodes);   // next node in pre-order that is not a descendant
+        {
+            struct Item { int node; uint32_t skip; };
+            std::vector<Item> st; st.push_back({0, nn_nodes});
+            while (!st.empty()) {
+                Item it = st.back(); st.pop_back();
+                skip[it.node] = it.skip;
+                const BuildNode &b = bnodes[it.node];
+                if (b.left >= 0) { st.push_back({b.left, (uint32_t) b.right}); st.push_back({b.right, it.skip}); }
+            }
+        }
+        prims_out.resize(np);
+        for (uint32_t i = 0; i < np; ++i) prims_out[i] = prims[bprims[i].idx];
+        for (uint32_t i = 0; i < nn_nodes; ++i) {
+            const BuildNode &b = bnodes[i];
+            for (int a = 0; a < 3; ++a) { nodes[i].lo[a] = b.lo[a] - pad; nodes[i].hi[a] = b.hi[a] + pad; }
+            nodes[i].skip = skip[i];
+            nodes[i].leaf = b.count ? ((b.first << 4) | b.count) : 0u;
         }
     }
-    std::vector<DevTri> tris_sorted(nt);
-    for (uint32_t i = 0; i < nt; ++i) tris_sorted[i] = tris[btris[i].idx];
-    std::vector<uint32_t> orig_to_sorted(nt);
-    for (uint32_t i = 0; i < nt; ++i) orig_to_sorted[btris[i].idx] = i;
-    for (uint32_t i = 0; i < nn; ++i) {
-        const BuildNode &b = bnodes[i];
-        for (int a = 0; a < 3; ++a) { nodes[i].lo[a] = b.lo[a] - pad; nodes[i].hi[a] = b.hi[a] + pad; }
-        nodes[i].skip = skip[i];
-        nodes[i].leaf = b.count ? ((b.first << 4) | b.count) : 0u;
-    }
 
-    // ---- shapes (+ sampling tables for meshes)
+    // ---- shapes (+ area pmf / cdf tables for meshes)
     std::vector<DevShape> shapes(ns);
-    std::vector<unsigned char> sampling;  // per mesh shape: pmf[n] | cdf[n] | sorted tri index[n]
+    std::vector<unsigned char> sampling;  // per mesh shape: pmf[n] | cdf[n]
     for (uint32_t s = 0; s < ns; ++s) {
         const TrShapeDesc &sd = desc->shapes[s];
         DevShape &d = shapes[s];
         memset(&d, 0, sizeof(d));
         d.type = sd.type; d.bsdf = sd.bsdf; d.emitter = sd.emitter; d.flags = sd.flags;
-        d.tri_begin_orig = sd.tri_begin; d.tri_count = sd.tri_count;
+        d.prim_begin = sd.prim_begin; d.prim_count = sd.prim_count;
         d.interior_medium = sd.interior_medium; d.exterior_medium = sd.exterior_medium;
         memcpy(d.to_world, sd.to_world, sizeof(d.to_world));
         double acc = 0.0;
-        std::vector<float> pmf(sd.tri_count), cdf(sd.tri_count);
-        for (uint32_t k = 0; k < sd.tri_count; ++k) {
-            float a = tri_area[sd.tri_begin + k];
+        std::vector<float> pmf(sd.prim_count), cdf(sd.prim_count);
+        for (uint32_t k = 0; k < sd.prim_count; ++k) {
+            float a = prims[sd.prim_begin + k].area;
             acc += (double) a; pmf[k] = a; cdf[k] = (float) acc;
         }
         d.area_sum = (float) acc; d.area_norm = (float) (1.0 / acc);
-        if (!(acc > 0.0)) { err = "shape with zero surface area"; return false; }
         if (sd.type == TR_SHAPE_RECTANGLE) {
             H3 dpdu = hxf_vector(sd.to_world, h3(2.0f, 0.0f, 0.0f));
             H3 dpdv = hxf_vector(sd.to_world, h3(0.0f, 2.0f, 0.0f));
             H3 c = hcross(dpdu, dpdv);
             d.inv_area = 1.0f / sqrtf(hdot(c, c));
-            const DevTri &t0 = tris[sd.tri_begin];
+            const DevPrim &t0 = prims[sd.prim_begin];
             H3 n = h3(t0.n[0], t0.n[1], t0.n[2]);
             float dd = hdot(n, dpdu);
             H3 sv = h3(fmaf(-n.x, dd, dpdu.x), fmaf(-n.y, dd, dpdu.y), fmaf(-n.z, dd, dpdu.z));
@@ -194,11 +214,9 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             d.inv_area = d.area_norm;
             d.samp_off = (uint32_t) sampling.size();  // relative for now, fixed up below
             size_t base = sampling.size();
-            sampling.resize(base + (size_t) sd.tri_count * 12);
-            memcpy(&sampling[base], pmf.data(), sd.tri_count * 4);
-            memcpy(&sampling[base + sd.tri_count * 4], cdf.data(), sd.tri_count * 4);
-            uint32_t *ti = (uint32_t *) &sampling[base + sd.tri_count * 8];
-            for (uint32_t k = 0; k < sd.tri_count; ++k) ti[k] = orig_to_sorted[sd.tri_begin + k];
+            sampling.resize(base + (size_t) sd.prim_count * 8);
+            memcpy(&sampling[base], pmf.data(), sd.prim_count * 4);
+            memcpy(&sampling[base + sd.prim_count * 4], cdf.data(), sd.prim_count * 4);
         }
     }
 
@@ -232,29 +250,31 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
 
     // ---- blob
     BlobHeader h; memset(&h, 0, sizeof(h));
-    h.n_tris = nt; h.n_nodes = nn; h.n_shapes = ns; h.n_bsdfs = desc->n_bsdfs; h.n_emitters = desc->n_emitters;
+    h.n_prims = np; h.n_nodes = nn_nodes; h.n_shapes = ns; h.n_bsdfs = desc->n_bsdfs; h.n_emitters = desc->n_emitters;
     h.n_media = desc->n_media; h.n_area_emitters = n_area;
     uint32_t off = sizeof(BlobHeader);
-    h.off_tris = off; off += nt * (uint32_t) sizeof(DevTri);
-    h.off_nodes = off; off += nn * (uint32_t) sizeof(DevNode);
+    h.off_prims = off; off += np * (uint32_t) sizeof(DevPrim);
+    h.off_nodes = off; off += nn_nodes * (uint32_t) sizeof(DevNode);
     h.off_shapes = off; off += ns * (uint32_t) sizeof(DevShape);
     h.off_bsdfs = off; off += (uint32_t) (bsdfs.size() * sizeof(DevBsdf));
     h.off_emitters = off; off += (uint32_t) (emitters.size() * sizeof(DevEmitter));
     h.off_media = off; off += (uint32_t) (media.size() * sizeof(DevMedium));
+    h.off_geom = off; off += np * (uint32_t) sizeof(DevGeom);
     h.off_sampling = off; off += align16((uint32_t) sampling.size());
     h.total_bytes = align16(off);
     for (uint32_t s = 0; s < ns; ++s)
         if (shapes[s].type != TR_SHAPE_RECTANGLE) shapes[s].samp_off += h.off_sampling;
     out.blob.assign(h.total_bytes, 0);
     memcpy(&out.blob[0], &h, sizeof(h));
-    memcpy(&out.blob[h.off_tris], tris_sorted.data(), nt * sizeof(DevTri));
-    memcpy(&out.blob[h.off_nodes], nodes.data(), nn * sizeof(DevNode));
+    memcpy(&out.blob[h.off_prims], prims_out.data(), np * sizeof(DevPrim));
+    if (nn_nodes) memcpy(&out.blob[h.off_nodes], nodes.data(), nn_nodes * sizeof(DevNode));
     memcpy(&out.blob[h.off_shapes], shapes.data(), ns * sizeof(DevShape));
     memcpy(&out.blob[h.off_bsdfs], bsdfs.data(), bsdfs.size() * sizeof(DevBsdf));
     memcpy(&out.blob[h.off_emitters], emitters.data(), emitters.size() * sizeof(DevEmitter));
     memcpy(&out.blob[h.off_media], media.data(), media.size() * sizeof(DevMedium));
+    memcpy(&out.blob[h.off_geom], geom.data(), np * sizeof(DevGeom));
     if (!sampling.empty()) memcpy(&out.blob[h.off_sampling], sampling.data(), sampling.size());
-    out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn; out.n_tris = nt;
+    out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
     return true;
 }
 
@@ -288,11 +308,11 @@ void tr_scene_destroy(TrScene *scene) {
     delete scene;
 }
 
-int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_tris) {
+int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_prims) {
     if (!scene) return tr::fail(TR_ERR_INVALID_ARGUMENT, "scene is NULL");
     if (blob_bytes) *blob_bytes = scene->impl.blob.size();
     if (n_nodes) *n_nodes = scene->impl.n_nodes;
-    if (n_tris) *n_tris = scene->impl.n_tris;
+    if (n_prims) *n_prims = scene->impl.n_prims;
     return TR_OK;
 }
 

@@ -14,30 +14,45 @@ namespace tr {
 
 struct BlobHeader {            // 64 bytes
     uint32_t total_bytes;      // multiple of 16
-    uint32_t n_tris, n_nodes, n_shapes, n_bsdfs, n_emitters, n_media;
-    uint32_t off_tris, off_nodes, off_shapes, off_bsdfs, off_emitters, off_media, off_sampling;
+    uint32_t n_prims, n_nodes, n_shapes, n_bsdfs, n_emitters, n_media;
+    uint32_t off_prims, off_nodes, off_shapes, off_bsdfs, off_emitters, off_media, off_sampling;
     uint32_t n_area_emitters;  // emitters usable by Scene::sample_emitter_direction
-    uint32_t _pad;
+    uint32_t off_geom;         // DevGeom[n_prims], ORIGINAL primitive order
 };
 static_assert(sizeof(BlobHeader) == 64, "BlobHeader must be 64 bytes");
 
-struct DevTri {                // 64 bytes = 4 x float4, BVH leaf order
-    float p0[3]; uint32_t shape;
-    float e1[3]; uint32_t prim;   // original triangle index (tie-break key)
-    float e2[3]; uint32_t _r0;
-    float n[3];  uint32_t _r1;
+// Intersection record of one planar primitive (triangle or parallelogram), 80 bytes = 5 x float4.
+//   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
+// Order in the blob: ORIGINAL order when the scene is small enough for the lock-step brute-force loop
+// (n_nodes == 0), BVH leaf order otherwise.
+struct DevPrim {
+    float N[3];  float d0;
+    float a1[3]; float c1;
+    float a2[3]; float c2;
+    float lim;                 // u + v <= lim : 1 for triangles, 3 for parallelograms
+    uint32_t shape;
+    uint32_t prim;             // original primitive index (tie-break key)
+    float area;
+    float n[3];  uint32_t _r0; // unit geometric normal (shading)
 };
-static_assert(sizeof(DevTri) == 64, "DevTri must be 64 bytes");
+static_assert(sizeof(DevPrim) == 80, "DevPrim must be 80 bytes");
+
+struct DevGeom {               // 48 bytes, used by position sampling (emitters, hidden geometry)
+    float p0[3]; uint32_t quad;
+    float e1[3]; float area;
+    float e2[3]; uint32_t _r0;
+};
+static_assert(sizeof(DevGeom) == 48, "DevGeom must be 48 bytes");
 
 struct DevNode {               // 32 bytes = 2 x float4, pre-order threaded BVH
     float lo[3]; uint32_t skip;   // node to visit when this one is missed / finished
-    float hi[3]; uint32_t leaf;   // 0 for inner nodes, else (first_tri << 4) | count
+    float hi[3]; uint32_t leaf;   // 0 for inner nodes, else (first_prim << 4) | count
 };
 static_assert(sizeof(DevNode) == 32, "DevNode must be 32 bytes");
 
 struct DevShape {              // 128 bytes
     int32_t type, bsdf, emitter, flags;
-    uint32_t tri_begin_orig, tri_count, samp_off /* byte offset in blob of pmf|cdf|tri index arrays */, _r0;
+    uint32_t prim_begin, prim_count, samp_off /* byte offset in blob of the pmf | cdf arrays */, _r0;
     float inv_area, area_sum, area_norm, _r1;
     float to_world[12];
     float n[3]; int32_t interior_medium;
@@ -63,7 +78,7 @@ struct SceneImpl {
     void *d_blob = nullptr;              // device copy
     TrSensorDesc sensor;
     TrFilmDesc film;
-    uint32_t n_nodes = 0, n_tris = 0;
+    uint32_t n_nodes = 0, n_prims = 0;
     int device = -1;
     // cached owned-pixel list (tile sharding), rebuilt when (tile, rank, world) changes
     void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;

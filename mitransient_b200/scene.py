@@ -62,22 +62,23 @@ _CUBE_FACES = (  # (origin corner, u edge, v edge) with u x v pointing outwards;
 )
 
 
-def _cube_triangles() -> np.ndarray:
-    tris = []
+def _cube_prims():
+    """Mitsuba `cube` ([-1,1]^3): six parallelogram primitives with outward normals."""
+    prims = []
     for o, u, v in _CUBE_FACES:
         o, u, v = np.array(o, float), np.array(u, float), np.array(v, float)
-        tris.append([o, o + u, o + u + v])
-        tris.append([o, o + u + v, o + v])
-    return np.array(tris, dtype=np.float64)
+        prims.append([o, o + u, o + v])
+    return np.array(prims, dtype=np.float64), np.full(len(prims), _abi.TR_PRIM_QUAD, dtype=np.uint8)
 
 
-def _rectangle_triangles() -> np.ndarray:
-    v0, v1, v2, v3 = (np.array(p, float) for p in ((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)))
-    return np.array([[v0, v1, v2], [v0, v2, v3]], dtype=np.float64)
+def _rectangle_prims():
+    """Mitsuba `rectangle` ([-1,1]^2 in z = 0, normal +z): one parallelogram primitive."""
+    return (np.array([[(-1, -1, 0), (1, -1, 0), (-1, 1, 0)]], dtype=np.float64),
+            np.full(1, _abi.TR_PRIM_QUAD, dtype=np.uint8))
 
 
 def load_obj(path: str) -> np.ndarray:
-    """Wavefront OBJ -> float64 [n_tris, 3, 3].  Polygons are fan-triangulated; ``l``, ``vt``, ``vn``, ``o``,
+    """Wavefront OBJ -> float64 [n_tris, 3, 3] triangle primitives.  Polygons are fan-triangulated; ``l``, ``vt``, ``vn``, ``o``,
     ``s`` ... records are ignored (face normals are used, as Mitsuba does for meshes without ``vn``)."""
     verts: List[List[float]] = []
     tris: List[List[int]] = []
@@ -100,11 +101,11 @@ def load_obj(path: str) -> np.ndarray:
     return v[t]
 
 
-def _apply(to_world: ScalarTransform4f, tris: np.ndarray, flip: bool) -> np.ndarray:
+def _apply(to_world: ScalarTransform4f, prims: np.ndarray, flip: bool) -> np.ndarray:
     m = to_world.matrix
-    out = tris @ m[:3, :3].T + m[:3, 3]
+    out = prims @ m[:3, :3].T + m[:3, 3]
     if (np.linalg.det(m[:3, :3]) < 0) != bool(flip):
-        out = out[:, ::-1, :]  # keep the geometric normal equal to the transformed (inverse-transpose) normal
+        out = out[:, [0, 2, 1], :]  # swap e1/e2: keeps the geometric normal equal to the transformed normal
     return np.ascontiguousarray(out)
 
 
@@ -129,8 +130,8 @@ def _to_transform(v) -> ScalarTransform4f:
 
 # ------------------------------------------------------------------------------------ host-side scene objects
 class Shape:
-    def __init__(self, name, kind, tris, to_world, bsdf_index, flip=False):
-        self.name, self.kind, self.tris, self.to_world = name, kind, tris, to_world
+    def __init__(self, name, kind, prims, prim_types, to_world, bsdf_index, flip=False):
+        self.name, self.kind, self.prims, self.prim_types, self.to_world = name, kind, prims, prim_types, to_world
         self.bsdf_index = bsdf_index
         self.emitter_index = -1
         self.is_sensor = False
@@ -139,9 +140,10 @@ class Shape:
         self.flip = flip
 
     def surface_area(self) -> float:
-        e1 = self.tris[:, 1] - self.tris[:, 0]
-        e2 = self.tris[:, 2] - self.tris[:, 0]
-        return float(0.5 * np.linalg.norm(np.cross(e1, e2), axis=1).sum())
+        e1 = self.prims[:, 1] - self.prims[:, 0]
+        e2 = self.prims[:, 2] - self.prims[:, 0]
+        w = np.where(self.prim_types == _abi.TR_PRIM_QUAD, 1.0, 0.5)
+        return float((w * np.linalg.norm(np.cross(e1, e2), axis=1)).sum())
 
 
 class Scene:
@@ -175,9 +177,11 @@ class Scene:
     def describe(self, sensor) -> _abi.TrSceneDesc:
         """Build the ctypes ``TrSceneDesc`` for ``sensor`` (arrays are kept alive on ``self``)."""
         film = sensor.film()
-        tris = [s.tris for s in self.shapes_]
-        tri_verts = np.ascontiguousarray(np.concatenate(tris, axis=0) if tris else np.zeros((0, 3, 3)),
-                                         dtype=np.float32)
+        prims = [s.prims for s in self.shapes_]
+        prim_verts = np.ascontiguousarray(np.concatenate(prims, axis=0) if prims else np.zeros((0, 3, 3)),
+                                          dtype=np.float32)
+        prim_types = np.ascontiguousarray(np.concatenate([s.prim_types for s in self.shapes_])
+                                          if prims else np.zeros(0), dtype=np.uint8)
         shapes = (_abi.TrShapeDesc * max(1, len(self.shapes_)))()
         begin = 0
         for i, s in enumerate(self.shapes_):
@@ -186,9 +190,9 @@ class Scene:
             d.bsdf, d.emitter = s.bsdf_index, s.emitter_index
             d.flags = _abi.TR_SHAPE_FLAG_SENSOR if s.is_sensor else 0
             d.interior_medium, d.exterior_medium = s.interior_medium, s.exterior_medium
-            d.tri_begin, d.tri_count = begin, len(s.tris)
+            d.prim_begin, d.prim_count = begin, len(s.prims)
             d.to_world[:] = s.to_world.affine3x4().reshape(-1).tolist()
-            begin += len(s.tris)
+            begin += len(s.prims)
         bsdfs = (_abi.TrBsdfDesc * max(1, len(self.bsdfs_)))()
         for i, b in enumerate(self.bsdfs_):
             bsdfs[i].type, bsdfs[i].flags = b["type"], b["flags"]
@@ -207,15 +211,16 @@ class Scene:
 
         desc = _abi.TrSceneDesc()
         desc.abi_version = _abi.TR_ABI_VERSION
-        desc.n_tris = tri_verts.shape[0]
-        desc.tri_verts = tri_verts.ctypes.data_as(C.POINTER(C.c_float))
+        desc.n_prims = prim_verts.shape[0]
+        desc.prim_verts = prim_verts.ctypes.data_as(C.POINTER(C.c_float))
+        desc.prim_types = prim_types.ctypes.data_as(C.POINTER(C.c_uint8))
         desc.n_shapes, desc.shapes = len(self.shapes_), shapes
         desc.n_bsdfs, desc.bsdfs = len(self.bsdfs_), bsdfs
         desc.n_emitters, desc.emitters = len(self.emitters_), emitters
         desc.n_media, desc.media = len(self.media_), media
         desc.sensor = sensor.describe(self)
         desc.film = film.describe()
-        self._keepalive = [tri_verts, shapes, bsdfs, emitters, media]
+        self._keepalive = [prim_verts, prim_types, shapes, bsdfs, emitters, media]
         return desc
 
     def description_key(self, sensor):
@@ -224,7 +229,7 @@ class Scene:
                 sensor.state_key())
 
     def __repr__(self):
-        return (f"Scene[shapes={len(self.shapes_)}, triangles={sum(len(s.tris) for s in self.shapes_)}, "
+        return (f"Scene[shapes={len(self.shapes_)}, primitives={sum(len(s.prims) for s in self.shapes_)}, "
                 f"bsdfs={len(self.bsdfs_)}, emitters={len(self.emitters_)}, sensors={len(self.sensors_)}]")
 
 
@@ -358,14 +363,15 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
             to_world = _to_transform(val.get("to_world"))
             flip = bool(val.get("flip_normals", False))
             if t == "rectangle":
-                base = _rectangle_triangles()
+                base, ptypes = _rectangle_prims()
             elif t == "cube":
-                base = _cube_triangles()
+                base, ptypes = _cube_prims()
             else:
                 fn = val["filename"]
                 if not os.path.isabs(fn) and base_dir:
                     fn = os.path.join(base_dir, fn)
                 base = load_obj(fn)
+                ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
             bspec = val.get("bsdf")
             if bspec is None:
                 bspec = next((v for k, v in val.items() if isinstance(v, dict) and
@@ -377,7 +383,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 bidx = default_bsdf
             else:
                 bidx = add_bsdf(bspec)
-            shape = Shape(key, t, _apply(to_world, base, flip), to_world, bidx, flip)
+            shape = Shape(key, t, _apply(to_world, base, flip), ptypes, to_world, bidx, flip)
             if "interior" in val:
                 shape.interior_medium = add_medium(val["interior"])
             if "exterior" in val:

@@ -33,6 +33,8 @@
 //      dot(a,b)   = fmaf(a.z,b.z, fmaf(a.y,b.y, a.x*b.x))
 //      cross(a,b) = ( fmaf(a.y,b.z, -(a.z*b.y)), fmaf(a.z,b.x, -(a.x*b.z)), fmaf(a.x,b.y, -(a.y*b.x)) )
 //      v / s      = v * (1.0f / s)            normalize(v) = v * (1.0f / sqrtf(dot(v,v)))
+//  Ray / primitive intersection (the reference delegates it to Embree/OptiX, whose bits cannot be
+//  reproduced): plane form with per-primitive precomputed duals, see Prim / prim_test below.
 //  sqrt and division are correctly rounded; sin/cos use the Cephes polynomial below.  With
 //  the same PCG32 streams the GPU then walks bit-identical paths; only the order of the fp32
 //  additions into a film bin differs.
@@ -133,17 +135,20 @@ inline void sample_tea_32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) 
 }
 
 // ------------------------------------------------------------------------------ scene
-struct Tri { V3 p0, e1, e2, n, s, t; uint32_t shape; };
+// A planar primitive (triangle or parallelogram) in intersection form:
+//   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
+// so that for a point p of the plane  u = dot(p,a1) - c1,  v = dot(p,a2) - c2  (p = p0 + u e1 + v e2).
+struct Prim { V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; };
 struct Shape {
     TrShapeDesc d;
     float inv_area;            // 1 / surface area
     V3 n;                      // rectangle: frame normal
-    std::vector<float> pmf;    // mesh: triangle areas (unnormalised pmf)
-    std::vector<float> cdf;    // mesh: running triangle-area sums (float, accumulated in double)
+    std::vector<float> pmf;    // mesh: primitive areas (unnormalised pmf)
+    std::vector<float> cdf;    // mesh: running area sums (float, accumulated in double)
     float area_sum, area_norm; // DiscreteDistribution m_sum / m_normalization
 };
 struct Scene {
-    std::vector<Tri> tris;
+    std::vector<Prim> prims;
     std::vector<Shape> shapes;
     std::vector<TrBsdfDesc> bsdfs;
     std::vector<TrEmitterDesc> emitters;
@@ -176,28 +181,34 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
     sc.sensor = desc->sensor; sc.film = desc->film;
     sc.bsdfs.assign(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
     sc.emitters.assign(desc->emitters, desc->emitters + desc->n_emitters);
-    sc.tris.resize(desc->n_tris);
+    sc.prims.resize(desc->n_prims);
     sc.shapes.resize(desc->n_shapes);
     for (uint32_t si = 0; si < desc->n_shapes; ++si) {
         Shape &sh = sc.shapes[si];
         sh.d = desc->shapes[si];
-        if (sh.d.tri_begin + sh.d.tri_count > desc->n_tris) { err = "shape triangle range out of bounds"; return false; }
+        if (sh.d.prim_begin + sh.d.prim_count > desc->n_prims) { err = "shape primitive range out of bounds"; return false; }
         double area_acc = 0.0;
         sh.cdf.clear(); sh.pmf.clear();
-        for (uint32_t k = 0; k < sh.d.tri_count; ++k) {
-            uint32_t ti = sh.d.tri_begin + k;
-            const float *v = desc->tri_verts + 9 * (size_t) ti;
-            Tri &t = sc.tris[ti];
+        for (uint32_t k = 0; k < sh.d.prim_count; ++k) {
+            uint32_t pi = sh.d.prim_begin + k;
+            const float *v = desc->prim_verts + 9 * (size_t) pi;
+            Prim &t = sc.prims[pi];
+            t.quad = desc->prim_types[pi] == TR_PRIM_QUAD;
             t.p0 = v3(v[0], v[1], v[2]);
             t.e1 = v3(v[3], v[4], v[5]) - t.p0;
             t.e2 = v3(v[6], v[7], v[8]) - t.p0;
-            V3 c = cross(t.e1, t.e2);
-            float len = sqrtf(dot(c, c));
-            t.n = c * (1.0f / len);
+            t.N = cross(t.e1, t.e2);
+            float nn = dot(t.N, t.N);
+            float inv_nn = 1.0f / nn;
+            float len = sqrtf(nn);
+            t.n = t.N * (1.0f / len);
+            t.d0 = dot(t.N, t.p0);
+            t.a1 = cross(t.e2, t.N) * inv_nn; t.c1 = dot(t.p0, t.a1);
+            t.a2 = cross(t.N, t.e1) * inv_nn; t.c2 = dot(t.p0, t.a2);
             t.shape = si;
-            float area = 0.5f * len;
-            area_acc += (double) area;
-            sh.pmf.push_back(area);
+            t.area = t.quad ? len : 0.5f * len;
+            area_acc += (double) t.area;
+            sh.pmf.push_back(t.area);
             sh.cdf.push_back((float) area_acc);
             if (sh.d.type == TR_SHAPE_RECTANGLE) {
                 // Rectangle: tangent from dp_du = to_world * (2,0,0), Gram-Schmidt against n
@@ -217,7 +228,7 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
             V3 dpdv = xf_vector(sh.d.to_world, v3(0.0f, 2.0f, 0.0f));
             V3 c = cross(dpdu, dpdv);
             sh.inv_area = 1.0f / sqrtf(dot(c, c));
-            sh.n = sh.d.tri_count ? sc.tris[sh.d.tri_begin].n : v3(0, 0, 1);
+            sh.n = sh.d.prim_count ? sc.prims[sh.d.prim_begin].n : v3(0, 0, 1);
         } else {
             sh.inv_area = sh.area_norm;
             sh.n = v3(0, 0, 0);
@@ -232,44 +243,41 @@ struct Hit {
     bool valid; float t; V3 p, n, s, tt; uint32_t shape, prim;
 };
 
-// Moeller-Trumbore as in Mitsuba's Mesh::ray_intersect_triangle.
-inline bool tri_test(const Tri &tr, const Ray &r, float *t_out, float *u_out, float *v_out) {
-    V3 pvec = cross(r.d, tr.e2);
-    float det = dot(tr.e1, pvec);
-    float inv_det = 1.0f / det;
-    V3 tvec = r.o - tr.p0;
-    float u = dot(tvec, pvec) * inv_det;
-    V3 qvec = cross(tvec, tr.e1);
-    float v = dot(r.d, qvec) * inv_det;
-    float t = dot(tr.e2, qvec) * inv_det;
-    bool ok = (u >= 0.0f) && (v >= 0.0f) && (u + v <= 1.0f) && (t >= 0.0f) && (t <= r.maxt);
-    *t_out = t; *u_out = u; *v_out = v;
+// Ray / primitive test of the arithmetic contract: intersect the supporting plane, then read the
+// parallelogram coordinates (u, v) of the hit point off the precomputed dual vectors.
+inline bool prim_test(const Prim &pr, const Ray &r, float *t_out, V3 *p_out) {
+    float denom = dot(pr.N, r.d);
+    float tnum = fmaf(-pr.N.z, r.o.z, fmaf(-pr.N.y, r.o.y, fmaf(-pr.N.x, r.o.x, pr.d0)));
+    float t = tnum / denom;
+    V3 p = fma3(r.d, t, r.o);
+    float u = fmaf(p.z, pr.a1.z, fmaf(p.y, pr.a1.y, fmaf(p.x, pr.a1.x, -pr.c1)));
+    float v = fmaf(p.z, pr.a2.z, fmaf(p.y, pr.a2.y, fmaf(p.x, pr.a2.x, -pr.c2)));
+    bool inside = pr.quad ? (u <= 1.0f && v <= 1.0f) : (u + v <= 1.0f);
+    bool ok = (u >= 0.0f) && (v >= 0.0f) && inside && (t >= 0.0f) && (t <= r.maxt);
+    *t_out = t; *p_out = p;
     return ok;
 }
 
 Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: closest hit, brute force
     Hit h; h.valid = false; h.t = kInf; h.prim = 0xffffffffu; h.shape = 0;
-    float bu = 0, bv = 0;
-    for (uint32_t i = 0; i < sc.tris.size(); ++i) {
-        float t, u, v;
-        if (tri_test(sc.tris[i], r, &t, &u, &v) && t < h.t) {  // ascending index + strict '<' == lowest index wins ties
-            h.valid = true; h.t = t; h.prim = i; bu = u; bv = v;
+    h.p = v3(0, 0, 0); h.n = v3(0, 0, 0); h.s = h.tt = v3(0, 0, 0);
+    for (uint32_t i = 0; i < sc.prims.size(); ++i) {
+        float t; V3 p;
+        if (prim_test(sc.prims[i], r, &t, &p) && t < h.t) {  // ascending index + strict '<' == lowest index wins ties
+            h.valid = true; h.t = t; h.prim = i; h.p = p;
         }
     }
     if (h.valid) {
-        const Tri &tr = sc.tris[h.prim];
-        h.p = fma3(tr.e2, bv, fma3(tr.e1, bu, tr.p0));
-        h.n = tr.n; h.s = tr.s; h.tt = tr.t; h.shape = tr.shape;
-    } else {
-        h.p = v3(0, 0, 0); h.n = v3(0, 0, 0); h.s = h.tt = v3(0, 0, 0);
+        const Prim &pr = sc.prims[h.prim];
+        h.n = pr.n; h.s = pr.s; h.tt = pr.t; h.shape = pr.shape;
     }
     return h;
 }
 
 bool ray_test(const Scene &sc, const Ray &r) {  // scene.ray_test: any hit
-    for (uint32_t i = 0; i < sc.tris.size(); ++i) {
-        float t, u, v;
-        if (tri_test(sc.tris[i], r, &t, &u, &v)) return true;
+    for (uint32_t i = 0; i < sc.prims.size(); ++i) {
+        float t; V3 p;
+        if (prim_test(sc.prims[i], r, &t, &p)) return true;
     }
     return false;
 }
@@ -323,17 +331,19 @@ inline void shape_sample_position(const Scene &sc, const Shape &sh, float u0, fl
         *p = xf_point(sh.d.to_world, fmaf(u0, 2.0f, -1.0f), fmaf(u1, 2.0f, -1.0f), 0.0f);
         *n = sh.n; *pdf = sh.inv_area;
     } else {
-        // Mesh::sample_position: face by area CDF reusing sample.y, uniform triangle warp
+        // Mesh::sample_position: face by area CDF reusing sample.y, then a uniform point on the
+        // primitive (triangle: Mitsuba's square_to_uniform_triangle; quad: p0 + u e1 + v e2)
         float value = u1 * sh.area_sum;
-        uint32_t lo = 0, hi = sh.d.tri_count ? sh.d.tri_count - 1 : 0;  // first idx with cdf[idx] >= value
+        uint32_t lo = 0, hi = sh.d.prim_count ? sh.d.prim_count - 1 : 0;  // first idx with cdf[idx] >= value
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sh.cdf[mid] < value) lo = mid + 1; else hi = mid; }
         uint32_t idx = lo;
         float cdf_prev = idx ? sh.cdf[idx - 1] : 0.0f;
         float pmf = sh.pmf[idx] * sh.area_norm;
         float u1r = (u1 - cdf_prev * sh.area_norm) / pmf;
-        const Tri &tr = sc.tris[sh.d.tri_begin + idx];
-        float t = sqrtf(fmaxf(1.0f - u0, 0.0f));
-        float b0 = 1.0f - t, b1 = t * u1r;
+        const Prim &tr = sc.prims[sh.d.prim_begin + idx];
+        float b0, b1;
+        if (tr.quad) { b0 = u0; b1 = u1r; }
+        else { float t = sqrtf(fmaxf(1.0f - u0, 0.0f)); b0 = 1.0f - t; b1 = t * u1r; }
         *p = fma3(tr.e1, b0, fma3(tr.e2, b1, tr.p0));
         *n = tr.n; *pdf = sh.area_norm;
     }

@@ -1,0 +1,35 @@
+"""Render one configuration N times on cuda:0 (target command for ncu captures).
+
+    python scripts/render_once.py [--width 512 --height 512 --bins 1024 --spp 256 --depth 8 --reps 2]
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import mitransient_b200 as mitr
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--width", type=int, default=512)
+ap.add_argument("--height", type=int, default=512)
+ap.add_argument("--bins", type=int, default=1024)
+ap.add_argument("--spp", type=int, default=256)
+ap.add_argument("--depth", type=int, default=8)
+ap.add_argument("--reps", type=int, default=2)
+a = ap.parse_args()
+
+scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
+integ = scene.integrator()
+integ.collect_counters = True
+for i in range(a.reps):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steady, transient = mitr.render(scene, spp=a.spp, seed=0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    c = integ.last_counters
+    print(f"rep {i}: {dt * 1e3:.2f} ms (render + develop), {a.width * a.height * a.spp / dt / 1e6:.1f} M-paths/s, "
+          f"counters {c}", flush=True)

@@ -56,3 +56,58 @@ def test_variants_parity(mitr, oracle, w, h, t, spp, seed, integ):
     assert err["zero_bins_mismatch"] == 0
     assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
     np.testing.assert_allclose(steady, ref["steady"], rtol=1e-4, atol=1e-6)
+
+
+def _write_obj(path, verts, faces):
+    with open(path, "w") as f:
+        f.write("# test mesh\no test\n")
+        for v in verts:
+            f.write(f"v {v[0]:.6f} {v[1]:.6f} {v[2]:.6f}\n")
+        for t in faces:
+            f.write("f " + " ".join(str(i + 1) for i in t) + "\n")
+
+
+def _uv_sphere(n_lat, n_lon, radius, center):
+    verts, faces = [], []
+    for i in range(n_lat + 1):
+        th = np.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2 * np.pi * j / n_lon
+            verts.append([center[0] + radius * np.sin(th) * np.cos(ph), center[1] + radius * np.cos(th),
+                          center[2] + radius * np.sin(th) * np.sin(ph)])
+    for i in range(n_lat):
+        for j in range(n_lon):
+            a, b = i * n_lon + j, i * n_lon + (j + 1) % n_lon
+            c, d = a + n_lon, b + n_lon
+            if i > 0:
+                faces.append([a, b, c])
+            if i < n_lat - 1:
+                faces.append([b, d, c])
+    return np.array(verts), faces
+
+
+def test_bvh_mesh_scene_parity(mitr, oracle, tmp_path):
+    """> 64 primitives: the threaded-BVH traversal must give the oracle's brute-force hits; the light is an
+    OBJ mesh (two triangles), which exercises Mesh::sample_position (area CDF + triangle warp)."""
+    sv, sf = _uv_sphere(10, 16, 0.35, (0.3, -0.65, 0.2))
+    _write_obj(tmp_path / "sphere.obj", sv, sf)
+    lv = np.array([[-0.25, 0.98, -0.2], [0.25, 0.98, -0.2], [0.25, 0.98, 0.2], [-0.25, 0.98, 0.2]])
+    _write_obj(tmp_path / "light.obj", lv, [[0, 1, 2], [0, 2, 3]])   # normal (0,-1,0): faces down
+    d = mitr.cornell_box_config(40, 40, 200, 16)
+    del d["light"], d["small-box"]
+    d["sphere"] = {"type": "obj", "filename": str(tmp_path / "sphere.obj"), "bsdf": {"type": "ref", "id": "green"}}
+    d["meshlight"] = {"type": "obj", "filename": str(tmp_path / "light.obj"), "bsdf": {"type": "ref", "id": "white"},
+                      "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [10.0, 9.0, 7.0]}}}
+    scene = mitr.load_dict(d)
+    integ = scene.integrator()
+    integ.collect_counters = True
+    steady, transient = integ.render(scene, seed=4, spp=16)
+    info = integ.device_scene(scene, scene.sensors()[0]).info()
+    assert info["bvh_nodes"] > 0 and info["triangles"] > 64
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = oracle.render(scene, integ, seed=4, spp=16)
+    assert integ.last_counters == ref["counters"]
+    assert ref["steady"].mean() > 1e-3                      # the mesh light actually illuminates the scene
+    err = film_l1(raw, ref["transient"])
+    assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
+    np.testing.assert_allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
