@@ -1,0 +1,117 @@
+"""Host-side logic (no GPU): scene ingestion, plugin parameters and the reference's accept/reject behaviour."""
+import math
+
+import numpy as np
+import pytest
+
+
+def test_plugin_names_and_defaults(mitr):
+    from mitransient_b200 import plugins
+    assert {"transient_path"} <= set(plugins.INTEGRATORS)
+    assert "transient_hdr_film" in plugins.FILMS and "nlos_capture_meter" in plugins.SENSORS
+    film = mitr.load_dict({"type": "transient_hdr_film"})
+    # transient_hdr_film.py:116-121 + mi.Film defaults
+    assert (film.temporal_bins, film.bin_width_opl, film.start_opl) == (2048, 0.003, 0.0)
+    assert film.size() == (768, 576) and film.exhaustive_scan is False and film.rfilter() == "box"
+    assert abs(film.end_opl() - 2048 * 0.003) < 1e-12
+    integ = mitr.load_dict({"type": "transient_path"})
+    assert (integ.max_depth, integ.rr_depth, integ.camera_unwarp, integ.discard_direct_light) == (6, 5, False, False)
+    assert mitr.load_dict({"type": "transient_path", "max_depth": -1}).max_depth == 0xFFFFFFFF
+    # temporal_filter / gaussian_stddev / block_size are accepted and ignored (common.py:28-30)
+    mitr.load_dict({"type": "transient_path", "temporal_filter": "gaussian", "gaussian_stddev": 3.0, "block_size": 32})
+    with pytest.raises(ValueError):
+        mitr.load_dict({"type": "transient_path", "rr_depth": 0})
+
+
+def test_cornell_box_scene(mitr):
+    d = mitr.cornell_box()
+    assert d["integrator"]["max_depth"] == 8 and d["sensor"]["film"]["temporal_bins"] == 300
+    scene = mitr.load_dict(d)
+    assert len(scene.shapes()) == 8 and len(scene.emitters()) == 1 and len(scene.bsdfs_) == 3
+    assert sum(len(s.prims) for s in scene.shapes()) == 6 + 12      # 6 rectangles + 2 cubes x 6 faces
+    light = scene.shapes()[0]
+    assert light.kind == "rectangle" and light.emitter_index == 0
+    assert abs(light.surface_area() - (2 * 0.23) * (2 * 0.19)) < 1e-9
+    n = np.cross(light.prims[0, 1] - light.prims[0, 0], light.prims[0, 2] - light.prims[0, 0])
+    assert n[1] < 0 and abs(n[0]) < 1e-12 and abs(n[2]) < 1e-12     # the light faces down
+    for s in scene.shapes()[1:6]:                                    # walls face the inside of the box
+        c = s.prims[0].mean(axis=0)
+        nn = np.cross(s.prims[0, 1] - s.prims[0, 0], s.prims[0, 2] - s.prims[0, 0])
+        assert np.dot(nn, -c) > 0, s.name
+    for s in scene.shapes()[6:]:                                     # cube faces point outwards
+        centre = s.prims.reshape(-1, 3).mean(axis=0)
+        for p in s.prims:
+            fc = p[0] + 0.5 * (p[1] - p[0]) + 0.5 * (p[2] - p[0])
+            assert np.dot(np.cross(p[1] - p[0], p[2] - p[0]), fc - centre) > 0
+        assert abs(s.surface_area() - 6 * np.linalg.norm(np.cross(s.prims[0, 1] - s.prims[0, 0],
+                                                                    s.prims[0, 2] - s.prims[0, 0]))) < 1.0
+    desc = scene.describe(scene.sensors()[0])
+    assert desc.n_prims == 18 and desc.n_shapes == 8 and desc.film.temporal_bins == 300
+    cfg = mitr.cornell_box_config(512, 512, 1024, 256)
+    assert cfg["sensor"]["film"]["bin_width_opl"] == 6.0 / 1024 and cfg["sensor"]["film"]["start_opl"] == 3.5
+
+
+def test_transforms(mitr):
+    T = mitr.ScalarTransform4f
+    m = T().translate([1, 2, 3]).rotate([0, 0, 1], 90).scale(2.0)
+    np.testing.assert_allclose(m.transform_affine([1, 0, 0]), [1, 4, 3], atol=1e-12)   # scale, rotate, translate
+    np.testing.assert_allclose((m @ m.inverse()).matrix, np.eye(4), atol=1e-12)
+    la = T().look_at(origin=[0, 0, 3.9], target=[0, 0, 0], up=[0, 1, 0])
+    np.testing.assert_allclose(la.matrix[:3, :3], [[-1, 0, 0], [0, 1, 0], [0, 0, -1]], atol=1e-12)
+    from mitransient_b200.transforms import parse_fov
+    assert parse_fov(40.0, "x", 2.0) == 40.0
+    assert abs(parse_fov(40.0, "smaller", 2.0) - math.degrees(2 * math.atan(math.tan(math.radians(20)) * 2))) < 1e-9
+    assert parse_fov(40.0, "smaller", 0.5) == 40.0
+
+
+def test_rejections_match_reference(mitr):
+    d = mitr.cornell_box_config(8, 8, 16, 1)
+    scene = mitr.load_dict(d)
+    integ = scene.integrator()
+    with pytest.raises(Exception, match="develop=True"):
+        integ.render(scene, develop=False)                           # common.py:130-132
+    d2 = mitr.cornell_box_config(8, 8, 16, 1)
+    d2["sensor"]["film"]["rfilter"] = {"type": "gaussian"}
+    s2 = mitr.load_dict(d2)
+    with pytest.raises(ValueError, match="rfilter"):
+        s2.sensors()[0].film().check_supported()                     # transient_image_block.py:150-151
+    with pytest.raises(ValueError):
+        mitr.load_dict({"type": "scene", "x": {"type": "sphere"}})
+    with pytest.raises(ValueError):
+        mitr.load_dict({"type": "scene", "x": {"type": "rectangle", "bsdf": {"type": "roughplastic"}}})
+
+
+def test_prepare_pass_split(mitr):
+    """common.py:51-85: one pass up to 2^32 samples, else passes of int((2^26-1)/(W*H)) spp with seeds drawn
+    from the sampler."""
+    from mitransient_b200.integrators.common import TransientADIntegrator
+    from mitransient_b200.sampler import independent_sampler_first_float
+
+    class FakeFilm:
+        def crop_size(self): return (512, 512)
+        def prepare(self, aovs): pass
+
+    class FakeSensor:
+        def __init__(self, s): self._s = s
+        def film(self): return FakeFilm()
+        def sampler(self): return self._s
+
+    from mitransient_b200.scene import IndependentSampler, Properties
+    integ = TransientADIntegrator(Properties())
+    s = IndependentSampler(Properties({"sample_count": 256}))
+    assert integ.prepare(None, FakeSensor(s), seed=7, spp=0) == [(7, 256)]
+    assert integ.prepare(None, FakeSensor(s), seed=0, spp=16384) == [(0, 16384)]          # exactly 2^32: one pass
+    passes = integ.prepare(None, FakeSensor(s), seed=3, spp=20000)
+    spp_per_pass = int((2 ** 26 - 1) / (512 * 512))
+    assert spp_per_pass == 255 and sum(p[1] for p in passes) == 20000
+    assert len(passes) == 20000 // 255 + 1 and passes[-1][1] == 20000 % 255
+    assert passes[0][0] == int(independent_sampler_first_float(3, 0) * 2.0 ** 32)
+    assert len({p[0] for p in passes}) == len(passes)
+
+
+def test_obj_loader_ignores_line_records(mitr, tmp_path):
+    p = tmp_path / "q.obj"
+    p.write_text("o q\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nl 1 2\nf 1/1/1 2/1/1 3/1/1 4/1/1\nf -4 -3 -2\n")
+    tris = mitr.load_obj(str(p))
+    assert tris.shape == (3, 3, 3)                                   # quad -> 2 triangles (fan) + 1 triangle
+    np.testing.assert_allclose(tris[2], [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
