@@ -11,7 +11,8 @@ import threading
 
 from . import _abi
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmitransient_b200.so")
+_LIB_PATH = os.environ.get("MITRANSIENT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                                   "libmitransient_b200.so")
 _lock = threading.Lock()
 _lib = None
 

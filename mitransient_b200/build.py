@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("TR_NVCC_EXTRA", "").split()
 
 
 def find_nvcc() -> str:

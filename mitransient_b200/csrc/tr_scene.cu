@@ -140,6 +140,39 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
         }
     }
 
+    // ---- boundary primitives: every scene vertex lies on the front side of the supporting plane (same
+    // arithmetic as the oracle's classify_boundary_prims).  They can never occlude a shadow ray.
+    uint32_t n_occ = 0;
+    {
+        std::vector<H3> verts;
+        verts.reserve((size_t) np * 4);
+        for (uint32_t i = 0; i < np; ++i) {
+            const DevGeom &g = geom[i];
+            H3 p0 = h3(g.p0[0], g.p0[1], g.p0[2]), e1 = h3(g.e1[0], g.e1[1], g.e1[2]), e2 = h3(g.e2[0], g.e2[1], g.e2[2]);
+            H3 p1 = h3(p0.x + e1.x, p0.y + e1.y, p0.z + e1.z), p2 = h3(p0.x + e2.x, p0.y + e2.y, p0.z + e2.z);
+            verts.push_back(p0); verts.push_back(p1); verts.push_back(p2);
+            if (g.quad) verts.push_back(h3(p1.x + e2.x, p1.y + e2.y, p1.z + e2.z));
+        }
+        float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (const H3 &x : verts) {
+            lo3[0] = fminf(lo3[0], x.x); hi3[0] = fmaxf(hi3[0], x.x);
+            lo3[1] = fminf(lo3[1], x.y); hi3[1] = fmaxf(hi3[1], x.y);
+            lo3[2] = fminf(lo3[2], x.z); hi3[2] = fmaxf(hi3[2], x.z);
+        }
+        const float ext = fmaxf(fmaxf(hi3[0] - lo3[0], hi3[1] - lo3[1]), hi3[2] - lo3[2]);
+        for (uint32_t i = 0; i < np; ++i) {
+            DevPrim &t = prims[i];
+            H3 N = h3(t.N[0], t.N[1], t.N[2]);
+            float tol = 1e-4f * sqrtf(hdot(N, N)) * ext;
+            bool boundary = true;
+            for (const H3 &x : verts) {
+                float sd = fmaf(N.z, x.z, fmaf(N.y, x.y, fmaf(N.x, x.x, -t.d0)));
+                if (!(sd >= -tol)) { boundary = false; break; }
+            }
+            if (boundary) t.lim = -t.lim; else n_occ++;
+        }
+    }
+
     // ---- acceleration: none for small scenes (the kernel runs a lock-step loop over all primitives, original
     // order); otherwise a median-split BVH, pre-order threaded.  Boxes are padded so that the fp32 slab test is
     // conservative w.r.t. the primitive test: culling never changes the result.
@@ -261,6 +294,8 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     h.off_media = off; off += (uint32_t) (media.size() * sizeof(DevMedium));
     h.off_geom = off; off += np * (uint32_t) sizeof(DevGeom);
     h.off_sampling = off; off += align16((uint32_t) sampling.size());
+    h.off_occluders = off; h.n_occluders = n_occ;
+    if (nn_nodes == 0) off += n_occ * (uint32_t) sizeof(DevPrim);
     h.total_bytes = align16(off);
     for (uint32_t s = 0; s < ns; ++s)
         if (shapes[s].type != TR_SHAPE_RECTANGLE) shapes[s].samp_off += h.off_sampling;
@@ -274,6 +309,11 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     memcpy(&out.blob[h.off_media], media.data(), media.size() * sizeof(DevMedium));
     memcpy(&out.blob[h.off_geom], geom.data(), np * sizeof(DevGeom));
     if (!sampling.empty()) memcpy(&out.blob[h.off_sampling], sampling.data(), sampling.size());
+    if (nn_nodes == 0) {   // brute-force mode: compact copy of the possible occluders, original order
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < np; ++i)
+            if (prims[i].lim > 0.0f) memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims[i], sizeof(DevPrim));
+    }
     out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
     return true;
 }

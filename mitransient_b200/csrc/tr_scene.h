@@ -12,14 +12,17 @@
 
 namespace tr {
 
-struct BlobHeader {            // 64 bytes
+struct BlobHeader {            // 96 bytes
     uint32_t total_bytes;      // multiple of 16
     uint32_t n_prims, n_nodes, n_shapes, n_bsdfs, n_emitters, n_media;
     uint32_t off_prims, off_nodes, off_shapes, off_bsdfs, off_emitters, off_media, off_sampling;
     uint32_t n_area_emitters;  // emitters usable by Scene::sample_emitter_direction
     uint32_t off_geom;         // DevGeom[n_prims], ORIGINAL primitive order
+    uint32_t off_occluders;    // DevPrim[n_occluders]: the non-boundary primitives (brute-force shadow loop)
+    uint32_t n_occluders;
+    uint32_t _pad[6];
 };
-static_assert(sizeof(BlobHeader) == 64, "BlobHeader must be 64 bytes");
+static_assert(sizeof(BlobHeader) == 96, "BlobHeader must be 96 bytes");
 
 // Intersection record of one planar primitive (triangle or parallelogram), 80 bytes = 5 x float4.
 //   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
@@ -29,7 +32,8 @@ struct DevPrim {
     float N[3];  float d0;
     float a1[3]; float c1;
     float a2[3]; float c2;
-    float lim;                 // u + v <= lim : 1 for triangles, 3 for parallelograms
+    float lim;                 // u + v <= |lim| : 1 for triangles, 3 for parallelograms; NEGATIVE for boundary
+                               // primitives (never occlude a shadow ray, see tr_scene.cu classify_boundary)
     uint32_t shape;
     uint32_t prim;             // original primitive index (tie-break key)
     float area;

@@ -138,7 +138,7 @@ inline void sample_tea_32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) 
 // A planar primitive (triangle or parallelogram) in intersection form:
 //   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
 // so that for a point p of the plane  u = dot(p,a1) - c1,  v = dot(p,a2) - c2  (p = p0 + u e1 + v e2).
-struct Prim { V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; };
+struct Prim { V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; bool boundary; };
 struct Shape {
     TrShapeDesc d;
     float inv_area;            // 1 / surface area
@@ -174,6 +174,32 @@ inline V3 xf_vector(const float *m, V3 v) {
     return v3(fmaf(m[0], v.x, fmaf(m[1], v.y, m[2] * v.z)),
               fmaf(m[4], v.x, fmaf(m[5], v.y, m[6] * v.z)),
               fmaf(m[8], v.x, fmaf(m[9], v.y, m[10] * v.z)));
+}
+
+// A primitive is a BOUNDARY primitive when every vertex of the scene lies on the front side of (or within a
+// tolerance of) its supporting plane.  A segment between two scene points can then only touch that plane at
+// its end points, so a boundary primitive never occludes a shadow ray: scene.ray_test skips it (this removes
+// the fp self-shadowing flicker at room corners and a third of the occlusion tests of a closed room).
+inline float plane_side(const Prim &pr, V3 x) { return fmaf(pr.N.z, x.z, fmaf(pr.N.y, x.y, fmaf(pr.N.x, x.x, -pr.d0))); }
+void classify_boundary_prims(Scene &sc) {
+    float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
+    std::vector<V3> verts;
+    for (const Prim &q : sc.prims) {
+        V3 c[4] = {q.p0, q.p0 + q.e1, q.p0 + q.e2, (q.p0 + q.e1) + q.e2};
+        for (int k = 0; k < (q.quad ? 4 : 3); ++k) {
+            verts.push_back(c[k]);
+            lo[0] = fminf(lo[0], c[k].x); hi[0] = fmaxf(hi[0], c[k].x);
+            lo[1] = fminf(lo[1], c[k].y); hi[1] = fmaxf(hi[1], c[k].y);
+            lo[2] = fminf(lo[2], c[k].z); hi[2] = fmaxf(hi[2], c[k].z);
+        }
+    }
+    float extent = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    for (Prim &pr : sc.prims) {
+        float tol = 1e-4f * sqrtf(dot(pr.N, pr.N)) * extent;
+        bool b = true;
+        for (const V3 &x : verts) if (!(plane_side(pr, x) >= -tol)) { b = false; break; }
+        pr.boundary = b;
+    }
 }
 
 bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
@@ -234,6 +260,7 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
             sh.n = v3(0, 0, 0);
         }
     }
+    classify_boundary_prims(sc);
     return true;
 }
 
@@ -276,6 +303,7 @@ Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: clos
 
 bool ray_test(const Scene &sc, const Ray &r) {  // scene.ray_test: any hit
     for (uint32_t i = 0; i < sc.prims.size(); ++i) {
+        if (sc.prims[i].boundary) continue;   // see classify_boundary_prims
         float t; V3 p;
         if (prim_test(sc.prims[i], r, &t, &p)) return true;
     }

@@ -1,0 +1,41 @@
+"""CUDA-event timing of tr_render alone (the bench's `value` leg) -- used for A/B runs of kernel variants.
+    [MITRANSIENT_B200_LIB=path/to/variant.so] python scripts/time_kernel.py [--steps 10]"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import mitransient_b200 as mitr
+from mitransient_b200 import _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--width", type=int, default=512)
+ap.add_argument("--height", type=int, default=512)
+ap.add_argument("--bins", type=int, default=1024)
+ap.add_argument("--spp", type=int, default=256)
+ap.add_argument("--depth", type=int, default=8)
+ap.add_argument("--steps", type=int, default=10)
+a = ap.parse_args()
+scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
+integ, sensor = scene.integrator(), scene.sensors()[0]
+dev = integ.device_scene(scene, sensor)
+lib = _lib.load()
+film = torch.zeros((a.height, a.width, a.bins, 4), dtype=torch.float32, device="cuda")
+steady = torch.zeros((a.height, a.width, 3), dtype=torch.float32, device="cuda")
+params = integ.make_params(a.spp, a.spp, 0)
+st = torch.cuda.current_stream()
+for _ in range(3):
+    _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(), None, st.cuda_stream))
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(), None, st.cuda_stream))
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+print(f"{os.environ.get('MITRANSIENT_B200_LIB', 'default'):40s} {ms:8.3f} ms/step  "
+      f"{a.width * a.height * a.spp / ms / 1e3:9.1f} M-paths/s  film.sum={film.sum().item():.6e}")
