@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 4
+#define TR_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -87,6 +87,9 @@ typedef struct TrEmitterDesc {
     float radiance[3];   /* area: radiance; projector: irradiance                           */
     float fov_x;         /* projector: horizontal field of view, degrees                    */
     float to_world[12];  /* projector: row-major 3x4 affine (origin + orientation)          */
+    float world_to_local[12];    /* projector: inverse of to_world (row-major 3x4 affine)       */
+    float camera_to_sample[16];  /* projector: Mitsuba's perspective_projection(1x1, fov_x, 1e-4,
+                                    1e4): local space -> [0,1]^2 texture coordinates            */
     float _pad[2];
 } TrEmitterDesc;
 
@@ -177,9 +180,8 @@ typedef struct TrRenderParams {
     /* transient_nlos_path */
     int32_t capture_type;   /* TR_CAPTURE_*                                                 */
     int32_t filter_depth;   /* -1 = off                                                     */
-    float laser_target[3];  /* `single` capture: illuminated relay-wall point (set by the
-                               host, cf. transientnlospath.py:328-336)                      */
-    uint32_t _reserved[4];
+    uint32_t _reserved[7];  /* (the `single` laser target and the per-pixel sensor targets,
+                               transientnlospath.py:295-339, are traced on the device)      */
 } TrRenderParams;
 
 /* Exact work counters; identical integers are produced by the CPU oracle, which makes

@@ -16,12 +16,14 @@ from . import films, integrators, sensors            # registers the plugins
 from ._lib import TransientError, lib_path
 from .films.transient_hdr_film import TransientHDRFilm
 from .integrators.common import TransientADIntegrator
+from .integrators.transientnlospath import CaptureType, TransientNLOSPath
 from .integrators.transientpath import TransientPath
+from . import nlos
 from .plugins import register_film, register_integrator, register_sensor
-from .scene import Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
+from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
 from .sensors.nloscapturemeter import NLOSCaptureMeter
 from .transforms import ScalarTransform4f
-from .utils import cornell_box, cornell_box_config, speed_of_light
+from .utils import cornell_box, cornell_box_config, letter_z_mesh, nlos_z_scene, speed_of_light
 
 __version__ = "0.1.0"
 

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 4
+TR_ABI_VERSION = 5
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -46,7 +46,8 @@ class TrBsdfDesc(C.Structure):
 
 class TrEmitterDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("shape", C.c_int32), ("radiance", C.c_float * 3), ("fov_x", C.c_float),
-                ("to_world", C.c_float * 12), ("_pad", C.c_float * 2)]
+                ("to_world", C.c_float * 12), ("world_to_local", C.c_float * 12), ("camera_to_sample", C.c_float * 16),
+                ("_pad", C.c_float * 2)]
 
 
 class TrMediumDesc(C.Structure):
@@ -79,8 +80,7 @@ class TrRenderParams(C.Structure):
                 ("flags", C.c_uint32), ("spp", C.c_uint32), ("total_spp", C.c_uint32), ("seed", C.c_uint32),
                 ("tile_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
                 ("film_channels", C.c_int32), ("accumulate", C.c_int32),
-                ("capture_type", C.c_int32), ("filter_depth", C.c_int32), ("laser_target", C.c_float * 3),
-                ("_reserved", C.c_uint32 * 4)]
+                ("capture_type", C.c_int32), ("filter_depth", C.c_int32), ("_reserved", C.c_uint32 * 7)]
 
 
 class TrCounters(C.Structure):

@@ -214,6 +214,7 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
 
     // ---- shapes (+ area pmf / cdf tables for meshes)
     std::vector<DevShape> shapes(ns);
+    std::vector<float> shape_rect_area(ns, 0.0f);
     std::vector<unsigned char> sampling;  // per mesh shape: pmf[n] | cdf[n]
     for (uint32_t s = 0; s < ns; ++s) {
         const TrShapeDesc &sd = desc->shapes[s];
@@ -234,7 +235,8 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             H3 dpdu = hxf_vector(sd.to_world, h3(2.0f, 0.0f, 0.0f));
             H3 dpdv = hxf_vector(sd.to_world, h3(0.0f, 2.0f, 0.0f));
             H3 c = hcross(dpdu, dpdv);
-            d.inv_area = 1.0f / sqrtf(hdot(c, c));
+            shape_rect_area[s] = sqrtf(hdot(c, c));
+            d.inv_area = 1.0f / shape_rect_area[s];
             const DevPrim &t0 = prims[sd.prim_begin];
             H3 n = h3(t0.n[0], t0.n[1], t0.n[2]);
             float dd = hdot(n, dpdu);
@@ -315,6 +317,16 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             if (prims[i].lim > 0.0f) memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims[i], sizeof(DevPrim));
     }
     out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
+    out.shapes.assign(desc->shapes, desc->shapes + ns);
+    out.emitters.assign(desc->emitters, desc->emitters + desc->n_emitters);
+    out.shape_area.resize(ns);
+    for (uint32_t s = 0; s < ns; ++s)   // Shape::surface_area(): rectangle |dp_du x dp_dv|, mesh = sum of primitive areas
+        out.shape_area[s] = (shapes[s].type == TR_SHAPE_RECTANGLE) ? shape_rect_area[s] : shapes[s].area_sum;
+    if (desc->sensor.type == TR_SENSOR_NLOS_CAPTURE_METER) {
+        if (desc->sensor.shape < 0 || (uint32_t) desc->sensor.shape >= ns || desc->shapes[desc->sensor.shape].type != TR_SHAPE_RECTANGLE) {
+            err = "nlos_capture_meter must be attached to a rectangle shape"; return false;
+        }
+    } else if (desc->sensor.type != TR_SENSOR_PERSPECTIVE) { err = "unknown sensor type"; return false; }
     return true;
 }
 
@@ -345,6 +357,7 @@ void tr_scene_destroy(TrScene *scene) {
     if (scene->impl.d_blob) cudaFree(scene->impl.d_blob);
     if (scene->impl.d_pixels) cudaFree(scene->impl.d_pixels);
     if (scene->impl.d_scratch) cudaFree(scene->impl.d_scratch);
+    if (scene->impl.d_nlos) cudaFree(scene->impl.d_nlos);
     delete scene;
 }
 

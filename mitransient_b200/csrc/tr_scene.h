@@ -88,6 +88,10 @@ struct SceneImpl {
     void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;
     // scratch for counters / work queue
     void *d_scratch = nullptr;
+    // host copies used by the NLOS prepare step (transientnlospath.py:251-383)
+    std::vector<TrShapeDesc> shapes; std::vector<TrEmitterDesc> emitters; std::vector<float> shape_area;
+    void *d_nlos = nullptr;              // float4 targets[H*W + 1] | float hg_table[2 * n_shapes]
+    uint32_t nlos_key = 0xffffffffu; float hg_sum = 0.f, hg_norm = 0.f;
 };
 
 bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err);

@@ -15,6 +15,8 @@ from ..scene import Properties
 
 
 class TransientHDRFilm:
+    plugin_name = "transient_hdr_film"
+
     def __init__(self, props: Properties):
         # base mi.Film parameters (transient_hdr_film.py:104-111)
         self._width = int(props.get("width", 768))

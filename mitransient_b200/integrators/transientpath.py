@@ -12,6 +12,7 @@ from .common import TransientADIntegrator
 
 class TransientPath(TransientADIntegrator):
     integrator_id = _abi.TR_INTEGRATOR_TRANSIENT_PATH
+    plugin_name = "transient_path"
 
     def check_scene_(self, scene, sensor):
         if not isinstance(sensor, PerspectiveSensor):

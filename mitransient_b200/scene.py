@@ -6,7 +6,7 @@ understands the subset of the dictionary format the hot path's configurations us
 triangles + shape/bsdf/emitter tables + one sensor/film (include/mitransient_b200.h).
 
 Supported plugin types
-  shapes     rectangle, cube, obj (v / f records; ``l`` records are ignored)
+  shapes     rectangle, cube, obj (v / f records; ``l`` records are ignored), trimesh (in-memory arrays)
   bsdfs      diffuse, twosided(diffuse), null, ref
   emitters   area (nested in a shape), projector (top level; transient_nlos_path's laser)
   sensors    perspective, nlos_capture_meter (nested in the relay-wall shape)
@@ -128,6 +128,64 @@ def _to_transform(v) -> ScalarTransform4f:
     return ScalarTransform4f(np.asarray(v, dtype=np.float64))
 
 
+# ------------------------------------------------------------------------------------ deferred plugins
+_SHAPE_TYPES = ("rectangle", "cube", "obj", "trimesh")
+_BSDF_TYPES = ("diffuse", "twosided", "null")
+
+
+class PluginSpec(dict):
+    """What ``load_dict`` returns for a shape / emitter / bsdf / medium dictionary: the dictionary itself, kept
+    until a scene is assembled (the reference builds its NLOS scenes this way: ``geometry = mi.load_dict({...})``
+    first, ``mi.load_dict({'type': 'scene', 'geometry': geometry, ...})`` later).  Mutable on purpose: e.g.
+    ``mitransient_b200.nlos.focus_emitter_at_relay_wall_pixel`` rewrites a projector's ``to_world``."""
+
+    def plugin_type(self):
+        return self.get("type")
+
+    # -- the bits of the mi.Shape / mi.Emitter interface the reference's helpers use
+    def world_transform(self) -> ScalarTransform4f:
+        return _to_transform(self.get("to_world"))
+
+    def sensor(self):
+        """The sensor attached to this shape (instantiated once, shared with the scene)."""
+        for k, v in self.items():
+            if _type_of(v) == "nlos_capture_meter":
+                if isinstance(v, dict):
+                    from . import plugins
+                    v = plugins.instantiate(v)
+                    self[k] = v
+                return v
+        raise ValueError("this shape carries no sensor")
+
+    def sample_position(self, time, uv, active=True):
+        """Shape::sample_position for a `rectangle`: to_world * (2u - 1, 2v - 1, 0)."""
+        if self.get("type") != "rectangle":
+            raise NotImplementedError("sample_position is provided for rectangles (the relay wall)")
+        p = self.world_transform().transform_affine([2.0 * float(uv[0]) - 1.0, 2.0 * float(uv[1]) - 1.0, 0.0])
+
+        class _PS:
+            pass
+        ps = _PS()
+        ps.p = p
+        return ps
+
+
+def _type_of(v):
+    if isinstance(v, dict):
+        return v.get("type")
+    return getattr(v, "plugin_name", None)
+
+
+def _find_child(d, types):
+    """First nested plugin (dictionary or instance, under ANY key) whose type is in ``types``."""
+    for k, v in d.items():
+        if k in ("interior", "exterior"):
+            continue
+        if _type_of(v) in types:
+            return k, v
+    return None, None
+
+
 # ------------------------------------------------------------------------------------ host-side scene objects
 class Shape:
     def __init__(self, name, kind, prims, prim_types, to_world, bsdf_index, flip=False):
@@ -201,8 +259,15 @@ class Scene:
         for i, e in enumerate(self.emitters_):
             emitters[i].type, emitters[i].shape = e["type"], e["shape"]
             emitters[i].radiance[:] = [float(x) for x in e["radiance"]]
-            emitters[i].fov_x = float(e.get("fov_x", 0.0))
-            emitters[i].to_world[:] = e.get("to_world", ScalarTransform4f()).affine3x4().reshape(-1).tolist()
+            spec = e.get("spec")
+            if spec is not None:      # projector: read the CURRENT state (nlos.focus_* may have re-aimed it)
+                emitters[i].radiance[:] = [float(x) for x in _rgb(spec.get("irradiance"), 1.0) * float(spec.get("scale", 1.0))]
+                emitters[i].fov_x = float(parse_fov(float(spec.get("fov", 45.0)), spec.get("fov_axis", "x"), 1.0))
+                tw = _to_transform(spec.get("to_world"))
+                emitters[i].to_world[:] = tw.affine3x4().reshape(-1).tolist()
+                emitters[i].world_to_local[:] = tw.inverse().affine3x4().reshape(-1).tolist()
+                c2s = perspective_projection((1, 1), (1, 1), (0, 0), float(emitters[i].fov_x), 1e-4, 1e4)
+                emitters[i].camera_to_sample[:] = c2s.matrix.astype(np.float32).reshape(-1).tolist()
         media = (_abi.TrMediumDesc * max(1, len(self.media_)))()
         for i, m in enumerate(self.media_):
             media[i].sigma_t[:] = [float(x) for x in m["sigma_t"]]
@@ -225,8 +290,9 @@ class Scene:
 
     def description_key(self, sensor):
         f = sensor.film()
+        em = tuple(_to_transform(e["spec"].get("to_world")).matrix.tobytes() for e in self.emitters_ if e.get("spec"))
         return (id(sensor), f.size(), f.temporal_bins, float(f.start_opl), float(f.bin_width_opl),
-                sensor.state_key())
+                sensor.state_key(), em)
 
     def __repr__(self):
         return (f"Scene[shapes={len(self.shapes_)}, primitives={sum(len(s.prims) for s in self.shapes_)}, "
@@ -298,7 +364,11 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
 
     t = d.get("type")
     if t != "scene":
-        return plugins.instantiate(d)
+        if t in plugins.INTEGRATORS or t in plugins.FILMS or t in plugins.SENSORS:
+            return plugins.instantiate(d)
+        if t in _SHAPE_TYPES or t in _BSDF_TYPES or t in ("projector", "area", "homogeneous", "perspective"):
+            return PluginSpec(d)
+        raise ValueError(f"load_dict(): unsupported plugin type {t!r}")
 
     scene = Scene()
     named_bsdf: Dict[str, int] = {}
@@ -316,8 +386,10 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
         flags = 0
         bt = spec.get("type")
         if bt == "twosided":
-            inner = spec.get("bsdf") or next(v for k, v in spec.items() if isinstance(v, dict))
-            if isinstance(inner, dict) and inner.get("type") == "ref":
+            _, inner = _find_child(spec, _BSDF_TYPES + ("ref",))
+            if inner is None:
+                raise ValueError("twosided bsdf without a nested bsdf")
+            if inner.get("type") == "ref":
                 inner = d[inner["id"]]
             flags |= _abi.TR_BSDF_FLAG_TWOSIDED
             spec, bt = inner, inner.get("type")
@@ -356,27 +428,28 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
             named_medium[key] = add_medium(val)
 
     for key, val in d.items():
-        if not isinstance(val, dict):
+        t = _type_of(val)
+        if t is None:
             continue
-        t = val.get("type")
-        if t in ("rectangle", "cube", "obj"):
+        if t in _SHAPE_TYPES:
             to_world = _to_transform(val.get("to_world"))
             flip = bool(val.get("flip_normals", False))
             if t == "rectangle":
                 base, ptypes = _rectangle_prims()
             elif t == "cube":
                 base, ptypes = _cube_prims()
+            elif t == "trimesh":   # in-memory triangle mesh (no Mitsuba counterpart): vertices (N,3), faces (M,3)
+                v = np.asarray(val["vertices"], dtype=np.float64).reshape(-1, 3)
+                f = np.asarray(val["faces"], dtype=np.int64).reshape(-1, 3)
+                base = v[f]
+                ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
             else:
                 fn = val["filename"]
                 if not os.path.isabs(fn) and base_dir:
                     fn = os.path.join(base_dir, fn)
                 base = load_obj(fn)
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
-            bspec = val.get("bsdf")
-            if bspec is None:
-                bspec = next((v for k, v in val.items() if isinstance(v, dict) and
-                              v.get("type") in ("diffuse", "twosided", "null", "ref") and k not in
-                              ("interior", "exterior")), None)
+            _, bspec = _find_child(val, _BSDF_TYPES + ("ref",))
             if bspec is None:
                 if default_bsdf is None:
                     default_bsdf = add_bsdf({"type": "diffuse"})
@@ -390,37 +463,39 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 shape.exterior_medium = add_medium(val["exterior"])
             scene.shapes_.append(shape)
             sidx = len(scene.shapes_) - 1
-            em = val.get("emitter")
+            _, em = _find_child(val, ("area",))
             if em is not None:
-                if em.get("type") != "area":
-                    raise ValueError(f"unsupported shape emitter {em.get('type')!r} (supported: area)")
                 scene.emitters_.append({"type": _abi.TR_EMITTER_AREA, "shape": sidx,
                                         "radiance": _rgb(em.get("radiance"), 1.0)})
                 shape.emitter_index = len(scene.emitters_) - 1
-            se = val.get("sensor")
+            bad_k, bad = _find_child(val, ("projector", "point", "spot", "constant", "envmap"))
+            if bad is not None:
+                raise ValueError(f"unsupported shape emitter {_type_of(bad)!r} (supported: area)")
+            sk, se = _find_child(val, tuple(plugins.SENSORS))
             if se is not None:
-                if se.get("type") != "nlos_capture_meter":
-                    raise ValueError("only nlos_capture_meter sensors can be attached to a shape")
+                if isinstance(se, dict):
+                    se = plugins.instantiate(se)
+                    val[sk] = se          # share the instance with PluginSpec.sensor()
                 shape.is_sensor = True
-                sensor = plugins.instantiate(se)
-                sensor.set_shape(sidx, shape)
-                scene.sensors_.append(sensor)
+                se.set_shape(sidx, shape)
+                scene.sensors_.append(se)
         elif t == "projector":
-            to_world = _to_transform(val.get("to_world"))
-            scene.emitters_.append({"type": _abi.TR_EMITTER_PROJECTOR, "shape": -1,
-                                    "radiance": _rgb(val.get("irradiance"), 1.0),
-                                    "fov_x": float(val.get("fov", 45.0)), "to_world": to_world})
-        elif t in ("perspective",):
-            film = plugins.instantiate(val["film"]) if "film" in val else plugins.instantiate(
-                {"type": "transient_hdr_film"})
-            sampler = IndependentSampler(Properties(val.get("sampler", {})))
+            spec = val if isinstance(val, PluginSpec) else PluginSpec(val)
+            scene.emitters_.append({"type": _abi.TR_EMITTER_PROJECTOR, "shape": -1, "spec": spec,
+                                    "radiance": _rgb(spec.get("irradiance"), 1.0)})
+        elif t == "perspective":
+            _, fspec = _find_child(val, tuple(plugins.FILMS))
+            film = fspec if (fspec is not None and not isinstance(fspec, dict)) else plugins.instantiate(
+                fspec if fspec is not None else {"type": "transient_hdr_film"})
+            _, sspec = _find_child(val, ("independent",))
+            sampler = IndependentSampler(Properties(sspec or {}))
             sensor = PerspectiveSensor(Properties(val), film, sampler)
             if "medium" in val:
                 sensor.medium = add_medium(val["medium"])
             scene.sensors_.append(sensor)
         elif t in plugins.INTEGRATORS:
-            scene.integrator_ = plugins.instantiate(val)
-        elif t in ("diffuse", "twosided", "null", "homogeneous", "scene"):
+            scene.integrator_ = val if not isinstance(val, dict) else plugins.instantiate(val)
+        elif t in _BSDF_TYPES or t in ("homogeneous", "scene"):
             pass
         else:
             raise ValueError(f"load_dict(): unsupported plugin type {t!r} for key {key!r}")

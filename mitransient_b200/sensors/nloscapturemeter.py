@@ -14,6 +14,8 @@ class NLOSSensor:          # mitransient/sensors/nlossensor.py:5-10
 
 
 class NLOSCaptureMeter(NLOSSensor):
+    plugin_name = "nlos_capture_meter"
+
     def __init__(self, props: Properties):
         from .. import plugins
         self.needs_sample_3 = False
@@ -26,8 +28,14 @@ class NLOSCaptureMeter(NLOSSensor):
         self._world_transform = ScalarTransform4f().translate(origin)
         self.laser_bounce_opl = 0.0
         self.laser_target = np.zeros(3)
-        self._film = plugins.instantiate(props.get("film", {"type": "transient_hdr_film"}))
-        self._sampler = IndependentSampler(Properties(props.get("sampler", {})))
+        # nested plugins are found by TYPE, under any key (the notebooks use "transient_film", the XML "film")
+        from ..scene import _find_child
+        _, fspec = _find_child(props, tuple(plugins.FILMS))
+        if fspec is None:
+            fspec = {"type": "transient_hdr_film"}
+        self._film = fspec if not isinstance(fspec, dict) else plugins.instantiate(fspec)
+        _, sspec = _find_child(props, ("independent",))
+        self._sampler = IndependentSampler(Properties(sspec or {}))
         self.original_film_width = props.get("original_film_width", None)
         self.original_film_height = props.get("original_film_height", None)
         if self.original_film_width is None or self.original_film_height is None:

@@ -76,3 +76,47 @@ def indent(obj, amount=2):
     if len(lines) <= 1:
         return "".join(lines)
     return "".join(line + " " * amount for line in lines)
+
+
+def letter_z_mesh(half=0.4, bar=0.1, z=0.0):
+    """A flat letter "Z" (two bars + a diagonal, 6 triangles) in the plane ``z``, facing -z -- a procedural
+    stand-in for the reference's examples/transient-nlos/Z.obj hidden object."""
+    import numpy as np
+    h, b = float(half), float(bar)
+    quads = [
+        [(-h, h - b), (h, h - b), (h, h), (-h, h)],                       # top bar
+        [(-h, -h), (h, -h), (h, -h + b), (-h, -h + b)],                   # bottom bar
+        [(-h, -h + b), (-h + 2.4 * b, -h + b), (h, h - b), (h - 2.4 * b, h - b)],   # diagonal
+    ]
+    verts, faces = [], []
+    for q in quads:
+        i = len(verts)
+        verts += [(x, y, z) for x, y in q]
+        faces += [(i, i + 2, i + 1), (i, i + 3, i + 2)]                   # clockwise seen from +z: normal -z
+    return np.array(verts, dtype=np.float64), np.array(faces, dtype=np.int64)
+
+
+def nlos_z_scene(width=64, height=64, temporal_bins=300, spp=1000, start_opl=1.85, window=1.8, capture_type="confocal",
+                 **integrator):
+    """The NLOS "letter Z" setup of examples/transient-nlos/1-simple-nlos-scenes.ipynb (cells 3, 17): hidden Z at
+    z = 1 facing the unit relay wall at z = 0, laser and sensor at (-0.5, 0, 0.25)."""
+    v, f = letter_z_mesh()
+    integ = {"type": "transient_nlos_path", "nlos_laser_sampling": True, "nlos_hidden_geometry_sampling": True,
+             "nlos_hidden_geometry_sampling_do_rroulette": False, "account_first_and_last_bounces": False,
+             "capture_type": capture_type, "temporal_filter": "box"}
+    integ.update(integrator)
+    return {
+        "type": "scene",
+        "geometry": {"type": "trimesh", "vertices": v, "faces": f, "to_world": T().translate([0.0, 0.0, 1.0]),
+                     "bsdf": {"type": "diffuse", "reflectance": 1.0}},
+        "emitter": {"type": "projector", "irradiance": 100.0, "fov": 0.2, "to_world": T().translate([-0.5, 0.0, 0.25])},
+        "relay_wall": {"type": "rectangle", "bsdf": {"type": "diffuse", "reflectance": 1.0},
+                       "nlos_sensor": {"type": "nlos_capture_meter",
+                                       "sampler": {"type": "independent", "sample_count": int(spp)},
+                                       "sensor_origin": [-0.5, 0.0, 0.25],
+                                       "transient_film": {"type": "transient_hdr_film", "width": int(width),
+                                                          "height": int(height), "temporal_bins": int(temporal_bins),
+                                                          "bin_width_opl": float(window) / int(temporal_bins),
+                                                          "start_opl": float(start_opl), "rfilter": {"type": "box"}}}},
+        "integrator": integ,
+    }

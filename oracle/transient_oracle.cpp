@@ -146,6 +146,7 @@ struct Shape {
     std::vector<float> pmf;    // mesh: primitive areas (unnormalised pmf)
     std::vector<float> cdf;    // mesh: running area sums (float, accumulated in double)
     float area_sum, area_norm; // DiscreteDistribution m_sum / m_normalization
+    float area;                // Shape::surface_area()
 };
 struct Scene {
     std::vector<Prim> prims;
@@ -253,9 +254,11 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
             V3 dpdu = xf_vector(sh.d.to_world, v3(2.0f, 0.0f, 0.0f));
             V3 dpdv = xf_vector(sh.d.to_world, v3(0.0f, 2.0f, 0.0f));
             V3 c = cross(dpdu, dpdv);
-            sh.inv_area = 1.0f / sqrtf(dot(c, c));
+            sh.area = sqrtf(dot(c, c));
+            sh.inv_area = 1.0f / sh.area;
             sh.n = sh.d.prim_count ? sc.prims[sh.d.prim_begin].n : v3(0, 0, 1);
         } else {
+            sh.area = sh.area_sum;
             sh.inv_area = sh.area_norm;
             sh.n = v3(0, 0, 0);
         }
@@ -584,10 +587,243 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
     return L;
 }
 
+
+// =============================================================================================
+//  transient_nlos_path  (mitransient/integrators/transientnlospath.py) + nlos_capture_meter
+//  (mitransient/sensors/nloscapturemeter.py).  Single and Confocal captures; Exhaustive and AD
+//  are out of scope.
+// =============================================================================================
+constexpr float kEps = 5.9604644775390625e-08f;   // dr.epsilon(Float) = 2^-24
+
+struct NlosCtx {
+    const TrEmitterDesc *em; V3 em_origin, em_forward;
+    std::vector<V3> sensor_targets; V3 laser_target_single; bool laser_single_valid;
+    std::vector<float> hg_pmf, hg_cdf; float hg_sum, hg_norm;   // DiscreteDistribution over shapes (:277-292)
+    uint32_t sensor_shape;
+};
+
+// NLOSCaptureMeter._sample_direction + sample_ray(_differential)   nloscapturemeter.py:136-202
+inline Ray nlos_sensor_ray(const Scene &sc, float sx, float sy) {
+    const Shape &wall = sc.shapes[sc.sensor.shape];
+    float Wf = (float) sc.film.width, Hf = (float) sc.film.height;
+    float gx = (floorf(sx * Wf) + 0.5f) / Wf, gy = (floorf(sy * Hf) + 0.5f) / Hf;           // :149-150
+    V3 target = xf_point(wall.d.to_world, fmaf(gx, 2.0f, -1.0f), fmaf(gy, 2.0f, -1.0f), 0.0f);   // :151-153
+    V3 origin = v3(sc.sensor.origin[0], sc.sensor.origin[1], sc.sensor.origin[2]);
+    V3 dir = target - origin;                                                                  // :155-157
+    float dist = sqrtf(dot(dir, dir));
+    dir = dir * (1.0f / dist);
+    return Ray{origin, dir, std::numeric_limits<float>::max()};
+}
+
+// TransientNLOSPath.prepare   transientnlospath.py:251-383
+bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::string &err) {
+    if (sc.emitters.size() != 1 || sc.emitters[0].type != TR_EMITTER_PROJECTOR) { err = "transient_nlos_path needs exactly one projector emitter"; return false; }
+    if (sc.sensor.type != TR_SENSOR_NLOS_CAPTURE_METER || sc.sensor.shape < 0 || (uint32_t) sc.sensor.shape >= sc.shapes.size() ||
+        sc.shapes[sc.sensor.shape].d.type != TR_SHAPE_RECTANGLE) { err = "transient_nlos_path needs an nlos_capture_meter on a rectangle"; return false; }
+    if (rp.capture_type != TR_CAPTURE_SINGLE && rp.capture_type != TR_CAPTURE_CONFOCAL) { err = "capture type not implemented"; return false; }
+    ctx.em = &sc.emitters[0];
+    const float *m = ctx.em->to_world;
+    ctx.em_origin = v3(m[3], m[7], m[11]);
+    ctx.em_forward = v3(m[2], m[6], m[10]);                   // trafo @ Vector3f(0, 0, 1)
+    ctx.sensor_shape = (uint32_t) sc.sensor.shape;
+    // hidden-geometry area distribution :277-292
+    ctx.hg_pmf.clear(); ctx.hg_cdf.clear();
+    double acc = 0.0;
+    for (uint32_t i = 0; i < sc.shapes.size(); ++i) {
+        bool wall = (sc.shapes[i].d.flags & TR_SHAPE_FLAG_SENSOR) != 0;
+        float a = (wall && !(rp.flags & TR_FLAG_NLOS_HG_SAMPLING_INCLUDES_RELAY_WALL)) ? 0.0f : sc.shapes[i].area;
+        acc += (double) a; ctx.hg_pmf.push_back(a); ctx.hg_cdf.push_back((float) acc);
+    }
+    ctx.hg_sum = (float) acc; ctx.hg_norm = (float) (1.0 / acc);
+    if ((rp.flags & TR_FLAG_NLOS_HG_SAMPLING) && !(acc > 0.0)) { err = "hidden geometry sampling without hidden geometry"; return false; }
+    // one sensor ray per film pixel -> scanned points :295-312
+    const uint32_t W = sc.film.width, H = sc.film.height;
+    ctx.sensor_targets.resize((size_t) W * H);
+    float stepx = 1.0f / (float) W, stepy = 1.0f / (float) H;     // dr.linspace(0, 1, n, endpoint=False)
+    for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x) {
+        Hit h = ray_intersect(sc, nlos_sensor_ray(sc, fmaf((float) x, stepx, 0.0f), fmaf((float) y, stepy, 0.0f)));
+        ctx.sensor_targets[(size_t) y * W + x] = h.p;             // si.p (zeros when the ray misses)
+    }
+    // Single capture: where the laser axis meets the scene :328-336
+    Hit hl = ray_intersect(sc, Ray{ctx.em_origin, ctx.em_forward, std::numeric_limits<float>::max()});
+    ctx.laser_target_single = hl.p; ctx.laser_single_valid = hl.valid;
+    if (rp.capture_type == TR_CAPTURE_SINGLE && (rp.flags & TR_FLAG_NLOS_LASER_SAMPLING) && !hl.valid) { err = "The emitter is not pointing at the scene!"; return false; }
+    return true;
+}
+
+// diffuse (optionally twosided) bsdf.eval:  R/pi * cos_o  iff both cosines are positive
+inline V3 bsdf_eval(const TrBsdfDesc &b, float cos_i, float cos_o) {
+    if (b.type != TR_BSDF_DIFFUSE) return v3(0, 0, 0);
+    if ((b.flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f) { cos_i = -cos_i; cos_o = -cos_o; }
+    if (!(cos_i > 0.0f && cos_o > 0.0f)) return v3(0, 0, 0);
+    return (v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * kInvPi) * cos_o;
+}
+
+// Projector::sample_direction [upstream projector.cpp]: delta position, perspective uv lookup, weight
+// irradiance * pi / (z_local^2 * cos(axis, -d)); pdf = 1.
+inline V3 projector_sample_direction(const TrEmitterDesc &em, V3 itp, V3 *ds_p, float *ds_dist) {
+    V3 loc = xf_point(em.world_to_local, itp.x, itp.y, itp.z);
+    const float *c = em.camera_to_sample;
+    float sx = fmaf(c[0], loc.x, fmaf(c[1], loc.y, fmaf(c[2], loc.z, c[3])));
+    float sy = fmaf(c[4], loc.x, fmaf(c[5], loc.y, fmaf(c[6], loc.z, c[7])));
+    float sw = fmaf(c[12], loc.x, fmaf(c[13], loc.y, fmaf(c[14], loc.z, c[15])));
+    float iw = 1.0f / sw;
+    float u = sx * iw, v = sy * iw;
+    bool active = (u >= 0.0f) && (u <= 1.0f) && (v >= 0.0f) && (v <= 1.0f) && (loc.z > 0.0f);
+    V3 p = v3(em.to_world[3], em.to_world[7], em.to_world[11]);
+    V3 n = v3(em.to_world[2], em.to_world[6], em.to_world[10]);
+    V3 d = p - itp;
+    float dist = sqrtf(dot(d, d));
+    d = d * (1.0f / dist);
+    *ds_p = p; *ds_dist = dist;
+    if (!active) return v3(0, 0, 0);
+    float f = kPi / ((loc.z * loc.z) * (-dot(n, d)));
+    return v3(em.radiance[0], em.radiance[1], em.radiance[2]) * f;
+}
+
+struct NlosVertex { V3 p, n; float cos_i; const TrBsdfDesc *bsdf; };
+
+// emitter_nee_sample   transientnlospath.py:433-509
+V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
+                           V3 beta, float distance, float eta, uint32_t depth, bool active_e, bool focus_laser,
+                           float px, float py, float sample_scale, Film &film) {
+    if (!active_e) return v3(0, 0, 0);
+    film.cnt->shadow_rays++;
+    if (ray_test(sc, spawn_ray_to(vx.p, vx.n, ctx.em_origin))) return v3(0, 0, 0);             // :442
+    V3 query = vx.p;
+    if (focus_laser && rp.capture_type == TR_CAPTURE_CONFOCAL) {                              // :448-458
+        V3 rel = ctx.em_origin - vx.p;
+        float dte = sqrtf(dot(rel, rel));
+        query = fma3(ctx.em_forward, dte, ctx.em_origin);
+    }
+    rng.next_1d(); rng.next_1d();                                                             // sampler.next_2d(active_e)
+    V3 dsp; float ds_dist;
+    V3 em_weight = projector_sample_direction(*ctx.em, query, &dsp, &ds_dist);
+    V3 wd = normalize(dsp - vx.p);                                                            // :484
+    V3 bsdf_spec = bsdf_eval(*vx.bsdf, vx.cos_i, dot(wd, vx.n));
+    if (rp.filter_depth != -1) active_e = active_e && ((int32_t) depth == rp.filter_depth);   // :489-490
+    if (rp.flags & TR_FLAG_DISCARD_DIRECT_PATHS) active_e = active_e && (depth > 2);          // :491-492
+    V3 Lr = active_e ? (beta * bsdf_spec) * em_weight : v3(0, 0, 0);                          // :493
+    if (rp.flags & TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES) distance += ds_dist * eta;         // :497-498
+    film.add_transient(px, py, Lr, distance, sample_scale, 1.0f);                             // :506-507
+    return Lr;
+}
+
+// emitter_laser_sample -> emitter_laser_targets_sample   transientnlospath.py:567-635, 512-564
+V3 nlos_emitter_laser_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
+                             V3 beta, float distance, float eta, uint32_t depth, bool active_e, uint32_t pixel_index,
+                             float px, float py, float sample_scale, Film &film) {
+    if (!active_e) return v3(0, 0, 0);
+    V3 target = (rp.capture_type == TR_CAPTURE_CONFOCAL) ? ctx.sensor_targets[pixel_index] : ctx.laser_target_single;  // :588-596
+    depth += 1;                                                                               // :635 (depth+1)
+    V3 d = target - vx.p;                                                                     // :526
+    float dl = sqrtf(dot(d, d));
+    if (!(dl > 0.0f)) return v3(0, 0, 0);     // confocal depth-0 vertex: target == si.p, NaN direction in the reference (:526-528, :545)
+    d = d * (1.0f / dl);
+    Ray ray_bsdf = spawn_ray_to(vx.p, vx.n, target);                                          // :529
+    film.cnt->shadow_rays++;
+    if (ray_test(sc, ray_bsdf)) return v3(0, 0, 0);                                           // :530
+    V3 bsdf_spec = bsdf_eval(*vx.bsdf, vx.cos_i, dot(d, vx.n));                               // :533-535
+    ray_bsdf.maxt = std::numeric_limits<float>::max();                                        // :537
+    Hit sb = ray_intersect(sc, ray_bsdf);                                                     // :538-540
+    if (!sb.valid) return v3(0, 0, 0);
+    if (!(bsdf_spec.x > kEps || bsdf_spec.y > kEps || bsdf_spec.z > kEps)) return v3(0, 0, 0);   // :541-542
+    float cos_wl = -dot(d, sb.n);                                                             // :544
+    if (!(cos_wl > 0.0f)) return v3(0, 0, 0);                                                 // :545
+    float pdf_ls = (dl * dl) / cos_wl;                                                        // :546-550
+    bsdf_spec = v3(bsdf_spec.x / pdf_ls, bsdf_spec.y / pdf_ls, bsdf_spec.z / pdf_ls);         // :551
+    NlosVertex vb{sb.p, sb.n, -dot(ray_bsdf.d, sb.n), &sc.bsdfs[sc.shapes[sb.shape].d.bsdf]}; // :553
+    return nlos_emitter_nee_sample(sc, rp, ctx, rng, vb, beta * bsdf_spec, distance + dl * eta, eta, depth + 1, true, true,
+                                   px, py, sample_scale, film);                               // :560-564
+}
+
+V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, Ray ray, uint32_t pixel_index,
+                   float px, float py, float sample_scale, Film &film) {
+    const bool laser_sampling = (rp.flags & TR_FLAG_NLOS_LASER_SAMPLING) != 0;
+    const bool hg_sampling = (rp.flags & TR_FLAG_NLOS_HG_SAMPLING) != 0;
+    const bool hg_rr = (rp.flags & TR_FLAG_NLOS_HG_SAMPLING_DO_RROULETTE) != 0 && hg_sampling;
+    const bool account_fl = (rp.flags & TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES) != 0;
+    uint32_t depth = 0; V3 L = v3(0, 0, 0), beta = v3(1, 1, 1); float eta = 1.0f; bool active = true;
+    float distance = 0.0f;                                                                    // ray.time  :718
+
+    for (uint32_t it = 0; active && it < rp.max_depth; ++it) {                                // :738-740
+        film.cnt->vertices++;
+        Hit si = ray_intersect(sc, ray);                                                      // :746-749
+        if (account_fl || depth > 0) distance += si.t * eta;                                  // :751-752
+        // direct emission :757-777: the only emitter is the (delta) projector, no shape emits: Le = 0
+        bool active_next = active && (depth + 1 < rp.max_depth) && si.valid;                  // :781
+        const TrBsdfDesc *bsdf = si.valid ? &sc.bsdfs[sc.shapes[si.shape].d.bsdf] : nullptr;
+        bool smooth = bsdf && bsdf->type == TR_BSDF_DIFFUSE;
+        bool active_em = active_next && smooth;                                               // :784-785
+        float cos_i = si.valid ? -dot(ray.d, si.n) : 0.0f;
+        NlosVertex vx{si.p, si.n, cos_i, bsdf};
+        V3 Lr = laser_sampling                                                                // :733-736, :788-793
+            ? nlos_emitter_laser_sample(sc, rp, ctx, rng, vx, beta, distance, eta, depth, active_em, pixel_index, px, py, sample_scale, film)
+            : nlos_emitter_nee_sample(sc, rp, ctx, rng, vx, beta, distance, eta, depth, active_em, false, px, py, sample_scale, film);
+
+        // ---- direction sampling :797-827
+        bool do_hg = hg_sampling; float pdf_method = 1.0f;
+        if (hg_rr) { do_hg = rng.next_1d() < 0.5f; pdf_method = 0.5f; }                       // :799-806
+        float h1 = rng.next_1d(); (void) h1;                                                  // arguments of hidden_geometry_sample
+        float h2x = rng.next_1d(), h2y = rng.next_1d();                                       //   are drawn unconditionally (:814)
+        float b1 = rng.next_1d(); (void) b1;                                                  // arguments of bsdf.sample (:821)
+        float b2x = rng.next_1d(), b2y = rng.next_1d();
+        V3 weight = v3(0, 0, 0), wo = v3(0, 0, 0); float bs_pdf = 0.0f;
+        bool twoside_back = bsdf && (bsdf->flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f;
+        if (active_next && do_hg && hg_sampling) {                                            // hidden_geometry_sample :638-670
+            // DiscreteDistribution.sample_reuse_pmf over shapes :420-423
+            float value = h2x * ctx.hg_sum;
+            uint32_t lo = 0, hi = (uint32_t) ctx.hg_cdf.size() - 1;
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ctx.hg_cdf[mid] < value) lo = mid + 1; else hi = mid; }
+            float cdf_prev = lo ? ctx.hg_cdf[lo - 1] : 0.0f;
+            float pmf = ctx.hg_pmf[lo] * ctx.hg_norm;
+            float u0 = (h2x - cdf_prev * ctx.hg_norm) / pmf;
+            V3 pp, pn; float ppdf;
+            shape_sample_position(sc, sc.shapes[lo], u0, h2y, &pp, &pn, &ppdf);               // :427
+            ppdf *= pmf;                                                                      // :428
+            V3 d = pp - si.p;
+            float dist = sqrtf(dot(d, d));
+            d = d * (1.0f / dist);
+            float cos_ti = dot(si.n, d), cos_g = -dot(pn, d);                                 // :648-649
+            bool act = (cos_ti > kEps) && (cos_g > kEps);
+            wo = v3(dot(d, si.s), dot(d, si.tt), dot(d, si.n));                               // si.to_local(d)
+            V3 spec = smooth ? bsdf_eval(*bsdf, cos_i, wo.z) : v3(0, 0, 0);
+            bs_pdf = ppdf * (dist * dist) / fabsf(cos_g);                                     // :662
+            act = act && (bs_pdf > kEps);
+            if (act) weight = v3(spec.x / bs_pdf, spec.y / bs_pdf, spec.z / bs_pdf);
+        } else if (active_next && !do_hg && smooth) {                                         // bsdf.sample :819-824
+            wo = square_to_cosine_hemisphere(b2x, b2y);
+            bs_pdf = kInvPi * wo.z;
+            float ci = twoside_back ? -cos_i : cos_i;
+            if (ci > 0.0f && bs_pdf > 0.0f) weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+            if (twoside_back) wo.z = -wo.z;
+        }
+        // ---- update loop variables :831-841
+        L = L + Lr;
+        V3 wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));
+        if (si.valid) ray = spawn_ray(si.p, si.n, wo_world);
+        V3 bw = beta * weight;
+        beta = v3(bw.x / pdf_method, bw.y / pdf_method, bw.z / pdf_method);                   // :834
+        // ---- stopping criterion :846-858 (same as transient_path)
+        float beta_max = max3(beta);
+        active_next = active_next && (beta_max != 0.0f);
+        float rr_prob = fminf(beta_max * (eta * eta), 0.95f);
+        active_next = active_next && (rr_prob > 0.0f);
+        bool rr_active = depth >= rp.rr_depth;
+        if (rr_active) { float r = (rr_prob > 0.0f) ? (1.0f / rr_prob) : 0.0f; beta = beta * r; }
+        bool rr_continue = rng.next_1d() < rr_prob;
+        active_next = active_next && (!rr_active || rr_continue);
+        if (si.valid) depth += 1;                                                             // :919
+        active = active_next;
+    }
+    return L;
+}
+
 struct RenderJob {
     const Scene *sc; const TrRenderParams *rp; float *film; float *steady; int C;
     std::atomic<uint32_t> next_row{0};
     std::mutex mu; TrCounters total{}; std::vector<TrDeposit> *log = nullptr; uint64_t log_cap = 0;
+    const NlosCtx *nlos = nullptr;
 };
 
 inline bool pixel_owned(const TrRenderParams &rp, uint32_t W, uint32_t x, uint32_t y) {
@@ -616,9 +852,16 @@ void render_rows(RenderJob *job) {
                 uint32_t v0, v1; sample_tea_32(rp.seed, idx, &v0, &v1);
                 Pcg32 rng; rng.seed(v0, v1);
                 float jx = rng.next_1d(), jy = rng.next_1d();      // pos_f = pos + sampler.next_2d()
-                Ray ray = sample_camera_ray(sc, x, y, jx, jy);
                 cnt.paths++;
-                V3 L = trace_transient_path(sc, rp, rng, ray, (float) x, (float) y, sample_scale, 1.0f, film);
+                V3 L;
+                if (job->nlos) {
+                    float sx = ((float) x + jx) * (1.0f / (float) W), sy = ((float) y + jy) * (1.0f / (float) H);
+                    L = trace_nlos_path(sc, rp, *job->nlos, rng, nlos_sensor_ray(sc, sx, sy), y * W + x, (float) x, (float) y,
+                                        sample_scale, film);
+                } else {
+                    Ray ray = sample_camera_ray(sc, x, y, jx, jy);
+                    L = trace_transient_path(sc, rp, rng, ray, (float) x, (float) y, sample_scale, 1.0f, film);
+                }
                 Lsum = Lsum + L;                                   // steady block.put (weight 1)  common.py:196-203
             }
             if (job->steady) {
@@ -654,8 +897,14 @@ int oracle_render(const TrSceneDesc *desc, const TrRenderParams *params, float *
     Scene sc; std::string err;
     if (!params || !film) { g_err = "null argument"; return TR_ERR_INVALID_ARGUMENT; }
     if (!build_scene(desc, sc, err)) { g_err = err; return TR_ERR_INVALID_ARGUMENT; }
-    if (params->integrator != TR_INTEGRATOR_TRANSIENT_PATH) { g_err = "oracle: integrator not implemented"; return TR_ERR_UNSUPPORTED; }
-    if (sc.sensor.type != TR_SENSOR_PERSPECTIVE) { g_err = "oracle: transient_path needs a perspective sensor"; return TR_ERR_UNSUPPORTED; }
+    NlosCtx nctx;
+    if (params->integrator == TR_INTEGRATOR_TRANSIENT_NLOS_PATH) {
+        if (!nlos_prepare(sc, *params, nctx, err)) { g_err = err; return TR_ERR_UNSUPPORTED; }
+    } else if (params->integrator != TR_INTEGRATOR_TRANSIENT_PATH) {
+        g_err = "oracle: integrator not implemented"; return TR_ERR_UNSUPPORTED;
+    } else if (sc.sensor.type != TR_SENSOR_PERSPECTIVE) {
+        g_err = "oracle: transient_path needs a perspective sensor"; return TR_ERR_UNSUPPORTED;
+    }
     if (params->film_channels != 3 && params->film_channels != 4) { g_err = "film_channels must be 3 or 4"; return TR_ERR_INVALID_ARGUMENT; }
     if (params->spp == 0 || params->total_spp == 0) { g_err = "spp must be > 0"; return TR_ERR_INVALID_ARGUMENT; }
     const uint32_t W = sc.film.width, H = sc.film.height, T = sc.film.temporal_bins;
@@ -666,6 +915,7 @@ int oracle_render(const TrSceneDesc *desc, const TrRenderParams *params, float *
                 memset(film + ((size_t) y * W + x) * T * C, 0, sizeof(float) * (size_t) T * C);
     }
     RenderJob job; job.sc = &sc; job.rp = params; job.film = film; job.steady = steady; job.C = C;
+    if (params->integrator == TR_INTEGRATOR_TRANSIENT_NLOS_PATH) job.nlos = &nctx;
     std::vector<TrDeposit> log;
     if (deposit_log && log_capacity) { job.log = &log; job.log_cap = log_capacity; log.reserve((size_t) std::min<uint64_t>(log_capacity, 1u << 22)); }
     int nt = n_threads > 0 ? n_threads : (int) std::thread::hardware_concurrency();
