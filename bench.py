@@ -179,21 +179,44 @@ def run_ours(args):
     lib = _lib.load()
     stream = torch.cuda.current_stream()
 
-    film = torch.zeros((H, W, T, 4), dtype=torch.float32, device="cuda")
-    steady = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    # N > 1: "peer" = every rank flushes its pixel histograms straight into rank 0's film over NVLink peer
+    # memory (fused into the kernel, one tiny all-reduce as a fence); "reduce" = private films + one NCCL reduce.
+    mode = args.multi_gpu_mode if n > 1 else "single"
+    peer = None
+    if mode == "peer":
+        try:
+            from mitransient_b200.distributed import PeerFilm
+            peer = PeerFilm((H, W, T, 4), (H, W, 3), dst=0)
+            film, steady = peer.film, peer.steady
+        except Exception as exc:                               # no P2P / IPC on this box: fall back to the reduce
+            if rank == 0:
+                print(f"peer film unavailable ({exc}); falling back to NCCL reduce", file=sys.stderr)
+            mode, peer = "reduce", None
+        flag = torch.tensor([1.0 if mode == "peer" else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0.0:
+            mode, peer = "reduce", None
+    if peer is None:
+        film = torch.zeros((H, W, T, 4), dtype=torch.float32, device="cuda")
+        steady = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
     counters = torch.zeros(8, dtype=torch.int64, device="cuda")
     params = integ.make_params(spp, spp, 0, rank=rank, world=n, film_channels=4)
     launches = [0]
 
+    def finish_step():
+        if mode == "peer":
+            peer.fence()
+        elif mode == "reduce":
+            dist.reduce(film, dst=0)
+            dist.reduce(steady, dst=0)
+
     def step(with_counters=False):
-        if n > 1 and rank == 0:
+        if mode == "reduce" and rank == 0:
             film.zero_()                                       # last step's reduce landed in rank 0's film
         _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(),
                                  counters.data_ptr() if with_counters else None, stream.cuda_stream))
         launches[0] += 1
-        if n > 1:
-            dist.reduce(film, dst=0)
-            dist.reduce(steady, dst=0)
+        finish_step()
 
     # ---- counters (N_v) from one untimed step
     step(with_counters=True)
@@ -217,16 +240,14 @@ def run_ours(args):
     kern = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev[0].record(stream)
     for i in range(args.steps):
-        if n > 1 and rank == 0:
+        if mode == "reduce" and rank == 0:
             film.zero_()
         kern[i][0].record(stream)
         _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(), None,
                                  stream.cuda_stream))
         kern[i][1].record(stream)
         launches[0] += 1
-        if n > 1:
-            dist.reduce(film, dst=0)
-            dist.reduce(steady, dst=0)
+        finish_step()
         ev[i + 1].record(stream)
     torch.cuda.synchronize()
     if n > 1:
@@ -323,8 +344,10 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2 cornell_box transient_path {W}x{H}x{T} bins, {spp} spp, max_depth 8, seed 0"
-                               + (f" (weak scaling: 256 spp x {n} GPUs, pixel tiles 32x32 round-robin, "
-                                  "NCCL reduce of film+steady to rank 0 inside the step)" if n > 1 else ""),
+                               + (f" (weak scaling: 256 spp x {n} GPUs, pixel tiles 32x32 round-robin, film assembled on "
+                                  f"rank 0 inside the step, mode={mode}: " +
+                                  ("kernel flushes into rank 0's film over NVLink peer memory + all-reduce fence)"
+                                   if mode == "peer" else "NCCL reduce of film+steady to rank 0)") if n > 1 else ""),
                    "paths_per_step": paths_total, "film_bytes": W * H * T * 16,
                    "l2": "no flush needed: each step writes the 4 GiB film (>> 126 MB L2); the scene lives in shared memory",
                    "parallelism": f"pixel-tile x{n}"},
@@ -343,6 +366,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-gpu-mode", default="peer", choices=["peer", "reduce"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

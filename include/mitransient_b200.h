@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 5
+#define TR_ABI_VERSION 6
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -252,6 +252,20 @@ int tr_film_scatter_add(float *film, const TrFilmDesc *film_desc, int32_t channe
  * weight last; out: float[n_bins][in_channels-1].                                         */
 int tr_film_develop(const float *film_raw, float *out, uint64_t n_bins, int32_t in_channels,
                     void *stream);
+
+/* ------------------------------------------------------------------ multi-GPU film assembly
+ * Pixel tiles have exactly one writer, so the ranks of one node can flush their finished pixel
+ * histograms straight into ONE film that lives on the destination rank, mapped into every process through
+ * CUDA IPC (NVLink peer memory).  The reference has no counterpart (single process); this replaces the
+ * "NCCL reduce of the film" with stores fused into the render kernel.
+ *   tr_peer_alloc  on the destination rank: zero-filled device buffer + a 64-byte handle to send to the peers
+ *   tr_peer_open   on the other ranks: map it (enables peer access); pass the pointer as `film` to tr_render
+ *   tr_peer_close / tr_peer_free   undo the above                                                          */
+#define TR_PEER_HANDLE_BYTES 64
+int tr_peer_alloc(uint64_t bytes, void **dev_ptr, unsigned char *handle /* [TR_PEER_HANDLE_BYTES] */);
+int tr_peer_open(const unsigned char *handle /* [TR_PEER_HANDLE_BYTES] */, void **dev_ptr);
+int tr_peer_close(void *dev_ptr);
+int tr_peer_free(void *dev_ptr);
 
 #ifdef __cplusplus
 }

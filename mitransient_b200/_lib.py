@@ -60,6 +60,14 @@ def load() -> C.CDLL:
         lib.tr_film_scatter_add.argtypes = [vp, C.POINTER(_abi.TrFilmDesc), C.c_int32, vp, C.c_uint64, vp]
         lib.tr_film_develop.restype = C.c_int
         lib.tr_film_develop.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp]
+        lib.tr_peer_alloc.restype = C.c_int
+        lib.tr_peer_alloc.argtypes = [C.c_uint64, C.POINTER(vp), C.c_char_p]
+        lib.tr_peer_open.restype = C.c_int
+        lib.tr_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        lib.tr_peer_close.restype = C.c_int
+        lib.tr_peer_close.argtypes = [vp]
+        lib.tr_peer_free.restype = C.c_int
+        lib.tr_peer_free.argtypes = [vp]
         if lib.tr_abi_version() != _abi.TR_ABI_VERSION:
             raise ImportError(f"{_LIB_PATH} was built for ABI {lib.tr_abi_version()}, "
                               f"the Python host expects {_abi.TR_ABI_VERSION}: rebuild it")

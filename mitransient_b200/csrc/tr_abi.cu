@@ -1,5 +1,6 @@
 // Library-level C-ABI entry points: version, device probe, last-error string.
 #include <cstdio>
+#include <cstring>
 
 #include "tr_common.h"
 
@@ -41,6 +42,46 @@ int tr_device_check(void) {
         snprintf(buf, sizeof(buf), "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, major, minor);
         return tr::fail(TR_ERR_NO_DEVICE, buf);
     }
+    return TR_OK;
+}
+
+// ---- multi-GPU film assembly over NVLink peer memory (see the header)
+int tr_peer_alloc(uint64_t bytes, void **dev_ptr, unsigned char *handle) {
+    if (!dev_ptr || !handle || bytes == 0) return tr::fail(TR_ERR_INVALID_ARGUMENT, "tr_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TR_PEER_HANDLE_BYTES, "IPC handle size");
+    int rc = tr_device_check();
+    if (rc != TR_OK) return rc;
+    void *p = nullptr;
+    TR_CUDA(cudaMalloc(&p, bytes));
+    TR_CUDA_OR(cudaMemset(p, 0, bytes), { cudaFree(p); });
+    cudaIpcMemHandle_t h;
+    TR_CUDA_OR(cudaIpcGetMemHandle(&h, p), { cudaFree(p); });
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return TR_OK;
+}
+
+int tr_peer_open(const unsigned char *handle, void **dev_ptr) {
+    if (!dev_ptr || !handle) return tr::fail(TR_ERR_INVALID_ARGUMENT, "tr_peer_open: bad argument");
+    int rc = tr_device_check();
+    if (rc != TR_OK) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    TR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return TR_OK;
+}
+
+int tr_peer_close(void *dev_ptr) {
+    if (!dev_ptr) return TR_OK;
+    TR_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return TR_OK;
+}
+
+int tr_peer_free(void *dev_ptr) {
+    if (!dev_ptr) return TR_OK;
+    TR_CUDA(cudaFree(dev_ptr));
     return TR_OK;
 }
 

@@ -39,7 +39,16 @@ def _worker(rank, world, port, outdir):
     if rank == 0:
         np.save(os.path.join(outdir, "film.npy"), raw.cpu().numpy())
         np.save(os.path.join(outdir, "steady.npy"), steady.cpu().numpy())
+    # fused variant: every rank flushes its pixels straight into rank 0's film over NVLink peer memory
+    from mitransient_b200.distributed import PeerFilm, render_distributed_peer
+    peer = PeerFilm((64, 96, 128, 4), (64, 96, 3), dst=0)
+    st_p, film_p = render_distributed_peer(scene, peer, seed=0, spp=8)
+    torch.cuda.synchronize()
+    if rank == 0:
+        np.save(os.path.join(outdir, "film_peer.npy"), film_p.cpu().numpy())
+        np.save(os.path.join(outdir, "steady_peer.npy"), st_p.cpu().numpy())
     dist.barrier()
+    peer.close()
     dist.destroy_process_group()
 
 
@@ -60,3 +69,6 @@ def test_two_gpu_tile_sharding_matches_single_gpu(tmp_path):
     num = np.abs(film2.astype(np.float64) - raw).sum()
     assert num / np.abs(raw).sum() <= 1e-6
     np.testing.assert_allclose(np.load(tmp_path / "steady.npy"), steady.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    film3 = np.load(tmp_path / "film_peer.npy")
+    assert np.abs(film3.astype(np.float64) - raw).sum() / np.abs(raw).sum() <= 1e-6
+    np.testing.assert_allclose(np.load(tmp_path / "steady_peer.npy"), steady.cpu().numpy(), rtol=1e-5, atol=1e-7)
