@@ -277,7 +277,7 @@ def run_ours(args):
             _lib.check(lib.tr_scene_create(C.byref(desc), C.byref(h)))
             try:
                 _lib.check(lib.tr_render_to_host(h, C.byref(p_e2e), host_T.data_ptr(), host_S.data_ptr(),
-                                                 C.byref(cnt_h), stream.cuda_stream))
+                                                 None, stream.cuda_stream))
             finally:
                 lib.tr_scene_destroy(h)
         for _ in range(2):
@@ -298,7 +298,7 @@ def run_ours(args):
         e2e_paths = W * H * C2["spp"] * n                       # every rank renders one full C2 film to ITS host buffer
         e2e = {"value": e2e_paths * k_e2e / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(blob_bytes + W * H * 4),
-               "d2h_bytes_per_step": int(host_T.numel() * 4 + host_S.numel() * 4 + C.sizeof(_abi.TrCounters)),
+               "d2h_bytes_per_step": int(host_T.numel() * 4 + host_S.numel() * 4),
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
                "what": "tr_scene_create + tr_render_to_host: developed (H,W,T,3) film + steady into pinned host "
                        "memory, D2H overlapped with rendering band by band" +

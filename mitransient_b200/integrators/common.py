@@ -169,10 +169,11 @@ class TransientADIntegrator:
         dev = self.device_scene(scene, sensor)
         params = self.make_params(spp, spp, (int(seed) + s.base_seed) & 0xFFFFFFFF, film_channels=ch)
         self.fill_params_(params, scene, sensor)
-        cnt = _abi.TrCounters()
+        cnt = _abi.TrCounters() if self.collect_counters else None
         _lib.check(_lib.load().tr_render_to_host(dev.handle, C.byref(params), out_transient.data_ptr(),
-                                                 out_steady.data_ptr(), C.byref(cnt), _lib.current_stream_ptr()))
-        self.last_counters = cnt.as_dict()
+                                                 out_steady.data_ptr(), C.byref(cnt) if cnt is not None else None,
+                                                 _lib.current_stream_ptr()))
+        self.last_counters = cnt.as_dict() if cnt is not None else None
         return out_steady, out_transient
 
     # hooks for subclasses

@@ -14,10 +14,11 @@ ap.add_argument("--res", type=int, default=256)
 ap.add_argument("--bins", type=int, default=4096)
 ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--counters", action="store_true")
 a = ap.parse_args()
 scene = mitr.load_dict(mitr.nlos_z_scene(a.res, a.res, a.bins, a.spp))
 integ = scene.integrator()
-integ.collect_counters = True
+integ.collect_counters = a.counters
 for i in range(a.reps):
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -19,11 +19,12 @@ ap.add_argument("--bins", type=int, default=1024)
 ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--counters", action="store_true")
 a = ap.parse_args()
 
 scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
 integ = scene.integrator()
-integ.collect_counters = True
+integ.collect_counters = a.counters
 for i in range(a.reps):
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -111,3 +111,53 @@ def test_bvh_mesh_scene_parity(mitr, oracle, tmp_path):
     err = film_l1(raw, ref["transient"])
     assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
     np.testing.assert_allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
+
+
+def test_plain_kernel_equals_counting_kernel(mitr):
+    """The counter-free build (768 threads/CTA) and the counting build (512 threads/CTA) walk the same paths."""
+    scene = mitr.load_dict(mitr.cornell_box_config(48, 32, 128, 16))
+    integ = scene.integrator()
+    integ.collect_counters = False
+    s0, t0 = integ.render(scene, seed=2, spp=16)
+    integ.collect_counters = True
+    s1, t1 = integ.render(scene, seed=2, spp=16)
+    a, b = t0.cpu().numpy().astype(np.float64), t1.cpu().numpy().astype(np.float64)
+    assert np.abs(a - b).sum() / np.abs(b).sum() <= 1e-6
+    assert np.array_equal(a != 0, b != 0)
+
+
+def test_render_to_host_matches_device_render(mitr):
+    """tr_render_to_host (banded, D2H overlapped) == tr_render + develop."""
+    scene = mitr.load_dict(mitr.cornell_box_config(64, 40, 96, 8))
+    integ = scene.integrator()
+    steady, transient = integ.render(scene, seed=1, spp=8)
+    hs, ht = integ.render_to_host(scene, seed=1, spp=8)
+    a, b = ht.numpy().astype(np.float64), transient.cpu().numpy().astype(np.float64)
+    assert ht.shape == (40, 64, 96, 3) and np.abs(a - b).sum() / np.abs(b).sum() <= 1e-6
+    np.testing.assert_allclose(hs.numpy(), steady.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    hs4, ht4 = integ.render_to_host(scene, seed=1, spp=8, raw=True)
+    assert ht4.shape == (40, 64, 96, 4) and np.all(ht4.numpy()[..., 3] == 0)
+
+
+def test_film_scatter_add_and_develop_kernels(mitr, oracle):
+    """K4 / K5 on their own against the oracle: a recorded deposit stream, including duplicates within a warp,
+    out-of-window and out-of-film deposits."""
+    import torch
+    scene = mitr.load_dict(mitr.cornell_box_config(16, 12, 64, 4))
+    ref = oracle.render(scene, scene.integrator(), seed=0, spp=4, log_deposits=200000)
+    dep = ref["deposits"]
+    assert len(dep) == ref["counters"]["deposits"]
+    extra = np.array([[3, 2, 5.0, 1, 1, 1]] * 40 + [[99, 1, 5.0, 1, 1, 1], [3, -1, 5.0, 1, 1, 1], [3, 2, 1e9, 1, 1, 1],
+                                                     [3, 2, np.inf, 1, 1, 1]], dtype=np.float32)
+    dep = np.concatenate([dep, extra])
+    film = scene.sensors()[0].film()
+    film.prepare()
+    d = torch.from_numpy(dep).cuda()
+    film.add_transient_data(d[:, 0:2], d[:, 2], None, d[:, 3:6])
+    got = film.develop(raw=True)[1].cpu().numpy()
+    want = np.zeros_like(got)
+    oracle.film_scatter_add(want, film.describe(), dep)
+    assert np.array_equal(got != 0, want != 0)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-7)
+    dev = film.develop()[1].cpu().numpy()
+    np.testing.assert_array_equal(dev, oracle.film_develop(got))
