@@ -33,8 +33,7 @@ def build(force: bool = False) -> str:
 def load() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()          # no-op unless the sources are newer than the library
         lib = C.CDLL(LIB)
         lib.oracle_last_error.restype = C.c_char_p
         lib.oracle_render.restype = C.c_int
