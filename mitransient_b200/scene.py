@@ -449,6 +449,12 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                     fn = os.path.join(base_dir, fn)
                 base = load_obj(fn)
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
+            for ck, cv in val.items():      # every nested plugin of a shape must be one this build understands
+                ct = _type_of(cv)
+                if ct is not None and ck not in ("interior", "exterior") and ct not in _BSDF_TYPES + (
+                        "ref", "area", "homogeneous") + tuple(plugins.SENSORS):
+                    raise ValueError(f"shape {key!r}: unsupported nested plugin type {ct!r} (supported bsdfs: diffuse, "
+                                     "twosided(diffuse), null; emitters: area; sensors: nlos_capture_meter)")
             _, bspec = _find_child(val, _BSDF_TYPES + ("ref",))
             if bspec is None:
                 if default_bsdf is None:
@@ -468,9 +474,6 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 scene.emitters_.append({"type": _abi.TR_EMITTER_AREA, "shape": sidx,
                                         "radiance": _rgb(em.get("radiance"), 1.0)})
                 shape.emitter_index = len(scene.emitters_) - 1
-            bad_k, bad = _find_child(val, ("projector", "point", "spot", "constant", "envmap"))
-            if bad is not None:
-                raise ValueError(f"unsupported shape emitter {_type_of(bad)!r} (supported: area)")
             sk, se = _find_child(val, tuple(plugins.SENSORS))
             if se is not None:
                 if isinstance(se, dict):
