@@ -18,12 +18,14 @@ from .films.transient_hdr_film import TransientHDRFilm
 from .integrators.common import TransientADIntegrator
 from .integrators.transientnlospath import CaptureType, TransientNLOSPath
 from .integrators.transientpath import TransientPath
+from .integrators.transient_prbvolpath import TransientPRBVolpathIntegrator
 from . import nlos
 from .plugins import register_film, register_integrator, register_sensor
 from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
 from .sensors.nloscapturemeter import NLOSCaptureMeter
 from .transforms import ScalarTransform4f
-from .utils import cornell_box, cornell_box_config, letter_z_mesh, nlos_z_scene, speed_of_light
+from .utils import (cornell_box, cornell_box_config, cornell_box_volumetric, letter_z_mesh, nlos_z_scene,
+                    speed_of_light)
 
 __version__ = "0.1.0"
 

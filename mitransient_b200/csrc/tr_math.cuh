@@ -61,6 +61,43 @@ __device__ __forceinline__ void sincos_cephes(float x, float *s_out, float *c_ou
     *s_out = s; *c_out = c;
 }
 
+// Cephes single-precision exp / log (same polynomials and fmaf placement as the oracle).
+__device__ __forceinline__ float exp_cephes(float x) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    float n = floorf(fmaf(1.44269504088896341f, x, 0.5f));
+    x = fmaf(n, -0.693359375f, x);
+    x = fmaf(n, 2.12194440e-4f, x);
+    float z = x * x;
+    float p = fmaf(1.9875691500e-4f, x, 1.3981999507e-3f);
+    p = fmaf(p, x, 8.3334519073e-3f);
+    p = fmaf(p, x, 4.1665795894e-2f);
+    p = fmaf(p, x, 1.6666665459e-1f);
+    p = fmaf(p, x, 5.0000001201e-1f);
+    p = fmaf(p, z, x) + 1.0f;
+    return p * __uint_as_float((uint32_t) ((int) n + 127) << 23);
+}
+__device__ __forceinline__ float log_cephes(float x) {
+    uint32_t bits = __float_as_uint(x);
+    int e = (int) ((bits >> 23) & 0xffu) - 126;
+    float m = __uint_as_float((bits & 0x007fffffu) | 0x3f000000u);
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+    float z = m * m;
+    float y = fmaf(7.0376836292e-2f, m, -1.1514610310e-1f);
+    y = fmaf(y, m, 1.1676998740e-1f);
+    y = fmaf(y, m, -1.2420140846e-1f);
+    y = fmaf(y, m, 1.4249322787e-1f);
+    y = fmaf(y, m, -1.6668057665e-1f);
+    y = fmaf(y, m, 2.0000714765e-1f);
+    y = fmaf(y, m, -2.4999993993e-1f);
+    y = fmaf(y, m, 3.3333331174e-1f);
+    y = (y * m) * z;
+    float fe = (float) e;
+    y = fmaf(-2.12194440e-4f, fe, y);
+    y = fmaf(-0.5f, z, y);
+    float r = m + y;
+    return fmaf(0.693359375f, fe, r);
+}
+
 // Mitsuba `independent` sampler: PCG32 per lane seeded through TEA from (seed, lane index).
 struct Pcg32 {
     uint64_t state, inc;
@@ -116,6 +153,14 @@ __device__ __forceinline__ V3 coordinate_system_s(V3 n) {
     float a = -(1.0f / (sign + n.z));
     float b = n.x * n.y * a;
     return v3(mulsign(n.x * n.x * a, n.z) + 1.0f, mulsign(b, n.z), mulsign(-n.x, n.z));
+}
+
+__device__ __forceinline__ void coordinate_system(V3 n, V3 *s, V3 *t) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -(1.0f / (sign + n.z));
+    float b = n.x * n.y * a;
+    *s = v3(mulsign(n.x * n.x * a, n.z) + 1.0f, mulsign(b, n.z), mulsign(-n.x, n.z));
+    *t = v3(b, fmaf(n.y, n.y * a, sign), -n.y);
 }
 
 __device__ __forceinline__ V3 offset_p(V3 p, V3 n, V3 dir) {

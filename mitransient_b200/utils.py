@@ -120,3 +120,18 @@ def nlos_z_scene(width=64, height=64, temporal_bins=300, spp=1000, start_opl=1.8
                                                           "start_opl": float(start_opl), "rfilter": {"type": "box"}}}},
         "integrator": integ,
     }
+
+
+def cornell_box_volumetric(width=256, height=384, temporal_bins=512, spp=64, max_depth=16, window=(3.5, 13.5)):
+    """The Cornell box with both boxes turned into homogeneous participating media behind `null` boundaries -- the
+    dictionary counterpart of examples/transient/cornell-box/cbox_volumetric.xml (albedos / Henyey-Greenstein g of
+    that file; sigma_t rescaled from its 556-unit box to this 2-unit box: 0.05 * 278, 0.02 * 278)."""
+    d = cornell_box_config(width, height, temporal_bins, spp, max_depth, window)
+    d["integrator"] = {"type": "transient_prbvolpath", "max_depth": int(max_depth), "camera_unwarp": False,
+                       "temporal_filter": "box"}
+    media = {"small-box": ((0.99, 0.4, 0.46), 0.05 * 278.0, 0.1), "large-box": ((0.44, 0.4, 0.96), 0.02 * 278.0, 0.7)}
+    for name, (albedo, sigma_t, g) in media.items():
+        d[name]["bsdf"] = {"type": "null"}
+        d[name]["interior"] = {"type": "homogeneous", "albedo": {"type": "rgb", "value": ScalarColor3d(*albedo)},
+                               "sigma_t": sigma_t, "phase": {"type": "hg", "g": g}}
+    return d

@@ -48,6 +48,8 @@ def load() -> C.CDLL:
         lib.oracle_tea32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.oracle_sampler_floats.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         lib.oracle_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.oracle_exp.restype = C.c_float; lib.oracle_exp.argtypes = [C.c_float]
+        lib.oracle_log.restype = C.c_float; lib.oracle_log.argtypes = [C.c_float]
         lib.oracle_cosine_hemisphere.argtypes = [C.c_float, C.c_float, C.c_void_p]
         lib.oracle_camera_ray.restype = C.c_int
         lib.oracle_camera_ray.argtypes = [C.POINTER(_abi.TrSceneDesc), C.c_uint32, C.c_uint32, C.c_float, C.c_float,
@@ -157,3 +159,11 @@ def ray_intersect(scene, sensor, o, d, maxt=3.4e38):
     if hit == 0:
         return None
     return {"t": t.value, "p": p, "n": n, "shape": shape.value, "prim": prim.value}
+
+
+def exp(x):
+    return load().oracle_exp(x)
+
+
+def log(x):
+    return load().oracle_log(x)

@@ -105,6 +105,46 @@ inline void sincos_cephes(float x, float *s_out, float *c_out) {
     *s_out = s; *c_out = c;
 }
 
+// Cephes single-precision exp / log (explicit fmaf; shared by specification with the CUDA kernels).
+inline float exp_cephes(float x) {
+    x = fminf(fmaxf(x, -87.0f), 88.0f);
+    float n = floorf(fmaf(1.44269504088896341f, x, 0.5f));
+    x = fmaf(n, -0.693359375f, x);
+    x = fmaf(n, 2.12194440e-4f, x);
+    float z = x * x;
+    float p = fmaf(1.9875691500e-4f, x, 1.3981999507e-3f);
+    p = fmaf(p, x, 8.3334519073e-3f);
+    p = fmaf(p, x, 4.1665795894e-2f);
+    p = fmaf(p, x, 1.6666665459e-1f);
+    p = fmaf(p, x, 5.0000001201e-1f);
+    p = fmaf(p, z, x) + 1.0f;
+    uint32_t bits = (uint32_t) ((int32_t) n + 127) << 23;      // 2^n, n in [-126, 127]
+    float scale; memcpy(&scale, &bits, 4);
+    return p * scale;
+}
+inline float log_cephes(float x) {          // x > 0, normal
+    uint32_t bits; memcpy(&bits, &x, 4);
+    int32_t e = (int32_t) ((bits >> 23) & 0xffu) - 126;        // frexp: x = m * 2^e, m in [0.5, 1)
+    bits = (bits & 0x007fffffu) | 0x3f000000u;
+    float m; memcpy(&m, &bits, 4);
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+    float z = m * m;
+    float y = fmaf(7.0376836292e-2f, m, -1.1514610310e-1f);
+    y = fmaf(y, m, 1.1676998740e-1f);
+    y = fmaf(y, m, -1.2420140846e-1f);
+    y = fmaf(y, m, 1.4249322787e-1f);
+    y = fmaf(y, m, -1.6668057665e-1f);
+    y = fmaf(y, m, 2.0000714765e-1f);
+    y = fmaf(y, m, -2.4999993993e-1f);
+    y = fmaf(y, m, 3.3333331174e-1f);
+    y = (y * m) * z;
+    float fe = (float) e;
+    y = fmaf(-2.12194440e-4f, fe, y);
+    y = fmaf(-0.5f, z, y);
+    float r = m + y;
+    return fmaf(0.693359375f, fe, r);
+}
+
 // ------------------------------------------------------------------------------ sampler
 // Mitsuba `independent` sampler: one PCG32 per lane, seeded through the Tiny Encryption
 // Algorithm from (seed, lane index) [upstream: Sampler::seed, sample_tea_32, drjit PCG32].
@@ -153,6 +193,7 @@ struct Scene {
     std::vector<Shape> shapes;
     std::vector<TrBsdfDesc> bsdfs;
     std::vector<TrEmitterDesc> emitters;
+    std::vector<TrMediumDesc> media;
     TrSensorDesc sensor;
     TrFilmDesc film;
 };
@@ -208,6 +249,7 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
     sc.sensor = desc->sensor; sc.film = desc->film;
     sc.bsdfs.assign(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
     sc.emitters.assign(desc->emitters, desc->emitters + desc->n_emitters);
+    if (desc->n_media) sc.media.assign(desc->media, desc->media + desc->n_media);
     sc.prims.resize(desc->n_prims);
     sc.shapes.resize(desc->n_shapes);
     for (uint32_t si = 0; si < desc->n_shapes; ++si) {
@@ -819,6 +861,282 @@ V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx
     return L;
 }
 
+
+// =============================================================================================
+//  transient_prbvolpath  (mitransient/integrators/transient_prbvolpath.py), primal, homogeneous media
+//  with Henyey-Greenstein phase functions and `null` boundaries (the reference's participating-media
+//  example, examples/transient/cornell-box/cbox_volumetric.xml).
+//  Upstream pieces restated: Medium::sample_interaction / transmittance_eval_pdf (homogeneous),
+//  HGPhaseFunction::sample / eval_pdf, Null BSDF, Interaction::spawn_ray(_to).
+// =============================================================================================
+struct MediumEvent { bool valid; float t, mint; V3 p, wi; V3 sigma_s, sigma_t; int medium; };
+
+inline V3 medium_sigma_t(const TrMediumDesc &m) { return v3(m.sigma_t[0] * m.scale, m.sigma_t[1] * m.scale, m.sigma_t[2] * m.scale); }
+inline float chan(V3 v, uint32_t c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+
+// Medium::sample_interaction (homogeneous): free-flight distance by the chosen channel's extinction
+inline MediumEvent medium_sample_interaction(const Scene &sc, int medium, const Ray &ray, float sample, uint32_t channel) {
+    MediumEvent me; me.medium = medium; me.wi = -ray.d; me.mint = 0.0f;
+    const TrMediumDesc &m = sc.media[medium];
+    V3 ce = medium_sigma_t(m);
+    float mm = chan(ce, channel);
+    float sampled_t = 0.0f + (-log_cephes(1.0f - sample) / mm);
+    me.valid = sampled_t <= ray.maxt;
+    me.t = me.valid ? sampled_t : kInf;
+    me.p = fma3(ray.d, sampled_t, ray.o);
+    me.sigma_t = ce;
+    me.sigma_s = v3(ce.x * m.albedo[0], ce.y * m.albedo[1], ce.z * m.albedo[2]);
+    return me;
+}
+// Medium::transmittance_eval_pdf: tr = exp(-t * sigma_t), pdf = tr (surface first) or tr * sigma_t
+inline void medium_transmittance_eval_pdf(const MediumEvent &me, float si_t, V3 *tr, V3 *pdf) {
+    float t = fminf(me.t, si_t) - me.mint;
+    *tr = v3(exp_cephes(-t * me.sigma_t.x), exp_cephes(-t * me.sigma_t.y), exp_cephes(-t * me.sigma_t.z));
+    *pdf = (si_t < me.t) ? *tr : (*tr) * me.sigma_t;
+}
+// HGPhaseFunction
+inline float hg_eval(float g, float cos_theta) {
+    float temp = 1.0f + g * g + 2.0f * g * cos_theta;
+    return 0.07957747154594766788f * (1.0f - g * g) / (temp * sqrtf(temp));
+}
+inline V3 hg_sample(float g, V3 wi, float s2x, float s2y, float *pdf) {
+    float cos_theta;
+    if (fabsf(g) < kEps) cos_theta = 1.0f - 2.0f * s2x;
+    else {
+        float sqr_term = (1.0f - g * g) / (1.0f - g + 2.0f * g * s2x);
+        cos_theta = (1.0f + g * g - sqr_term * sqr_term) / (2.0f * g);
+    }
+    float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+    float sp, cp; sincos_cephes(2.0f * kPi * s2y, &sp, &cp);
+    V3 s, t; coordinate_system(wi, &s, &t);                       // mei.sh_frame = Frame3f(mei.wi)
+    V3 local = v3(sin_theta * cp, sin_theta * sp, -cos_theta);
+    *pdf = hg_eval(g, -cos_theta);
+    return fma3(wi, local.z, fma3(t, local.y, s * local.x));
+}
+
+inline int target_medium(const Scene &sc, const Hit &si, V3 d) {   // si.target_medium(d)
+    const TrShapeDesc &sh = sc.shapes[si.shape].d;
+    return dot(d, si.n) > 0.0f ? sh.exterior_medium : sh.interior_medium;
+}
+inline bool is_medium_transition(const Scene &sc, const Hit &si) {
+    const TrShapeDesc &sh = sc.shapes[si.shape].d;
+    return sh.interior_medium >= 0 || sh.exterior_medium >= 0;
+}
+
+// sample_emitter   transient_prbvolpath.py:414-512: emitter sample without visibility test, then walk the
+// segment through null surfaces / media accumulating transmittance (homogeneous shortcut :463-468).
+V3 vol_sample_emitter(const Scene &sc, Pcg32 &rng, bool from_medium, V3 ref_p, const Hit &si, int medium, uint32_t channel,
+                      DirectionSample *ds_out, TrCounters *cnt) {
+    const uint32_t n_em = (uint32_t) sc.emitters.size();
+    float u0 = rng.next_1d(), u1 = rng.next_1d();                                  // :424-425
+    ds_out->pdf = 0.0f; ds_out->dist = 0.0f; ds_out->delta = false; ds_out->d = v3(0, 0, 0);
+    if (n_em == 0) return v3(0, 0, 0);
+    uint32_t ei = 0; float emw = 1.0f, pdf_pick = 1.0f;
+    if (n_em > 1) {
+        float fi = u0 * (float) n_em;
+        ei = (uint32_t) fi; if (ei > n_em - 1) ei = n_em - 1;
+        u0 = fi - (float) ei; emw = (float) n_em; pdf_pick = 1.0f / (float) n_em;
+    }
+    DirectionSample ds;
+    V3 emitter_val = area_sample_direction(sc, sc.emitters[ei], ref_p, u0, u1, &ds) * emw;
+    ds.pdf *= pdf_pick;
+    *ds_out = ds;
+    if (ds.pdf == 0.0f) return v3(0, 0, 0);                                        // :429-431
+    bool nz = emitter_val.x != 0.0f || emitter_val.y != 0.0f || emitter_val.z != 0.0f;
+    if (!nz) return v3(0, 0, 0);                                                   // the walk below only scales emitter_val
+    if (!from_medium && is_medium_transition(sc, si)) medium = target_medium(sc, si, ds.d);   // :434-435
+    Ray ray;
+    if (from_medium) {                                                             // Interaction::spawn_ray_to (no offset)
+        V3 d = ds.p - ref_p; float dist = sqrtf(dot(d, d));
+        ray = Ray{ref_p, d * (1.0f / dist), dist * (1.0f - kShadowEpsilon)};
+    } else {
+        ray = spawn_ray_to(si.p, si.n, ds.p);
+    }
+    const float max_dist = ray.maxt; float total_dist = 0.0f;                     // :438-439
+    Hit si2; si2.valid = false; si2.t = kInf;
+    bool needs_intersection = true, active = true;
+    V3 transmittance = v3(1, 1, 1);
+    while (active) {                                                               // :444
+        float remaining = max_dist - total_dist;
+        ray.maxt = remaining;
+        active = remaining > 0.0f;
+        if (!active) break;
+        if (needs_intersection) { cnt->shadow_rays++; si2 = ray_intersect(sc, ray); needs_intersection = false; }
+        bool active_medium = medium >= 0, active_surface = !active_medium;
+        V3 tr_mult = v3(1, 1, 1);
+        bool escaped_medium = false;
+        if (active_medium) {                                                       // :456-471
+            float u = rng.next_1d(); (void) u;                                     // medium.sample_interaction(ray, next_1d(active_medium), ...)
+            MediumEvent me; me.mint = 0.0f; me.sigma_t = medium_sigma_t(sc.media[medium]);
+            me.t = fminf(remaining, si2.t);
+            V3 pdf; medium_transmittance_eval_pdf(me, si2.t, &tr_mult, &pdf);
+            escaped_medium = true; active_medium = false;                          // mei.t = inf: never a real interaction
+        }
+        active_surface = (active_surface || escaped_medium) && si2.valid;          // :481-482
+        if (active_surface) {
+            const TrBsdfDesc &b = sc.bsdfs[sc.shapes[si2.shape].d.bsdf];
+            float null_tr = (b.type == TR_BSDF_NULL) ? 1.0f : 0.0f;                // bsdf.eval_null_transmission
+            tr_mult = tr_mult * null_tr;
+        }
+        transmittance = transmittance * tr_mult;                                   // :492
+        if (active_surface) { ray = spawn_ray(si2.p, si2.n, ray.d); needs_intersection = true; }   // :495-497
+        ray.maxt = remaining;
+        active = (active_medium || active_surface) && (transmittance.x != 0.0f || transmittance.y != 0.0f || transmittance.z != 0.0f);
+        if (active) total_dist += si2.t;                                           // :502
+        if (active_surface && is_medium_transition(sc, si2)) medium = target_medium(sc, si2, ray.d);   // :505-506
+    }
+    return emitter_val * transmittance;
+}
+
+V3 trace_volpath(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray, float px, float py, float sample_scale, Film &film) {
+    const uint32_t n_em = (uint32_t) sc.emitters.size();
+    const bool hide_emitters = (rp.flags & TR_FLAG_HIDE_EMITTERS) != 0;
+    uint32_t depth = 0; V3 L = v3(0, 0, 0), beta = v3(1, 1, 1); float eta = 1.0f; bool active = true;
+    Hit si; si.valid = false; si.t = kInf; si.p = v3(0, 0, 0); si.n = v3(0, 0, 0); si.shape = 0;
+    bool needs_intersection = true;
+    V3 last_scatter_p = v3(0, 0, 0); float last_scatter_direction_pdf = 1.0f;     // :150-151
+    int medium = -1;                                                               // :154 (sensors inside media unsupported)
+    bool specular_chain = true;
+    float distance = 0.0f;
+    if (rp.flags & TR_FLAG_CAMERA_UNWARP) {                                        // first_surface :515-528
+        Ray r = ray; float dsum = 0.0f; bool act = true;
+        while (act) {
+            Hit h = ray_intersect(sc, r);
+            act = h.valid;
+            if (!act) break;
+            dsum = dsum + h.t;
+            act = sc.bsdfs[sc.shapes[h.shape].d.bsdf].type == TR_BSDF_NULL;
+            r = Ray{fma3(r.d, kRayEpsilon * 2.0f, h.p), r.d, std::numeric_limits<float>::max()};
+        }
+        distance = -dsum;
+    }
+    float cf = 3.0f * rng.next_1d();                                               // :165-168 colour channel for free flights
+    uint32_t channel = (uint32_t) fminf(cf, 2.0f);
+
+    while (active) {                                                               // :170
+        film.cnt->vertices++;
+        active = active && (beta.x != 0.0f || beta.y != 0.0f || beta.z != 0.0f);   // :172
+        if (!active) break;
+        float q = fminf(max3(beta) * (eta * eta), 0.99f);                          // :176-180 russian roulette
+        bool perform_rr = depth > rp.rr_depth;
+        float rr_u = rng.next_1d();
+        active = active && ((rr_u < q) || !perform_rr);
+        if (perform_rr) beta = beta * (1.0f / q);
+        if (!active) break;
+        bool active_medium = medium >= 0, active_surface = !active_medium;         // :182-183
+        bool act_medium_scatter = false, escaped_medium = false;
+        MediumEvent mei; mei.valid = false; mei.t = kInf; mei.medium = -1; mei.p = v3(0, 0, 0); mei.wi = v3(0, 0, 0);
+        if (active_medium) {                                                       // :189-230
+            float u = rng.next_1d();
+            mei = medium_sample_interaction(sc, medium, ray, u, channel);
+            if (mei.valid) ray.maxt = mei.t;                                       // :194-195
+            if (needs_intersection) si = ray_intersect(sc, ray);                   // :196-197
+            needs_intersection = false;
+            if (si.t < mei.t) mei.t = kInf;                                        // :200
+            V3 tr, ffp; medium_transmittance_eval_pdf(mei, si.t, &tr, &ffp);       // :203-209
+            float tr_pdf = chan(ffp, channel);
+            V3 weight = tr_pdf > 0.0f ? v3(tr.x / tr_pdf, tr.y / tr_pdf, tr.z / tr_pdf) : v3(0, 0, 0);
+            mei.valid = mei.t < kInf;
+            escaped_medium = !mei.valid; active_medium = mei.valid;                // :211-212
+            act_medium_scatter = active_medium;                                    // :225-226
+            if (act_medium_scatter) { depth += 1; last_scatter_p = mei.p; distance += mei.t * eta; }   // :228-231
+            active = active && (depth < rp.max_depth);                             // :234
+            act_medium_scatter = act_medium_scatter && active;
+            if (act_medium_scatter) weight = weight * mei.sigma_s;                 // :240-241
+            beta = beta * weight;                                                  // :242
+        } else {
+            active = active && (depth < rp.max_depth);                             // :234 (unconditional in the reference)
+        }
+        // ---- surface interactions :258-283
+        active_surface = active_surface || escaped_medium;
+        if (active_surface && needs_intersection) { si = ray_intersect(sc, ray); needs_intersection = false; }
+        if (active_surface) distance += si.t * eta;                                // :262
+        bool count_direct = (active_surface && depth == 0) || specular_chain;      // :266-267
+        if (active_surface && si.valid && sc.shapes[si.shape].d.emitter >= 0 && !(depth == 0 && hide_emitters)) {
+            const TrEmitterDesc &em = sc.emitters[sc.shapes[si.shape].d.emitter];
+            V3 rel = si.p - last_scatter_p;                                        // DirectionSample3f(scene, si, last_scatter_event)
+            float dist = sqrtf(dot(rel, rel));
+            V3 dsd = rel * (1.0f / dist);
+            float emitter_pdf = area_pdf_direction(sc, em, dsd, si.n, dist);
+            if (n_em > 1) emitter_pdf *= 1.0f / (float) n_em;
+            float cos_i = -dot(ray.d, si.n);
+            V3 emitted = cos_i > 0.0f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0, 0, 0);
+            V3 contrib = count_direct ? beta * emitted : (beta * mis_weight(last_scatter_direction_pdf, emitter_pdf)) * emitted;   // :277-278
+            L = L + contrib;
+            film.add_transient(px, py, contrib, distance, sample_scale, 1.0f);     // :282-283
+        }
+        active_surface = active_surface && si.valid;                               // :285
+        const TrBsdfDesc *bsdf = active_surface ? &sc.bsdfs[sc.shapes[si.shape].d.bsdf] : nullptr;
+        const bool smooth = bsdf && bsdf->type == TR_BSDF_DIFFUSE;
+        const float cos_i = active_surface ? -dot(ray.d, si.n) : 0.0f;
+        // ---- emitter sampling :291-331
+        bool active_e_surface = active_surface && smooth && (depth + 1 < rp.max_depth);
+        if (act_medium_scatter) specular_chain = false;                            // :295-296 (media sample emitters)
+        bool active_e_medium = act_medium_scatter;
+        if (active_e_surface || active_e_medium) {
+            DirectionSample ds;
+            V3 emitted = vol_sample_emitter(sc, rng, active_e_medium, active_e_medium ? mei.p : si.p, si, medium, channel, &ds, film.cnt);
+            V3 nee_weight; float nee_pdf;
+            if (active_e_surface) {
+                float cos_o = dot(ds.d, si.n);
+                nee_weight = bsdf_eval(*bsdf, cos_i, cos_o);
+                bool two_back = (bsdf->flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f;
+                float ci = two_back ? -cos_i : cos_i, co = two_back ? -cos_o : cos_o;
+                nee_pdf = (ci > 0.0f && co > 0.0f) ? kInvPi * co : 0.0f;
+            } else {
+                float ph = hg_eval(sc.media[mei.medium].g, dot(ds.d, mei.wi));     // phase.eval_pdf(mei, ds.d)
+                nee_weight = v3(ph, ph, ph); nee_pdf = ph;
+            }
+            V3 contrib = ((beta * nee_weight) * mis_weight(ds.pdf, nee_pdf)) * emitted;   // :322-323
+            L = L + contrib;
+            film.add_transient(px, py, contrib, distance + ds.dist * eta, sample_scale, 1.0f);   // :329-331
+        }
+        // ---- phase function sampling :335-360
+        if (act_medium_scatter) {
+            float p1 = rng.next_1d(); (void) p1;
+            float p2x = rng.next_1d(), p2y = rng.next_1d();
+            float ppdf;
+            V3 wo = hg_sample(sc.media[mei.medium].g, mei.wi, p2x, p2y, &ppdf);
+            act_medium_scatter = ppdf > 0.0f;
+            if (act_medium_scatter) {                                              // phase_weight = 1
+                ray = Ray{mei.p, wo, std::numeric_limits<float>::max()};           // mei.spawn_ray(wo)
+                needs_intersection = true;
+                last_scatter_direction_pdf = ppdf;
+            }
+        }
+        // ---- BSDF sampling :364-408
+        if (active_surface) {
+            float b1 = rng.next_1d(); (void) b1;
+            float b2x = rng.next_1d(), b2y = rng.next_1d();
+            V3 wo_world; V3 bw = v3(0, 0, 0); float bs_pdf; bool is_null = bsdf->type == TR_BSDF_NULL;
+            if (is_null) {                                                         // Null BSDF: straight through
+                wo_world = ray.d; bw = v3(1, 1, 1); bs_pdf = 1.0f;
+            } else {
+                V3 wo = square_to_cosine_hemisphere(b2x, b2y);
+                bs_pdf = kInvPi * wo.z;
+                bool two_back = (bsdf->flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f;
+                float ci = two_back ? -cos_i : cos_i;
+                if (smooth && ci > 0.0f && bs_pdf > 0.0f) bw = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+                if (two_back) wo.z = -wo.z;
+                wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));
+            }
+            active_surface = bs_pdf > 0.0f;                                        // :370
+            if (active_surface) {
+                beta = beta * bw;                                                  // :386
+                ray = spawn_ray(si.p, si.n, wo_world);                             // :388-389
+                needs_intersection = true;
+                if (!is_null) {                                                    // non_null_bsdf :392-399
+                    depth += 1; last_scatter_p = si.p; last_scatter_direction_pdf = bs_pdf;
+                    specular_chain = false;                                        // :402-405 (diffuse is smooth, never delta)
+                }
+                if (is_medium_transition(sc, si)) medium = target_medium(sc, si, ray.d);   // :406-407
+            }
+        }
+        active = active && (active_surface || active_medium);                      // :408
+    }
+    return L;
+}
+
 struct RenderJob {
     const Scene *sc; const TrRenderParams *rp; float *film; float *steady; int C;
     std::atomic<uint32_t> next_row{0};
@@ -854,7 +1172,9 @@ void render_rows(RenderJob *job) {
                 float jx = rng.next_1d(), jy = rng.next_1d();      // pos_f = pos + sampler.next_2d()
                 cnt.paths++;
                 V3 L;
-                if (job->nlos) {
+                if (rp.integrator == TR_INTEGRATOR_TRANSIENT_PRBVOLPATH) {
+                    L = trace_volpath(sc, rp, rng, sample_camera_ray(sc, x, y, jx, jy), (float) x, (float) y, sample_scale, film);
+                } else if (job->nlos) {
                     float sx = ((float) x + jx) * (1.0f / (float) W), sy = ((float) y + jy) * (1.0f / (float) H);
                     L = trace_nlos_path(sc, rp, *job->nlos, rng, nlos_sensor_ray(sc, sx, sy), y * W + x, (float) x, (float) y,
                                         sample_scale, film);
@@ -900,10 +1220,10 @@ int oracle_render(const TrSceneDesc *desc, const TrRenderParams *params, float *
     NlosCtx nctx;
     if (params->integrator == TR_INTEGRATOR_TRANSIENT_NLOS_PATH) {
         if (!nlos_prepare(sc, *params, nctx, err)) { g_err = err; return TR_ERR_UNSUPPORTED; }
-    } else if (params->integrator != TR_INTEGRATOR_TRANSIENT_PATH) {
+    } else if (params->integrator != TR_INTEGRATOR_TRANSIENT_PATH && params->integrator != TR_INTEGRATOR_TRANSIENT_PRBVOLPATH) {
         g_err = "oracle: integrator not implemented"; return TR_ERR_UNSUPPORTED;
     } else if (sc.sensor.type != TR_SENSOR_PERSPECTIVE) {
-        g_err = "oracle: transient_path needs a perspective sensor"; return TR_ERR_UNSUPPORTED;
+        g_err = "oracle: transient_path / transient_prbvolpath need a perspective sensor"; return TR_ERR_UNSUPPORTED;
     }
     if (params->film_channels != 3 && params->film_channels != 4) { g_err = "film_channels must be 3 or 4"; return TR_ERR_INVALID_ARGUMENT; }
     if (params->spp == 0 || params->total_spp == 0) { g_err = "spp must be > 0"; return TR_ERR_INVALID_ARGUMENT; }
@@ -962,6 +1282,8 @@ void oracle_sampler_floats(uint32_t seed, uint32_t lane, float *out, int n) {
     for (int i = 0; i < n; ++i) out[i] = r.next_1d();
 }
 void oracle_sincos(float x, float *s, float *c) { sincos_cephes(x, s, c); }
+float oracle_exp(float x) { return exp_cephes(x); }
+float oracle_log(float x) { return log_cephes(x); }
 void oracle_cosine_hemisphere(float u0, float u1, float *xyz) {
     V3 w = square_to_cosine_hemisphere(u0, u1); xyz[0] = w.x; xyz[1] = w.y; xyz[2] = w.z;
 }
