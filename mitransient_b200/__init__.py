@@ -24,6 +24,7 @@ from .plugins import register_film, register_integrator, register_sensor
 from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
 from .sensors.nloscapturemeter import NLOSCaptureMeter
 from .transforms import ScalarTransform4f
+from .xml import load_file, xml_to_dict
 from .utils import (cornell_box, cornell_box_config, cornell_box_volumetric, letter_z_mesh, nlos_z_scene,
                     speed_of_light)
 

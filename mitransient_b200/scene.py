@@ -101,6 +101,55 @@ def load_obj(path: str) -> np.ndarray:
     return v[t]
 
 
+def merge_quads(tris: np.ndarray, rel_eps: float = 1e-6):
+    """Greedily merge pairs of triangles that share an edge and together form a parallelogram into one
+    TR_PRIM_QUAD (p0, p1, p2 with the fourth corner p1 + p2 - p0).  Geometry and orientation are unchanged;
+    a ray tests one primitive instead of two.  Returns (prims [n,3,3], types [n])."""
+    n = len(tris)
+    used = np.zeros(n, dtype=bool)
+    scale = max(1e-30, float(np.abs(tris).max())) if n else 1.0
+    eps = rel_eps * scale
+    key = lambda p: tuple(np.round(p / max(eps, 1e-30)).astype(np.int64))   # noqa: E731
+    edge_map: Dict[Any, List[int]] = {}
+    for i in range(n):
+        ks = [key(tris[i, k]) for k in range(3)]
+        for a, b in ((0, 1), (1, 2), (2, 0)):
+            edge_map.setdefault(frozenset((ks[a], ks[b])), []).append(i)
+    prims, types = [], []
+    for i in range(n):
+        if used[i]:
+            continue
+        merged = False
+        ki = [key(tris[i, k]) for k in range(3)]
+        for a, b, c in ((0, 1, 2), (1, 2, 0), (2, 0, 1)):        # shared edge (a, b), apex c of triangle i
+            for j in edge_map.get(frozenset((ki[a], ki[b])), []):
+                if j == i or used[j]:
+                    continue
+                kj = [key(tris[j, k]) for k in range(3)]
+                other = [k for k in range(3) if kj[k] not in (ki[a], ki[b])]
+                if len(other) != 1:
+                    continue
+                pa, s1, s2, pb = tris[i, c], tris[i, a], tris[i, b], tris[j, other[0]]
+                if np.abs((pa + pb) - (s1 + s2)).max() > 4 * eps:
+                    continue                                      # not a parallelogram
+                ni = np.cross(tris[i, 1] - tris[i, 0], tris[i, 2] - tris[i, 0])
+                nj = np.cross(tris[j, 1] - tris[j, 0], tris[j, 2] - tris[j, 0])
+                if np.dot(ni, nj) <= 0:
+                    continue                                      # opposite orientation
+                prims.append([pa, s1, s2])                        # cyclic order (c, a, b) keeps triangle i's normal
+                types.append(_abi.TR_PRIM_QUAD)
+                used[i] = used[j] = True
+                merged = True
+                break
+            if merged:
+                break
+        if not merged:
+            used[i] = True
+            prims.append(tris[i])
+            types.append(_abi.TR_PRIM_TRIANGLE)
+    return (np.array(prims, dtype=np.float64).reshape(-1, 3, 3), np.array(types, dtype=np.uint8))
+
+
 def _apply(to_world: ScalarTransform4f, prims: np.ndarray, flip: bool) -> np.ndarray:
     m = to_world.matrix
     out = prims @ m[:3, :3].T + m[:3, 3]
@@ -449,6 +498,8 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                     fn = os.path.join(base_dir, fn)
                 base = load_obj(fn)
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
+            if t in ("obj", "trimesh") and bool(val.get("merge_quads", True)) and len(base) > 1:
+                base, ptypes = merge_quads(base)     # coplanar triangle pairs -> parallelogram primitives
             for ck, cv in val.items():      # every nested plugin of a shape must be one this build understands
                 ct = _type_of(cv)
                 if ct is not None and ck not in ("interior", "exterior") and ct not in _BSDF_TYPES + (

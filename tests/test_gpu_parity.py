@@ -97,6 +97,7 @@ def test_bvh_mesh_scene_parity(mitr, oracle, tmp_path):
     del d["light"], d["small-box"]
     d["sphere"] = {"type": "obj", "filename": str(tmp_path / "sphere.obj"), "bsdf": {"type": "ref", "id": "green"}}
     d["meshlight"] = {"type": "obj", "filename": str(tmp_path / "light.obj"), "bsdf": {"type": "ref", "id": "white"},
+                      "merge_quads": False,     # keep two triangles: area CDF + uniform-triangle warp
                       "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [10.0, 9.0, 7.0]}}}
     scene = mitr.load_dict(d)
     integ = scene.integrator()

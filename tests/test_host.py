@@ -115,3 +115,64 @@ def test_obj_loader_ignores_line_records(mitr, tmp_path):
     tris = mitr.load_obj(str(p))
     assert tris.shape == (3, 3, 3)                                   # quad -> 2 triangles (fan) + 1 triangle
     np.testing.assert_allclose(tris[2], [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
+
+
+_XML = """<scene version="3.3.0">
+    <default name="spp" value="4"/>
+    <default name="res" value="16"/>
+    <integrator type="transient_path"><integer name="max_depth" value="5"/><boolean name="camera_unwarp" value="false"/></integrator>
+    <sensor type="perspective" id="sensor">
+        <string name="fov_axis" value="smaller"/><float name="near_clip" value="0.01"/><float name="far_clip" value="100"/>
+        <float name="fov" value="40"/>
+        <transform name="to_world"><lookat origin="0, 0, 4" target="0, 0, 0" up="0, 1, 0"/></transform>
+        <sampler type="independent"><integer name="sample_count" value="$spp"/></sampler>
+        <film type="transient_hdr_film">
+            <integer name="width" value="$res"/><integer name="height" value="$res"/>
+            <integer name="temporal_bins" value="32"/><float name="start_opl" value="2"/><float name="bin_width_opl" value="0.25"/>
+            <rfilter type="box"/>
+        </film>
+    </sensor>
+    <bsdf type="diffuse" id="white"><rgb name="reflectance" value="0.8, 0.7, 0.6"/></bsdf>
+    <shape type="obj" id="wall"><string name="filename" value="quad.obj"/><ref id="white"/></shape>
+    <shape type="rectangle" id="light">
+        <transform name="to_world"><scale value="0.25"/><rotate x="1" angle="180"/><translate x="0" y="0" z="3"/></transform>
+        <bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.5"/></bsdf></bsdf>
+        <emitter type="area"><rgb name="radiance" value="10, 9, 8"/></emitter>
+    </shape>
+</scene>"""
+
+
+def test_xml_scene_file(mitr, tmp_path):
+    (tmp_path / "quad.obj").write_text("v -1 -1 0\nv 1 -1 0\nv 1 1 0\nv -1 1 0\nf 1 2 3\nf 1 3 4\n")
+    (tmp_path / "scene.xml").write_text(_XML)
+    d = mitr.xml_to_dict(str(tmp_path / "scene.xml"), res=24)
+    assert d["sensor"]["film"]["width"] == 24 and d["sensor"]["sampler"]["sample_count"] == 4   # <default> + override
+    scene = mitr.load_file(str(tmp_path / "scene.xml"), res=24)
+    assert scene.integrator().max_depth == 5 and scene.sensors()[0].film().size() == (24, 24)
+    assert len(scene.shapes()) == 2 and len(scene.emitters()) == 1
+    wall, light = scene.shapes()
+    assert len(wall.prims) == 1 and wall.prim_types[0] == 1                    # two coplanar triangles -> one quad
+    # transform ops apply in file order: scale, then rotate, then translate
+    np.testing.assert_allclose(light.to_world.transform_affine([1, 1, 0]), [0.25, -0.25, 3.0], atol=1e-12)
+    n = np.cross(light.prims[0, 1] - light.prims[0, 0], light.prims[0, 2] - light.prims[0, 0])
+    assert n[2] < 0                                                            # rotated to face the wall
+    assert scene.bsdfs_[light.bsdf_index]["flags"] == 1                         # twosided
+    with pytest.raises(ValueError):
+        bad = _XML.replace('type="diffuse" id="white"', 'type="roughconductor" id="white"')
+        (tmp_path / "bad.xml").write_text(bad)
+        mitr.load_file(str(tmp_path / "bad.xml"))
+
+
+def test_merge_quads(mitr):
+    from mitransient_b200.scene import merge_quads
+    v = np.array([[0, 0, 0], [2, 0, 0], [2, 1, 0], [0, 1, 0], [3, 3, 0]], dtype=float)
+    tris = v[np.array([[0, 1, 2], [0, 2, 3], [1, 4, 2]])]        # a rectangle (2 tris) + a lone triangle
+    prims, types = merge_quads(tris)
+    assert types.tolist() == [1, 0] and prims.shape == (2, 3, 3)
+    p0, p1, p2 = prims[0]
+    corners = {tuple(p0), tuple(p1), tuple(p2), tuple(p1 + p2 - p0)}
+    assert corners == {tuple(x) for x in v[:4]}
+    assert np.cross(p1 - p0, p2 - p0)[2] > 0                      # orientation of the source triangles is kept
+    trap = v[np.array([[0, 1, 2], [0, 2, 3]])].copy()
+    trap[1, 2] = [0.5, 1, 0]                                      # a trapezoid is not a parallelogram: not merged
+    assert merge_quads(trap)[1].tolist() == [0, 0]
