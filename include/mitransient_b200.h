@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 6
+#define TR_ABI_VERSION 7
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -46,12 +46,13 @@ typedef enum TrStatus {
  * emitter table, one sensor and its film (mitransient/utils.py:78-220 is the benchmark
  * scene expressed this way).
  *
- * A primitive is three vertices (p0, p1, p2).  TR_PRIM_TRIANGLE covers {p0 + u e1 + v e2 :
- * u, v >= 0, u + v <= 1}; TR_PRIM_QUAD covers the parallelogram {u, v in [0, 1]} whose fourth
- * corner is p1 + p2 - p0 (Mitsuba's analytic `rectangle`, a cube face, or two coplanar mesh
- * triangles merged by the loader).  e1 = p1 - p0, e2 = p2 - p0; the geometric normal is
- * normalize(cross(e1, e2)).                                                                */
-enum { TR_PRIM_TRIANGLE = 0, TR_PRIM_QUAD = 1 };
+ * A primitive is four vertices (p0, p1, p2, p3); e_k = p_k - p0.  TR_PRIM_TRIANGLE covers
+ * {p0 + u e1 + v e2 : u, v >= 0, u + v <= 1}; TR_PRIM_QUAD covers the parallelogram {u, v in [0, 1]}
+ * whose fourth corner is p1 + p2 - p0 (Mitsuba's analytic `rectangle`, or two coplanar mesh triangles
+ * merged by the loader); for both the geometric normal is normalize(cross(e1, e2)) and p3 is ignored.
+ * TR_PRIM_BOX is the SOLID parallelepiped {p0 + u e1 + v e2 + w e3 : u, v, w in [0, 1]} with outward
+ * face normals (Mitsuba's `cube`: one slab test instead of twelve triangles); det(e1, e2, e3) != 0.   */
+enum { TR_PRIM_TRIANGLE = 0, TR_PRIM_QUAD = 1, TR_PRIM_BOX = 2 };
 
 enum { TR_SHAPE_MESH = 0, TR_SHAPE_RECTANGLE = 1 };
 enum { TR_SHAPE_FLAG_SENSOR = 1 };       /* the shape carrying the nlos_capture_meter      */
@@ -123,7 +124,7 @@ typedef struct TrFilmDesc {  /* mitransient/films/transient_hdr_film.py:114-121 
 typedef struct TrSceneDesc {
     uint32_t abi_version;          /* must be TR_ABI_VERSION                                */
     uint32_t n_prims;
-    const float *prim_verts;       /* host, [n_prims][3 vertices][xyz], world space         */
+    const float *prim_verts;       /* host, [n_prims][4 vertices][xyz], world space         */
     const uint8_t *prim_types;     /* host, [n_prims] TR_PRIM_*                             */
     uint32_t n_shapes;
     const TrShapeDesc *shapes;     /* host                                                  */

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 6
+TR_ABI_VERSION = 7
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -13,7 +13,7 @@ TR_ERR_NO_DEVICE = -4
 TR_ERR_OUT_OF_MEMORY = -5
 
 TR_SHAPE_MESH, TR_SHAPE_RECTANGLE = 0, 1
-TR_PRIM_TRIANGLE, TR_PRIM_QUAD = 0, 1
+TR_PRIM_TRIANGLE, TR_PRIM_QUAD, TR_PRIM_BOX = 0, 1, 2
 TR_SHAPE_FLAG_SENSOR = 1
 TR_BSDF_DIFFUSE, TR_BSDF_NULL = 0, 1
 TR_BSDF_FLAG_TWOSIDED = 1

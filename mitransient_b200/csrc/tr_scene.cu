@@ -103,38 +103,73 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     std::vector<DevGeom> geom(np);
     std::vector<BuildTri> bprims(np);
     float slo[3] = {INFINITY, INFINITY, INFINITY}, shi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    std::vector<DevBoxExtra> box_extra;
+    std::vector<uint32_t> box_index(np, 0xffffffffu);
     for (uint32_t i = 0; i < np; ++i) {
-        const float *v = desc->prim_verts + 9 * (size_t) i;
-        for (int k = 0; k < 9; ++k) if (!std::isfinite(v[k])) { err = "non-finite vertex"; return false; }
-        if (desc->prim_types[i] > TR_PRIM_QUAD) { err = "unknown primitive type"; return false; }
-        const bool quad = desc->prim_types[i] == TR_PRIM_QUAD;
+        const float *v = desc->prim_verts + 12 * (size_t) i;
+        for (int k = 0; k < 12; ++k) if (!std::isfinite(v[k])) { err = "non-finite vertex"; return false; }
+        if (desc->prim_types[i] > TR_PRIM_BOX) { err = "unknown primitive type"; return false; }
+        const bool quad = desc->prim_types[i] == TR_PRIM_QUAD, box = desc->prim_types[i] == TR_PRIM_BOX;
         H3 p0 = h3(v[0], v[1], v[2]);
-        H3 e1 = h3(v[3], v[4], v[5]) - p0, e2 = h3(v[6], v[7], v[8]) - p0;
+        H3 e1 = h3(v[3], v[4], v[5]) - p0, e2 = h3(v[6], v[7], v[8]) - p0, e3 = h3(v[9], v[10], v[11]) - p0;
         H3 N = hcross(e1, e2);
         float nn = hdot(N, N);
         if (!(nn > 0.0f)) { err = "degenerate primitive (zero area)"; return false; }
         float inv_nn = 1.0f / nn;
         float len = sqrtf(nn);
         H3 n = N * (1.0f / len);
-        H3 a1 = hcross(e2, N) * inv_nn, a2 = hcross(N, e1) * inv_nn;
         DevPrim &t = prims[i];
         memset(&t, 0, sizeof(t));
-        t.N[0] = N.x; t.N[1] = N.y; t.N[2] = N.z; t.d0 = hdot(N, p0);
-        t.a1[0] = a1.x; t.a1[1] = a1.y; t.a1[2] = a1.z; t.c1 = hdot(p0, a1);
-        t.a2[0] = a2.x; t.a2[1] = a2.y; t.a2[2] = a2.z; t.c2 = hdot(p0, a2);
-        t.lim = quad ? 3.0f : 1.0f; t.shape = prim_shape[i]; t.prim = i;
-        t.area = quad ? len : 0.5f * len;
-        t.n[0] = n.x; t.n[1] = n.y; t.n[2] = n.z;
         DevGeom &g = geom[i];
         memset(&g, 0, sizeof(g));
-        g.p0[0] = p0.x; g.p0[1] = p0.y; g.p0[2] = p0.z; g.quad = quad ? 1u : 0u;
+        if (box) {   // same arithmetic as the oracle's build_scene (TR_PRIM_BOX)
+            H3 c23 = hcross(e2, e3), c31 = hcross(e3, e1);
+            float det = hdot(e1, c23);
+            if (!(std::fabs(det) > 0.0f)) { err = "degenerate box primitive"; return false; }
+            float inv_det = 1.0f / det;
+            H3 a1 = c23 * inv_det, a2 = c31 * inv_det, a3 = N * inv_det;
+            t.N[0] = a1.x; t.N[1] = a1.y; t.N[2] = a1.z; t.d0 = hdot(p0, a1);
+            t.a1[0] = a2.x; t.a1[1] = a2.y; t.a1[2] = a2.z; t.c1 = hdot(p0, a2);
+            t.a2[0] = a3.x; t.a2[1] = a3.y; t.a2[2] = a3.z; t.c2 = hdot(p0, a3);
+            float il0 = 1.0f / sqrtf(hdot(a1, a1)), il1 = 1.0f / sqrtf(hdot(a2, a2)), il2 = 1.0f / sqrtf(hdot(a3, a3));
+            t.n[0] = il0; t.n[1] = il1; t.n[2] = il2;
+            float fa0 = sqrtf(hdot(c23, c23)), fa1 = sqrtf(hdot(c31, c31)), fa2 = len;
+            t.lim = 5.0f;
+            t.area = 2.0f * ((fa2 + fa0) + fa1);
+            DevBoxExtra be; memset(&be, 0, sizeof(be));
+            be.e3[0] = e3.x; be.e3[1] = e3.y; be.e3[2] = e3.z; be.fa0 = fa0;
+            be.a1[0] = a1.x; be.a1[1] = a1.y; be.a1[2] = a1.z; be.fa1 = fa1;
+            be.a2[0] = a2.x; be.a2[1] = a2.y; be.a2[2] = a2.z; be.fa2 = fa2;
+            be.a3[0] = a3.x; be.a3[1] = a3.y; be.a3[2] = a3.z; be.il0 = il0; be.il1 = il1; be.il2 = il2;
+            box_index[i] = (uint32_t) box_extra.size();
+            box_extra.push_back(be);
+        } else {
+            H3 a1 = hcross(e2, N) * inv_nn, a2 = hcross(N, e1) * inv_nn;
+            t.N[0] = N.x; t.N[1] = N.y; t.N[2] = N.z; t.d0 = hdot(N, p0);
+            t.a1[0] = a1.x; t.a1[1] = a1.y; t.a1[2] = a1.z; t.c1 = hdot(p0, a1);
+            t.a2[0] = a2.x; t.a2[1] = a2.y; t.a2[2] = a2.z; t.c2 = hdot(p0, a2);
+            t.lim = quad ? 3.0f : 1.0f;
+            t.area = quad ? len : 0.5f * len;
+            t.n[0] = n.x; t.n[1] = n.y; t.n[2] = n.z;
+        }
+        t.shape = prim_shape[i]; t.prim = i;
+        g.p0[0] = p0.x; g.p0[1] = p0.y; g.p0[2] = p0.z; g.quad = desc->prim_types[i];
         g.e1[0] = e1.x; g.e1[1] = e1.y; g.e1[2] = e1.z; g.area = t.area;
         g.e2[0] = e2.x; g.e2[1] = e2.y; g.e2[2] = e2.z;
         BuildTri &b = bprims[i];
         b.idx = i;
         for (int a = 0; a < 3; ++a) {
-            float x0 = v[a], x1 = v[3 + a], x2 = v[6 + a], x3 = quad ? (x1 + x2 - x0) : x0;
-            b.lo[a] = std::min(std::min(x0, x3), std::min(x1, x2)); b.hi[a] = std::max(std::max(x0, x3), std::max(x1, x2));
+            float x0 = v[a], x1 = v[3 + a], x2 = v[6 + a], x3 = v[9 + a];
+            float lo, hi;
+            if (box) {   // all eight corners p0 + {0,1} e1 + {0,1} e2 + {0,1} e3
+                float d1 = x1 - x0, d2 = x2 - x0, d3 = x3 - x0;
+                lo = x0 + std::min(d1, 0.0f) + std::min(d2, 0.0f) + std::min(d3, 0.0f);
+                hi = x0 + std::max(d1, 0.0f) + std::max(d2, 0.0f) + std::max(d3, 0.0f);
+            } else {
+                float x4 = quad ? (x1 + x2 - x0) : x0;
+                lo = std::min(std::min(x0, x4), std::min(x1, x2)); hi = std::max(std::max(x0, x4), std::max(x1, x2));
+            }
+            b.lo[a] = lo; b.hi[a] = hi;
             b.c[a] = (b.lo[a] + b.hi[a]) * 0.5f;
             slo[a] = std::min(slo[a], b.lo[a]); shi[a] = std::max(shi[a], b.hi[a]);
         }
@@ -150,8 +185,15 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             const DevGeom &g = geom[i];
             H3 p0 = h3(g.p0[0], g.p0[1], g.p0[2]), e1 = h3(g.e1[0], g.e1[1], g.e1[2]), e2 = h3(g.e2[0], g.e2[1], g.e2[2]);
             H3 p1 = h3(p0.x + e1.x, p0.y + e1.y, p0.z + e1.z), p2 = h3(p0.x + e2.x, p0.y + e2.y, p0.z + e2.z);
+            H3 p12 = h3(p1.x + e2.x, p1.y + e2.y, p1.z + e2.z);
             verts.push_back(p0); verts.push_back(p1); verts.push_back(p2);
-            if (g.quad) verts.push_back(h3(p1.x + e2.x, p1.y + e2.y, p1.z + e2.z));
+            if (g.quad != TR_PRIM_TRIANGLE) verts.push_back(p12);
+            if (g.quad == TR_PRIM_BOX) {
+                const DevBoxExtra &be = box_extra[box_index[i]];
+                H3 e3 = h3(be.e3[0], be.e3[1], be.e3[2]);
+                verts.push_back(h3(p0.x + e3.x, p0.y + e3.y, p0.z + e3.z)); verts.push_back(h3(p1.x + e3.x, p1.y + e3.y, p1.z + e3.z));
+                verts.push_back(h3(p2.x + e3.x, p2.y + e3.y, p2.z + e3.z)); verts.push_back(h3(p12.x + e3.x, p12.y + e3.y, p12.z + e3.z));
+            }
         }
         float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (const H3 &x : verts) {
@@ -162,6 +204,7 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
         const float ext = fmaxf(fmaxf(hi3[0] - lo3[0], hi3[1] - lo3[1]), hi3[2] - lo3[2]);
         for (uint32_t i = 0; i < np; ++i) {
             DevPrim &t = prims[i];
+            if (t.lim == 5.0f) { n_occ++; continue; }     // a solid box is never a boundary
             H3 N = h3(t.N[0], t.N[1], t.N[2]);
             float tol = 1e-4f * sqrtf(hdot(N, N)) * ext;
             bool boundary = true;
@@ -179,8 +222,10 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     std::vector<DevNode> nodes;
     std::vector<DevPrim> prims_out;
     uint32_t nn_nodes = 0;
+    uint32_t n_planar = 0;
     if (np <= kBruteForceMaxPrims) {
-        prims_out = prims;
+        for (uint32_t i = 0; i < np; ++i) if (prims[i].lim != 5.0f) { prims_out.push_back(prims[i]); n_planar++; }
+        for (uint32_t i = 0; i < np; ++i) if (prims[i].lim == 5.0f) prims_out.push_back(prims[i]);
     } else {
         std::vector<BuildNode> bnodes;
         bnodes.reserve(2 * np);
@@ -296,7 +341,9 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     h.off_media = off; off += (uint32_t) (media.size() * sizeof(DevMedium));
     h.off_geom = off; off += np * (uint32_t) sizeof(DevGeom);
     h.off_sampling = off; off += align16((uint32_t) sampling.size());
-    h.off_occluders = off; h.n_occluders = n_occ;
+    h.off_box_extra = off; h.n_boxes = (uint32_t) box_extra.size(); off += (uint32_t) (box_extra.size() * sizeof(DevBoxExtra));
+    for (uint32_t i = 0; i < np; ++i) if (box_index[i] != 0xffffffffu) geom[i].extra = h.off_box_extra + box_index[i] * (uint32_t) sizeof(DevBoxExtra);
+    h.off_occluders = off; h.n_occluders = n_occ; h.n_planar = n_planar;
     if (nn_nodes == 0) off += n_occ * (uint32_t) sizeof(DevPrim);
     h.total_bytes = align16(off);
     for (uint32_t s = 0; s < ns; ++s)
@@ -311,10 +358,14 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     memcpy(&out.blob[h.off_media], media.data(), media.size() * sizeof(DevMedium));
     memcpy(&out.blob[h.off_geom], geom.data(), np * sizeof(DevGeom));
     if (!sampling.empty()) memcpy(&out.blob[h.off_sampling], sampling.data(), sampling.size());
-    if (nn_nodes == 0) {   // brute-force mode: compact copy of the possible occluders, original order
-        uint32_t k = 0;
+    if (!box_extra.empty()) memcpy(&out.blob[h.off_box_extra], box_extra.data(), box_extra.size() * sizeof(DevBoxExtra));
+    if (nn_nodes == 0) {   // brute-force mode: compact copy of the possible occluders, planar first then boxes
+        uint32_t k = 0, kp = 0;
         for (uint32_t i = 0; i < np; ++i)
-            if (prims[i].lim > 0.0f) memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims[i], sizeof(DevPrim));
+            if (prims_out[i].lim > 0.0f && prims_out[i].lim != 5.0f) { memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims_out[i], sizeof(DevPrim)); kp++; }
+        for (uint32_t i = 0; i < np; ++i)
+            if (prims_out[i].lim == 5.0f) memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims_out[i], sizeof(DevPrim));
+        reinterpret_cast<BlobHeader *>(out.blob.data())->n_occ_planar = kp;
     }
     out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
     out.shapes.assign(desc->shapes, desc->shapes + ns);

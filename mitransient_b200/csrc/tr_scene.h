@@ -20,33 +20,48 @@ struct BlobHeader {            // 96 bytes
     uint32_t off_geom;         // DevGeom[n_prims], ORIGINAL primitive order
     uint32_t off_occluders;    // DevPrim[n_occluders]: the non-boundary primitives (brute-force shadow loop)
     uint32_t n_occluders;
-    uint32_t _pad[6];
+    uint32_t off_box_extra;    // DevBoxExtra[n_boxes]: sampling data of box primitives
+    uint32_t n_boxes;
+    uint32_t n_planar;         // brute-force order: DevPrim[0, n_planar) planar, [n_planar, n_prims) boxes
+    uint32_t n_occ_planar;     // same split inside the occluder list
+    uint32_t _pad[2];
 };
 static_assert(sizeof(BlobHeader) == 96, "BlobHeader must be 96 bytes");
 
 // Intersection record of one planar primitive (triangle or parallelogram), 80 bytes = 5 x float4.
 //   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
-// Order in the blob: ORIGINAL order when the scene is small enough for the lock-step brute-force loop
-// (n_nodes == 0), BVH leaf order otherwise.
+// Order in the blob: when the scene is small enough for the lock-step brute-force loop (n_nodes == 0), planar
+// primitives in original order followed by boxes in original order (the oracle tests them in that order); BVH
+// leaf order otherwise.
 struct DevPrim {
-    float N[3];  float d0;
-    float a1[3]; float c1;
-    float a2[3]; float c2;
+    float N[3];  float d0;     // box: a1, c1   (duals of the parallelepiped: u = a1.x - c1, ...)
+    float a1[3]; float c1;     // box: a2, c2
+    float a2[3]; float c2;     // box: a3, c3
     float lim;                 // u + v <= |lim| : 1 for triangles, 3 for parallelograms; NEGATIVE for boundary
-                               // primitives (never occlude a shadow ray, see tr_scene.cu classify_boundary)
+                               // primitives (never occlude a shadow ray, see tr_scene.cu classify_boundary);
+                               // 5 marks a TR_PRIM_BOX
     uint32_t shape;
     uint32_t prim;             // original primitive index (tie-break key)
     float area;
-    float n[3];  uint32_t _r0; // unit geometric normal (shading)
+    float n[3];  uint32_t _r0; // unit geometric normal (shading); box: 1/|a1|, 1/|a2|, 1/|a3|
 };
 static_assert(sizeof(DevPrim) == 80, "DevPrim must be 80 bytes");
 
 struct DevGeom {               // 48 bytes, used by position sampling (emitters, hidden geometry)
-    float p0[3]; uint32_t quad;
+    float p0[3]; uint32_t quad;   // TR_PRIM_* (0 triangle, 1 quad, 2 box)
     float e1[3]; float area;
-    float e2[3]; uint32_t _r0;
+    float e2[3]; uint32_t extra;  // box: byte offset in the blob of its DevBoxExtra
 };
 static_assert(sizeof(DevGeom) == 48, "DevGeom must be 48 bytes");
+
+struct DevBoxExtra {           // 80 bytes: what sampling a point on a box needs beyond DevGeom
+    float e3[3]; float fa0;       // third edge; face areas |e2 x e3|, |e3 x e1|, |e1 x e2|
+    float a1[3]; float fa1;
+    float a2[3]; float fa2;
+    float a3[3]; float il0;       // duals and their inverse lengths (outward normals = +- a_k / |a_k|)
+    float il1, il2, _r0, _r1;
+};
+static_assert(sizeof(DevBoxExtra) == 80, "DevBoxExtra must be 80 bytes");
 
 struct DevNode {               // 32 bytes = 2 x float4, pre-order threaded BVH
     float lo[3]; uint32_t skip;   // node to visit when this one is missed / finished

@@ -62,18 +62,29 @@ _CUBE_FACES = (  # (origin corner, u edge, v edge) with u x v pointing outwards;
 )
 
 
-def _cube_prims():
-    """Mitsuba `cube` ([-1,1]^3): six parallelogram primitives with outward normals."""
+def _with_p3(prims3: np.ndarray, types: np.ndarray) -> np.ndarray:
+    """[n,3,3] planar primitives -> [n,4,3] (the fourth vertex is only meaningful for boxes)."""
+    p3 = np.where((types == _abi.TR_PRIM_QUAD)[:, None], prims3[:, 1] + prims3[:, 2] - prims3[:, 0], prims3[:, 0])
+    return np.concatenate([prims3, p3[:, None, :]], axis=1)
+
+
+def _cube_prims(as_box: bool = True):
+    """Mitsuba `cube` ([-1,1]^3): ONE solid box primitive (corner + three edges), or six outward-facing
+    parallelogram primitives when ``as_box`` is False."""
+    if as_box:
+        c = np.array([[(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)]], dtype=np.float64)
+        return c, np.full(1, _abi.TR_PRIM_BOX, dtype=np.uint8)
     prims = []
     for o, u, v in _CUBE_FACES:
         o, u, v = np.array(o, float), np.array(u, float), np.array(v, float)
         prims.append([o, o + u, o + v])
-    return np.array(prims, dtype=np.float64), np.full(len(prims), _abi.TR_PRIM_QUAD, dtype=np.uint8)
+    types = np.full(len(prims), _abi.TR_PRIM_QUAD, dtype=np.uint8)
+    return _with_p3(np.array(prims, dtype=np.float64), types), types
 
 
 def _rectangle_prims():
     """Mitsuba `rectangle` ([-1,1]^2 in z = 0, normal +z): one parallelogram primitive."""
-    return (np.array([[(-1, -1, 0), (1, -1, 0), (-1, 1, 0)]], dtype=np.float64),
+    return (np.array([[(-1, -1, 0), (1, -1, 0), (-1, 1, 0), (1, 1, 0)]], dtype=np.float64),
             np.full(1, _abi.TR_PRIM_QUAD, dtype=np.uint8))
 
 
@@ -154,7 +165,7 @@ def _apply(to_world: ScalarTransform4f, prims: np.ndarray, flip: bool) -> np.nda
     m = to_world.matrix
     out = prims @ m[:3, :3].T + m[:3, 3]
     if (np.linalg.det(m[:3, :3]) < 0) != bool(flip):
-        out = out[:, [0, 2, 1], :]  # swap e1/e2: keeps the geometric normal equal to the transformed normal
+        out = out[:, [0, 2, 1, 3], :]  # swap e1/e2: keeps the geometric normal equal to the transformed normal
     return np.ascontiguousarray(out)
 
 
@@ -249,8 +260,12 @@ class Shape:
     def surface_area(self) -> float:
         e1 = self.prims[:, 1] - self.prims[:, 0]
         e2 = self.prims[:, 2] - self.prims[:, 0]
-        w = np.where(self.prim_types == _abi.TR_PRIM_QUAD, 1.0, 0.5)
-        return float((w * np.linalg.norm(np.cross(e1, e2), axis=1)).sum())
+        e3 = self.prims[:, 3] - self.prims[:, 0]
+        a12 = np.linalg.norm(np.cross(e1, e2), axis=1)
+        box = 2.0 * (a12 + np.linalg.norm(np.cross(e2, e3), axis=1) + np.linalg.norm(np.cross(e3, e1), axis=1))
+        area = np.where(self.prim_types == _abi.TR_PRIM_BOX, box,
+                        np.where(self.prim_types == _abi.TR_PRIM_QUAD, 1.0, 0.5) * a12)
+        return float(area.sum())
 
 
 class Scene:
@@ -285,7 +300,7 @@ class Scene:
         """Build the ctypes ``TrSceneDesc`` for ``sensor`` (arrays are kept alive on ``self``)."""
         film = sensor.film()
         prims = [s.prims for s in self.shapes_]
-        prim_verts = np.ascontiguousarray(np.concatenate(prims, axis=0) if prims else np.zeros((0, 3, 3)),
+        prim_verts = np.ascontiguousarray(np.concatenate(prims, axis=0) if prims else np.zeros((0, 4, 3)),
                                           dtype=np.float32)
         prim_types = np.ascontiguousarray(np.concatenate([s.prim_types for s in self.shapes_])
                                           if prims else np.zeros(0), dtype=np.uint8)
@@ -486,7 +501,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
             if t == "rectangle":
                 base, ptypes = _rectangle_prims()
             elif t == "cube":
-                base, ptypes = _cube_prims()
+                base, ptypes = _cube_prims(as_box=bool(val.get("box_primitive", True)))
             elif t == "trimesh":   # in-memory triangle mesh (no Mitsuba counterpart): vertices (N,3), faces (M,3)
                 v = np.asarray(val["vertices"], dtype=np.float64).reshape(-1, 3)
                 f = np.asarray(val["faces"], dtype=np.int64).reshape(-1, 3)
@@ -500,6 +515,8 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
             if t in ("obj", "trimesh") and bool(val.get("merge_quads", True)) and len(base) > 1:
                 base, ptypes = merge_quads(base)     # coplanar triangle pairs -> parallelogram primitives
+            if base.shape[1] == 3:
+                base = _with_p3(base, ptypes)
             for ck, cv in val.items():      # every nested plugin of a shape must be one this build understands
                 ct = _type_of(cv)
                 if ct is not None and ck not in ("interior", "exterior") and ct not in _BSDF_TYPES + (

@@ -178,7 +178,11 @@ inline void sample_tea_32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1) 
 // A planar primitive (triangle or parallelogram) in intersection form:
 //   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
 // so that for a point p of the plane  u = dot(p,a1) - c1,  v = dot(p,a2) - c2  (p = p0 + u e1 + v e2).
-struct Prim { V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; bool boundary; };
+struct Prim {
+    V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; bool boundary;
+    // TR_PRIM_BOX: solid parallelepiped p0 + u e1 + v e2 + w e3; (a1,c1),(a2,c2),(a3,c3) are the duals giving (u,v,w)
+    bool box; V3 e3, a3; float c3, inv_len[3], face_area[3];
+};
 struct Shape {
     TrShapeDesc d;
     float inv_area;            // 1 / surface area
@@ -227,8 +231,9 @@ void classify_boundary_prims(Scene &sc) {
     float lo[3] = {kInf, kInf, kInf}, hi[3] = {-kInf, -kInf, -kInf};
     std::vector<V3> verts;
     for (const Prim &q : sc.prims) {
-        V3 c[4] = {q.p0, q.p0 + q.e1, q.p0 + q.e2, (q.p0 + q.e1) + q.e2};
-        for (int k = 0; k < (q.quad ? 4 : 3); ++k) {
+        V3 c[8] = {q.p0, q.p0 + q.e1, q.p0 + q.e2, (q.p0 + q.e1) + q.e2,
+                   q.p0 + q.e3, (q.p0 + q.e1) + q.e3, (q.p0 + q.e2) + q.e3, ((q.p0 + q.e1) + q.e2) + q.e3};
+        for (int k = 0; k < (q.box ? 8 : (q.quad ? 4 : 3)); ++k) {
             verts.push_back(c[k]);
             lo[0] = fminf(lo[0], c[k].x); hi[0] = fmaxf(hi[0], c[k].x);
             lo[1] = fminf(lo[1], c[k].y); hi[1] = fmaxf(hi[1], c[k].y);
@@ -238,8 +243,8 @@ void classify_boundary_prims(Scene &sc) {
     float extent = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     for (Prim &pr : sc.prims) {
         float tol = 1e-4f * sqrtf(dot(pr.N, pr.N)) * extent;
-        bool b = true;
-        for (const V3 &x : verts) if (!(plane_side(pr, x) >= -tol)) { b = false; break; }
+        bool b = !pr.box;      // a solid box is never a boundary
+        if (b) for (const V3 &x : verts) if (!(plane_side(pr, x) >= -tol)) { b = false; break; }
         pr.boundary = b;
     }
 }
@@ -260,22 +265,37 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
         sh.cdf.clear(); sh.pmf.clear();
         for (uint32_t k = 0; k < sh.d.prim_count; ++k) {
             uint32_t pi = sh.d.prim_begin + k;
-            const float *v = desc->prim_verts + 9 * (size_t) pi;
             Prim &t = sc.prims[pi];
+            const float *v = desc->prim_verts + 12 * (size_t) pi;
             t.quad = desc->prim_types[pi] == TR_PRIM_QUAD;
+            t.box = desc->prim_types[pi] == TR_PRIM_BOX;
             t.p0 = v3(v[0], v[1], v[2]);
             t.e1 = v3(v[3], v[4], v[5]) - t.p0;
             t.e2 = v3(v[6], v[7], v[8]) - t.p0;
+            t.e3 = v3(v[9], v[10], v[11]) - t.p0;
             t.N = cross(t.e1, t.e2);
             float nn = dot(t.N, t.N);
             float inv_nn = 1.0f / nn;
             float len = sqrtf(nn);
             t.n = t.N * (1.0f / len);
             t.d0 = dot(t.N, t.p0);
-            t.a1 = cross(t.e2, t.N) * inv_nn; t.c1 = dot(t.p0, t.a1);
-            t.a2 = cross(t.N, t.e1) * inv_nn; t.c2 = dot(t.p0, t.a2);
+            if (t.box) {
+                // duals of the parallelepiped: u = a1.(x - p0), v = a2.(x - p0), w = a3.(x - p0)
+                V3 c23 = cross(t.e2, t.e3), c31 = cross(t.e3, t.e1), c12 = t.N;
+                float inv_det = 1.0f / dot(t.e1, c23);
+                t.a1 = c23 * inv_det; t.c1 = dot(t.p0, t.a1);
+                t.a2 = c31 * inv_det; t.c2 = dot(t.p0, t.a2);
+                t.a3 = c12 * inv_det; t.c3 = dot(t.p0, t.a3);
+                t.inv_len[0] = 1.0f / sqrtf(dot(t.a1, t.a1)); t.inv_len[1] = 1.0f / sqrtf(dot(t.a2, t.a2));
+                t.inv_len[2] = 1.0f / sqrtf(dot(t.a3, t.a3));
+                t.face_area[0] = sqrtf(dot(c23, c23)); t.face_area[1] = sqrtf(dot(c31, c31)); t.face_area[2] = len;
+            } else {
+                t.a1 = cross(t.e2, t.N) * inv_nn; t.c1 = dot(t.p0, t.a1);
+                t.a2 = cross(t.N, t.e1) * inv_nn; t.c2 = dot(t.p0, t.a2);
+                t.a3 = v3(0, 0, 0); t.c3 = 0.0f;
+            }
             t.shape = si;
-            t.area = t.quad ? len : 0.5f * len;
+            t.area = t.box ? 2.0f * ((t.face_area[2] + t.face_area[0]) + t.face_area[1]) : (t.quad ? len : 0.5f * len);
             area_acc += (double) t.area;
             sh.pmf.push_back(t.area);
             sh.cdf.push_back((float) area_acc);
@@ -330,18 +350,52 @@ inline bool prim_test(const Prim &pr, const Ray &r, float *t_out, V3 *p_out) {
     return ok;
 }
 
+// Ray / box test of the arithmetic contract: three slabs in the parallelepiped's (u, v, w) coordinates.  A ray
+// that starts inside leaves through the far face.  *face = axis * 2 + (outward normal along +a_axis ? 1 : 0).
+inline bool box_test(const Prim &pr, const Ray &r, float *t_out, int *face) {
+    const V3 a[3] = {pr.a1, pr.a2, pr.a3}; const float c[3] = {pr.c1, pr.c2, pr.c3};
+    float tmin[3], tmax[3], ud[3];
+    for (int k = 0; k < 3; ++k) {
+        float uo = fmaf(a[k].z, r.o.z, fmaf(a[k].y, r.o.y, fmaf(a[k].x, r.o.x, -c[k])));
+        ud[k] = dot(a[k], r.d);
+        float inv = 1.0f / ud[k];
+        float t0 = (-uo) * inv, t1 = (1.0f - uo) * inv;
+        tmin[k] = fminf(t0, t1); tmax[k] = fmaxf(t0, t1);
+    }
+    float t_near = fmaxf(fmaxf(tmin[0], tmin[1]), tmin[2]), t_far = fminf(fminf(tmax[0], tmax[1]), tmax[2]);
+    bool entering = t_near >= 0.0f;
+    int k;
+    if (entering) k = (tmin[0] >= tmin[1] && tmin[0] >= tmin[2]) ? 0 : (tmin[1] >= tmin[2] ? 1 : 2);
+    else k = (tmax[0] <= tmax[1] && tmax[0] <= tmax[2]) ? 0 : (tmax[1] <= tmax[2] ? 1 : 2);
+    bool plus = entering ? !(ud[k] > 0.0f) : (ud[k] > 0.0f);
+    *face = k * 2 + (plus ? 1 : 0);
+    *t_out = entering ? t_near : t_far;
+    return (t_near <= t_far) && (t_far >= 0.0f) && (*t_out <= r.maxt);
+}
+inline V3 box_face_normal(const Prim &pr, int face) {
+    const V3 a = (face >> 1) == 0 ? pr.a1 : ((face >> 1) == 1 ? pr.a2 : pr.a3);
+    float il = pr.inv_len[face >> 1];
+    return (face & 1) ? a * il : (-a) * il;
+}
+
 Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: closest hit, brute force
     Hit h; h.valid = false; h.t = kInf; h.prim = 0xffffffffu; h.shape = 0;
     h.p = v3(0, 0, 0); h.n = v3(0, 0, 0); h.s = h.tt = v3(0, 0, 0);
-    for (uint32_t i = 0; i < sc.prims.size(); ++i) {
-        float t; V3 p;
-        if (prim_test(sc.prims[i], r, &t, &p) && t < h.t) {  // ascending index + strict '<' == lowest index wins ties
-            h.valid = true; h.t = t; h.prim = i; h.p = p;
+    int best_face = 0;
+    // planar primitives first, then boxes, each in ascending index; strict '<' == first tested wins ties
+    for (int pass = 0; pass < 2; ++pass)
+        for (uint32_t i = 0; i < sc.prims.size(); ++i) {
+            if (sc.prims[i].box != (pass == 1)) continue;
+            float t; V3 p; int face = 0;
+            bool ok = sc.prims[i].box ? box_test(sc.prims[i], r, &t, &face) : prim_test(sc.prims[i], r, &t, &p);
+            if (ok && t < h.t) { h.valid = true; h.t = t; h.prim = i; best_face = face; }
         }
-    }
     if (h.valid) {
         const Prim &pr = sc.prims[h.prim];
-        h.n = pr.n; h.s = pr.s; h.tt = pr.t; h.shape = pr.shape;
+        h.p = fma3(r.d, h.t, r.o);
+        h.shape = pr.shape;
+        if (pr.box) { h.n = box_face_normal(pr, best_face); V3 tt; coordinate_system(h.n, &h.s, &tt); h.tt = cross(h.n, h.s); }
+        else { h.n = pr.n; h.s = pr.s; h.tt = pr.t; }
     }
     return h;
 }
@@ -349,8 +403,8 @@ Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: clos
 bool ray_test(const Scene &sc, const Ray &r) {  // scene.ray_test: any hit
     for (uint32_t i = 0; i < sc.prims.size(); ++i) {
         if (sc.prims[i].boundary) continue;   // see classify_boundary_prims
-        float t; V3 p;
-        if (prim_test(sc.prims[i], r, &t, &p)) return true;
+        float t; V3 p; int face;
+        if (sc.prims[i].box ? box_test(sc.prims[i], r, &t, &face) : prim_test(sc.prims[i], r, &t, &p)) return true;
     }
     return false;
 }
@@ -414,6 +468,24 @@ inline void shape_sample_position(const Scene &sc, const Shape &sh, float u0, fl
         float pmf = sh.pmf[idx] * sh.area_norm;
         float u1r = (u1 - cdf_prev * sh.area_norm) / pmf;
         const Prim &tr = sc.prims[sh.d.prim_begin + idx];
+        if (tr.box) {
+            // a face by area (reusing u0), then a uniform point on it; faces in the order u=0, u=1, v=0, v=1, w=0, w=1
+            const float fa[6] = {tr.face_area[0], tr.face_area[0], tr.face_area[1], tr.face_area[1], tr.face_area[2], tr.face_area[2]};
+            float x = u0 * tr.area;
+            float cdf[5]; cdf[0] = fa[0];
+            for (int k = 1; k < 5; ++k) cdf[k] = cdf[k - 1] + fa[k];
+            int f = x < cdf[0] ? 0 : (x < cdf[1] ? 1 : (x < cdf[2] ? 2 : (x < cdf[3] ? 3 : (x < cdf[4] ? 4 : 5))));
+            float prev = f == 0 ? 0.0f : cdf[f - 1];
+            float s0 = fminf(fmaxf((x - prev) / fa[f], 0.0f), 1.0f);
+            const int axis = f >> 1; const bool far_side = (f & 1) != 0;
+            const V3 ea = axis == 0 ? tr.e2 : (axis == 1 ? tr.e3 : tr.e1), eb = axis == 0 ? tr.e3 : (axis == 1 ? tr.e1 : tr.e2);
+            const V3 en = axis == 0 ? tr.e1 : (axis == 1 ? tr.e2 : tr.e3);
+            V3 base = far_side ? tr.p0 + en : tr.p0;
+            *p = fma3(ea, s0, fma3(eb, u1r, base));
+            *n = box_face_normal(tr, f);
+            *pdf = sh.area_norm;
+            return;
+        }
         float b0, b1;
         if (tr.quad) { b0 = u0; b1 = u1r; }
         else { float t = sqrtf(fmaxf(1.0f - u0, 0.0f)); b0 = 1.0f - t; b1 = t * u1r; }

@@ -162,3 +162,24 @@ def test_film_scatter_add_and_develop_kernels(mitr, oracle):
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-7)
     dev = film.develop()[1].cpu().numpy()
     np.testing.assert_array_equal(dev, oracle.film_develop(got))
+
+
+def test_box_as_emitter_and_quads_variant(mitr, oracle):
+    """A `cube` that is an area light exercises position sampling on a box primitive (face by area, uniform point);
+    the same scene with box_primitive=False goes through six parallelograms."""
+    for as_box in (True, False):
+        d = mitr.cornell_box_config(24, 24, 96, 32, max_depth=5)
+        d["small-box"]["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": [2.0, 1.5, 1.0]}}
+        d["small-box"]["box_primitive"] = as_box
+        d["large-box"]["box_primitive"] = as_box
+        scene = mitr.load_dict(d)
+        assert len(scene.emitters()) == 2
+        integ = scene.integrator()
+        integ.collect_counters = True
+        steady, _ = integ.render(scene, seed=9, spp=32)
+        raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+        ref = oracle.render(scene, integ, seed=9, spp=32)
+        assert integ.last_counters == ref["counters"]
+        err = film_l1(raw, ref["transient"])
+        assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
+        np.testing.assert_allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)

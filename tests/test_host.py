@@ -28,25 +28,32 @@ def test_cornell_box_scene(mitr):
     assert d["integrator"]["max_depth"] == 8 and d["sensor"]["film"]["temporal_bins"] == 300
     scene = mitr.load_dict(d)
     assert len(scene.shapes()) == 8 and len(scene.emitters()) == 1 and len(scene.bsdfs_) == 3
-    assert sum(len(s.prims) for s in scene.shapes()) == 6 + 12      # 6 rectangles + 2 cubes x 6 faces
+    assert sum(len(s.prims) for s in scene.shapes()) == 6 + 2       # 6 rectangles + 2 cubes (one box primitive each)
     light = scene.shapes()[0]
     assert light.kind == "rectangle" and light.emitter_index == 0
     assert abs(light.surface_area() - (2 * 0.23) * (2 * 0.19)) < 1e-9
     n = np.cross(light.prims[0, 1] - light.prims[0, 0], light.prims[0, 2] - light.prims[0, 0])
     assert n[1] < 0 and abs(n[0]) < 1e-12 and abs(n[2]) < 1e-12     # the light faces down
+    np.testing.assert_allclose(light.prims[0, 3], light.prims[0, 1] + light.prims[0, 2] - light.prims[0, 0], atol=1e-12)
     for s in scene.shapes()[1:6]:                                    # walls face the inside of the box
-        c = s.prims[0].mean(axis=0)
+        c = s.prims[0, :3].mean(axis=0)
         nn = np.cross(s.prims[0, 1] - s.prims[0, 0], s.prims[0, 2] - s.prims[0, 0])
         assert np.dot(nn, -c) > 0, s.name
-    for s in scene.shapes()[6:]:                                     # cube faces point outwards
-        centre = s.prims.reshape(-1, 3).mean(axis=0)
-        for p in s.prims:
-            fc = p[0] + 0.5 * (p[1] - p[0]) + 0.5 * (p[2] - p[0])
-            assert np.dot(np.cross(p[1] - p[0], p[2] - p[0]), fc - centre) > 0
-        assert abs(s.surface_area() - 6 * np.linalg.norm(np.cross(s.prims[0, 1] - s.prims[0, 0],
-                                                                    s.prims[0, 2] - s.prims[0, 0]))) < 1.0
+    small, large = scene.shapes()[6:]
+    assert small.prim_types.tolist() == [2] and abs(small.surface_area() - 6 * 0.36) < 1e-9
+    e = large.prims[0, 1:] - large.prims[0, 0]
+    assert np.linalg.det(e) > 0 and np.allclose(sorted(np.linalg.norm(e, axis=1)), [0.6, 0.6, 1.22])
+    # the same cubes as six outward-facing quads (box_primitive = False)
+    d6 = mitr.cornell_box()
+    d6["small-box"]["box_primitive"] = False
+    s6 = mitr.load_dict(d6).shapes()[6]
+    assert len(s6.prims) == 6 and abs(s6.surface_area() - small.surface_area()) < 1e-9
+    centre = s6.prims[:, :3].reshape(-1, 3).mean(axis=0)
+    for p in s6.prims:
+        fc = p[0] + 0.5 * (p[1] - p[0]) + 0.5 * (p[2] - p[0])
+        assert np.dot(np.cross(p[1] - p[0], p[2] - p[0]), fc - centre) > 0
     desc = scene.describe(scene.sensors()[0])
-    assert desc.n_prims == 18 and desc.n_shapes == 8 and desc.film.temporal_bins == 300
+    assert desc.n_prims == 8 and desc.n_shapes == 8 and desc.film.temporal_bins == 300
     cfg = mitr.cornell_box_config(512, 512, 1024, 256)
     assert cfg["sensor"]["film"]["bin_width_opl"] == 6.0 / 1024 and cfg["sensor"]["film"]["start_opl"] == 3.5
 
@@ -151,7 +158,7 @@ def test_xml_scene_file(mitr, tmp_path):
     assert scene.integrator().max_depth == 5 and scene.sensors()[0].film().size() == (24, 24)
     assert len(scene.shapes()) == 2 and len(scene.emitters()) == 1
     wall, light = scene.shapes()
-    assert len(wall.prims) == 1 and wall.prim_types[0] == 1                    # two coplanar triangles -> one quad
+    assert len(wall.prims) == 1 and wall.prim_types[0] == 1 and wall.prims.shape == (1, 4, 3)   # two coplanar triangles -> one quad
     # transform ops apply in file order: scale, then rotate, then translate
     np.testing.assert_allclose(light.to_world.transform_affine([1, 1, 0]), [0.25, -0.25, 3.0], atol=1e-12)
     n = np.cross(light.prims[0, 1] - light.prims[0, 0], light.prims[0, 2] - light.prims[0, 0])
@@ -169,7 +176,7 @@ def test_merge_quads(mitr):
     tris = v[np.array([[0, 1, 2], [0, 2, 3], [1, 4, 2]])]        # a rectangle (2 tris) + a lone triangle
     prims, types = merge_quads(tris)
     assert types.tolist() == [1, 0] and prims.shape == (2, 3, 3)
-    p0, p1, p2 = prims[0]
+    p0, p1, p2 = prims[0][:3]
     corners = {tuple(p0), tuple(p1), tuple(p2), tuple(p1 + p2 - p0)}
     assert corners == {tuple(x) for x in v[:4]}
     assert np.cross(p1 - p0, p2 - p0)[2] > 0                      # orientation of the source triangles is kept

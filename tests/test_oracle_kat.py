@@ -204,6 +204,35 @@ def test_kat5_furnace(oracle, mitr):
     np.testing.assert_allclose(r["transient"][..., :3].sum(axis=2), r["steady"], rtol=2e-5)
 
 
+def test_box_primitive_equals_six_quads(oracle, mitr):
+    """TR_PRIM_BOX (one slab test) gives the hits of the same cube described as six parallelograms."""
+    d6 = mitr.cornell_box_config(16, 16, 32, 4)
+    d6["small-box"]["box_primitive"] = False
+    d6["large-box"]["box_primitive"] = False
+    s1, s6 = mitr.load_dict(mitr.cornell_box_config(16, 16, 32, 4)), mitr.load_dict(d6)
+    rng = np.random.default_rng(3)
+    n_hit = 0
+    for _ in range(1500):
+        o = rng.uniform(-0.95, 0.95, 3)
+        dd = rng.normal(size=3)
+        dd /= np.linalg.norm(dd)
+        a = oracle.ray_intersect(s1, s1.sensors()[0], o, dd)
+        b = oracle.ray_intersect(s6, s6.sensors()[0], o, dd)
+        assert (a is None) == (b is None)
+        if a is None:
+            continue
+        n_hit += 1
+        if abs(a["t"] - b["t"]) > 1e-4:          # grazing an edge: the two descriptions may pick different faces
+            continue
+        assert a["shape"] == b["shape"]
+        if a["shape"] >= 6 and np.abs(a["n"] - b["n"]).max() > 1e-4:
+            assert abs(np.dot(a["n"], b["n"])) < 0.1          # adjacent faces at an edge
+    assert n_hit > 1000
+    ra = oracle.render(s1, s1.integrator(), spp=64, seed=0)["steady"]
+    rb = oracle.render(s6, s6.integrator(), spp=64, seed=0)["steady"]
+    assert abs(ra.mean() - rb.mean()) / rb.mean() < 2e-3
+
+
 def test_seed_changes_result_and_is_deterministic(oracle, mitr):
     scene = mitr.load_dict(mitr.cornell_box_config(16, 16, 32, 4))
     a = oracle.render(scene, scene.integrator(), spp=4, seed=0, n_threads=1)
