@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 7
+#define TR_ABI_VERSION 8
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -114,11 +114,27 @@ typedef struct TrSensorDesc {
     int32_t medium;         /* index of the medium the sensor sits in, or -1                */
 } TrSensorDesc;
 
+/* Film kinds.  TR_FILM_TRANSIENT_HDR: time histogram, film[y][x][t][c]
+ * (mitransient/films/transient_hdr_film.py, render/transient_image_block.py:63-68).  With
+ * laser_scan_width/height > 0 it is the `exhaustive_scan` layout film[y][x][ly][lx][t][c] addressed with
+ * the reference's flat index ((((y*W + x)*Lw + laser_x)*Lh + laser_y)*T + t)*C
+ * (transient_image_block.py:59-66, 134-140).
+ * TR_FILM_PHASOR_HDR: frequency-domain film (mitransient/films/phasor_hdr_film.py,
+ * render/phasor_image_block.py:43-67): film[y][x][2*F + 1] = (Re, Im) per stored frequency + weight;
+ * a deposit (spec, opl) adds spec.x * (cos, sin)(fmod(-2 pi f (opl - start_opl), 2 pi)) for every
+ * frequency f; there is no time window (every finite opl counts).                                    */
+enum { TR_FILM_TRANSIENT_HDR = 0, TR_FILM_PHASOR_HDR = 1 };
+
 typedef struct TrFilmDesc {  /* mitransient/films/transient_hdr_film.py:114-121             */
     uint32_t width, height;
     uint32_t temporal_bins;
     float start_opl;
     float bin_width_opl;
+    uint32_t laser_scan_width, laser_scan_height; /* exhaustive_scan film (transient_hdr_film.py:119-121); 0, 0 = off */
+    uint32_t type;                 /* TR_FILM_*                                             */
+    uint32_t n_frequencies;        /* phasor film: F                                        */
+    uint32_t _pad;
+    const float *frequencies;      /* phasor film: host, [F] (phasor_hdr_film.py:125-137)   */
 } TrFilmDesc;
 
 typedef struct TrSceneDesc {
@@ -176,7 +192,7 @@ typedef struct TrRenderParams {
     uint32_t tile_size;
     uint32_t rank, world;
     int32_t film_channels;  /* layout of `film` passed to tr_render: 4 = raw RGBW
-                               (develop(raw=True)), 3 = developed RGB                      */
+                               (develop(raw=True)), 3 = developed RGB; phasor film: 2F + 1  */
     int32_t accumulate;     /* 0: owned pixels are overwritten; 1: added to (multi-pass)    */
     /* transient_nlos_path */
     int32_t capture_type;   /* TR_CAPTURE_*                                                 */
@@ -227,7 +243,8 @@ int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes,
  * (transientpath.py:88-326) / TransientNLOSPath.sample (transientnlospath.py:673-927)
  * -> add_transient_data (transient_hdr_film.py:250-276) -> TransientImageBlock.put_/accum
  * (transient_image_block.py:103-151,79-81), plus the steady-image splat.
- *   film     device, float[H][W][T][film_channels]
+ *   film     device, float[H][W][T][film_channels]; exhaustive_scan: float[H][W][Lh][Lw][T][film_channels]
+ *            (must be zero-filled by the caller, accumulate = 1); phasor film: float[H][W][2F+1]
  *   steady   device, float[H][W][3]   (mean of L over total_spp), may be NULL
  *   counters device, TrCounters accumulated with atomics, may be NULL
  * Asynchronous on `stream`.                                                               */

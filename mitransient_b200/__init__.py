@@ -15,6 +15,7 @@ from . import _abi
 from . import films, integrators, sensors            # registers the plugins
 from ._lib import TransientError, lib_path
 from .films.transient_hdr_film import TransientHDRFilm
+from .films.phasor_hdr_film import PhasorHDRFilm
 from .integrators.common import TransientADIntegrator
 from .integrators.transientnlospath import CaptureType, TransientNLOSPath
 from .integrators.transientpath import TransientPath
@@ -41,6 +42,16 @@ def render(scene: Scene, params=None, sensor=0, seed: int = 0, spp: int = 0, **k
 
 
 def set_variant(*names):
-    """Accepted for source compatibility with ``mi.set_variant``; this build has exactly one variant
-    (CUDA, RGB, fp32)."""
-    return "cuda_rgb"
+    """``mi.set_variant`` for source compatibility.  Everything runs in CUDA fp32; the only thing a variant name
+    selects is the colour mode: names containing ``mono`` (``llvm_ad_mono``, ``cuda_mono`` ...) switch to
+    monochromatic rendering (colours become their luminance; required by ``phasor_hdr_film``), every other name
+    is RGB.  Returns the active variant, ``cuda_rgb`` or ``cuda_mono``."""
+    from . import colour_mode as _v
+    name = names[0] if names else "cuda_rgb"
+    _v.set_monochromatic("mono" in str(name))
+    return variant()
+
+
+def variant() -> str:
+    from . import colour_mode as _v
+    return "cuda_mono" if _v.is_monochromatic() else "cuda_rgb"

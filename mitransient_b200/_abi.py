@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 7
+TR_ABI_VERSION = 8
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -32,6 +32,7 @@ TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES = 128
 TR_FLAG_DISCARD_DIRECT_PATHS = 256
 
 TR_CAPTURE_SINGLE, TR_CAPTURE_CONFOCAL, TR_CAPTURE_EXHAUSTIVE = 0, 1, 2
+TR_FILM_TRANSIENT_HDR, TR_FILM_PHASOR_HDR = 0, 1
 
 
 class TrShapeDesc(C.Structure):
@@ -62,7 +63,10 @@ class TrSensorDesc(C.Structure):
 
 class TrFilmDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("temporal_bins", C.c_uint32),
-                ("start_opl", C.c_float), ("bin_width_opl", C.c_float)]
+                ("start_opl", C.c_float), ("bin_width_opl", C.c_float),
+                ("laser_scan_width", C.c_uint32), ("laser_scan_height", C.c_uint32),
+                ("type", C.c_uint32), ("n_frequencies", C.c_uint32), ("_pad", C.c_uint32),
+                ("frequencies", C.POINTER(C.c_float))]
 
 
 class TrSceneDesc(C.Structure):

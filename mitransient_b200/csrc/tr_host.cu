@@ -85,7 +85,10 @@ extern "C" int tr_render_to_host(const TrScene *scene_c, const TrRenderParams *p
     if (params->accumulate) return fail(TR_ERR_UNSUPPORTED, "tr_render_to_host does not accumulate");
     cudaStream_t stream = (cudaStream_t) stream_v;
 
-    const uint32_t W = sc.film.width, H = sc.film.height, T = sc.film.temporal_bins;
+    if (sc.film.laser_scan_width) return fail(TR_ERR_UNSUPPORTED, "tr_render_to_host does not support exhaustive_scan films");
+    const uint32_t W = sc.film.width, H = sc.film.height;
+    // floats per pixel: T * C (time histogram) or 2F + 1 (phasor film, film_channels = 2F + 1)
+    const uint32_t T = sc.film.type == TR_FILM_PHASOR_HDR ? 1u : sc.film.temporal_bins;
     const int C = params->film_channels;
     const size_t row_floats = (size_t) W * T * C;
     // band height: ~96 MiB of film per band (the first copy starts early, the last one ends soon after the last kernel)

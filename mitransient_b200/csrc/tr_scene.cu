@@ -81,6 +81,15 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     if (f.width == 0 || f.height == 0 || f.temporal_bins == 0) { err = "film has a zero dimension"; return false; }
     if (!(f.bin_width_opl > 0.0f)) { err = "bin_width_opl must be > 0"; return false; }
     if ((uint64_t) f.width * f.height >= (1ull << 31)) { err = "film too large"; return false; }
+    if (f.type != TR_FILM_TRANSIENT_HDR && f.type != TR_FILM_PHASOR_HDR) { err = "unknown film type"; return false; }
+    if (f.type == TR_FILM_PHASOR_HDR && (f.n_frequencies == 0 || !f.frequencies || f.n_frequencies > 4096)) {
+        err = "phasor film needs 1..4096 frequencies"; return false;
+    }
+    if ((f.laser_scan_width == 0) != (f.laser_scan_height == 0)) { err = "laser_scan_width and laser_scan_height must both be set"; return false; }
+    if (f.laser_scan_width && f.type != TR_FILM_TRANSIENT_HDR) { err = "exhaustive_scan is a transient_hdr_film layout"; return false; }
+    if ((uint64_t) f.width * f.height * std::max(1u, f.laser_scan_width) * std::max(1u, f.laser_scan_height) * f.temporal_bins >= (1ull << 40)) {
+        err = "film too large"; return false;
+    }
 
     const uint32_t np = desc->n_prims, ns = desc->n_shapes;
     std::vector<uint32_t> prim_shape(np, 0xffffffffu);
@@ -368,6 +377,9 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
         reinterpret_cast<BlobHeader *>(out.blob.data())->n_occ_planar = kp;
     }
     out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
+    out.frequencies.clear();
+    if (f.type == TR_FILM_PHASOR_HDR) out.frequencies.assign(f.frequencies, f.frequencies + f.n_frequencies);
+    out.film.frequencies = nullptr;      // the caller's array is not ours to keep
     out.shapes.assign(desc->shapes, desc->shapes + ns);
     out.emitters.assign(desc->emitters, desc->emitters + desc->n_emitters);
     out.shape_area.resize(ns);
@@ -399,6 +411,12 @@ int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene) {
     TR_CUDA_OR(cudaMemcpy(s->impl.d_blob, s->impl.blob.data(), s->impl.blob.size(), cudaMemcpyHostToDevice),
                { cudaFree(s->impl.d_blob); delete s; });
     TR_CUDA_OR(cudaMalloc(&s->impl.d_scratch, 4096), { cudaFree(s->impl.d_blob); delete s; });
+    if (!s->impl.frequencies.empty()) {
+        const size_t fb = s->impl.frequencies.size() * sizeof(float);
+        TR_CUDA_OR(cudaMalloc(&s->impl.d_freqs, fb), { cudaFree(s->impl.d_scratch); cudaFree(s->impl.d_blob); delete s; });
+        TR_CUDA_OR(cudaMemcpy(s->impl.d_freqs, s->impl.frequencies.data(), fb, cudaMemcpyHostToDevice),
+                   { cudaFree(s->impl.d_freqs); cudaFree(s->impl.d_scratch); cudaFree(s->impl.d_blob); delete s; });
+    }
     *out_scene = s;
     return TR_OK;
 }
@@ -409,6 +427,7 @@ void tr_scene_destroy(TrScene *scene) {
     if (scene->impl.d_pixels) cudaFree(scene->impl.d_pixels);
     if (scene->impl.d_scratch) cudaFree(scene->impl.d_scratch);
     if (scene->impl.d_nlos) cudaFree(scene->impl.d_nlos);
+    if (scene->impl.d_freqs) cudaFree(scene->impl.d_freqs);
     delete scene;
 }
 

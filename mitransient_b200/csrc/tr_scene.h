@@ -105,6 +105,7 @@ struct SceneImpl {
     void *d_scratch = nullptr;
     // host copies used by the NLOS prepare step (transientnlospath.py:251-383)
     std::vector<TrShapeDesc> shapes; std::vector<TrEmitterDesc> emitters; std::vector<float> shape_area;
+    std::vector<float> frequencies; void *d_freqs = nullptr;   // phasor film: host / device copy of TrFilmDesc.frequencies
     void *d_nlos = nullptr;              // float4 targets[H*W + 1] | float hg_table[2 * n_shapes]
     uint32_t nlos_key = 0xffffffffu; float hg_sum = 0.f, hg_norm = 0.f;
 };

@@ -11,6 +11,7 @@ import ctypes as C
 from typing import Sequence
 
 from .. import _abi, _lib
+from .. import colour_mode as _variant
 from ..scene import Properties
 
 
@@ -64,15 +65,29 @@ class TransientHDRFilm:
         d = _abi.TrFilmDesc()
         d.width, d.height, d.temporal_bins = self._width, self._height, self.temporal_bins
         d.start_opl, d.bin_width_opl = self.start_opl, self.bin_width_opl
+        d.type = _abi.TR_FILM_TRANSIENT_HDR
+        if self.exhaustive_scan:               # transient_image_block.py:59-66
+            d.laser_scan_width, d.laser_scan_height = self.laser_scan_width, self.laser_scan_height
         return d
+
+    def state_key(self):
+        return ("transient_hdr_film", self.exhaustive_scan, self.laser_scan_width, self.laser_scan_height)
+
+    def raw_channels(self) -> int:
+        return len(self.channels)
+
+    def needs_zeroed_accumulate(self) -> bool:
+        """exhaustive_scan films are accumulated with global vector reductions (a pixel owns Lw*Lh histograms):
+        the kernel adds into the zero-filled storage instead of overwriting it."""
+        return self.exhaustive_scan
 
     def check_supported(self):
         if self._rfilter != "box":
             # the reference's TransientImageBlock rejects everything else (transient_image_block.py:150-151)
             raise ValueError("TransientImageBlock::put_(): using a rfilter but it is not supported "
                              "(only the box reconstruction filter)")
-        if self.exhaustive_scan:
-            raise NotImplementedError("exhaustive_scan films are out of scope of this build (SURVEY section 8f)")
+        if self.exhaustive_scan and (self.laser_scan_width <= 0 or self.laser_scan_height <= 0):
+            raise ValueError("exhaustive_scan needs laser_scan_width and laser_scan_height > 0")
         if self._crop_offset != (0, 0) or self._crop_size != (self._width, self._height):
             raise NotImplementedError("crop windows are not supported by the transient block "
                                       "(the reference sizes it from size(), transient_hdr_film.py:194-195)")
@@ -86,8 +101,11 @@ class TransientHDRFilm:
             raise NotImplementedError("AOVs are not supported")
         _lib.check(_lib.load().tr_device_check())
         w, h = self.size()
-        self.transient_storage = torch.zeros((h, w, self.temporal_bins, len(self.channels)),
-                                             dtype=torch.float32, device="cuda")
+        if self.exhaustive_scan:               # (H, W, Lh, Lw, T, C)   transient_image_block.py:63-66
+            shape = (h, w, self.laser_scan_height, self.laser_scan_width, self.temporal_bins, len(self.channels))
+        else:
+            shape = (h, w, self.temporal_bins, len(self.channels))
+        self.transient_storage = torch.zeros(shape, dtype=torch.float32, device="cuda")
         self.steady_storage = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
         return len(self.channels)
 
@@ -104,6 +122,8 @@ class TransientHDRFilm:
         import torch
         if self.transient_storage is None:
             raise RuntimeError("No transient storage allocated, was prepare() called first?")
+        if self.exhaustive_scan:
+            raise NotImplementedError("add_transient_data on an exhaustive_scan film is only available through render()")
         n = int(distance.shape[0])
         spec = spec * ray_weight
         if active is not None:
@@ -117,7 +137,12 @@ class TransientHDRFilm:
 
     # ---- develop (transient_hdr_film.py:210-248)
     def develop(self, raw: bool = False):
-        return self.steady_storage, self.develop_transient_(raw=raw)
+        steady, transient = self.steady_storage, self.develop_transient_(raw=raw)
+        if _variant.is_monochromatic():        # "L" instead of "RGB" (transient_hdr_film.py:174, hdrfilm luminance)
+            steady = steady[..., :1]
+            if not raw:
+                transient = transient[..., :1]
+        return steady, transient
 
     def develop_transient_(self, raw: bool = False):
         import torch

@@ -126,8 +126,9 @@ class TransientADIntegrator:
         lib = _lib.load()
         counters = torch.zeros(8, dtype=torch.int64, device="cuda") if self.collect_counters else None
         for i, (seed_i, spp_i) in enumerate(passes):
-            params = self.make_params(spp_i, total_spp, seed_i, rank=rank, world=world, film_channels=4,
-                                      accumulate=(i > 0))
+            params = self.make_params(spp_i, total_spp, seed_i, rank=rank, world=world,
+                                      film_channels=film.raw_channels(),
+                                      accumulate=(i > 0) or film.needs_zeroed_accumulate())
             self.fill_params_(params, scene, sensor)
             _lib.check(lib.tr_render(dev.handle, C.byref(params), film.transient_storage.data_ptr(),
                                      film.steady_storage.data_ptr(),
@@ -156,6 +157,8 @@ class TransientADIntegrator:
         self.check_transient_(scene, sensor)
         self.check_scene_(scene, sensor)
         film.check_supported()
+        if film.raw_channels() != 4 or film.needs_zeroed_accumulate():
+            raise NotImplementedError("render_to_host supports plain transient_hdr_film films")
         s = sensor.sampler().clone()
         if spp != 0:
             s.set_sample_count(spp)

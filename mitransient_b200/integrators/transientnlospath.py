@@ -2,7 +2,8 @@
 
 Plugin parameters, defaults and rejections follow transientnlospath.py:201-249; ``prepare`` (:251-383: hidden
 geometry area distribution, per-pixel sensor targets, laser targets) and ``sample`` (:673-927) run on the device
-(csrc/tr_render.cu, NLOS branch).  Exhaustive captures and AD are out of scope.
+(csrc/tr_render.cu, NLOS branch).  Exhaustive captures are implemented for equal sensor / laser grids
+(``force_equal_illumination_scanning=True``, the default) on an ``exhaustive_scan`` film; AD is out of scope.
 """
 from __future__ import annotations
 
@@ -70,8 +71,17 @@ class TransientNLOSPath(TransientADIntegrator):
                              "meter. You should have only 1.")
         if ems[0]["type"] != _abi.TR_EMITTER_PROJECTOR:
             raise NotImplementedError("transient_nlos_path expects a `projector` emitter (the laser)")
+        film = sensor.film()
         if self.capture_type == CaptureType.Exhaustive:
-            raise NotImplementedError("Exhaustive captures are out of scope of this build (SURVEY section 8f)")
+            if not self.force_equal_grids:
+                raise NotImplementedError("Exhaustive captures are implemented for force_equal_illumination_scanning=True "
+                                          "(the illumination_scan_fov laser grid, transientnlospath.py:349-379, is not)")
+            if not getattr(film, "exhaustive_scan", False):
+                raise ValueError("Exhaustive captures need a transient_hdr_film with exhaustive_scan=True "
+                                 "(laser_scan_width / laser_scan_height = the film size)")
+            if (film.laser_scan_width, film.laser_scan_height) != tuple(film.size()):           # :345-348
+                raise AssertionError("Sensor and laser scan resolution must be equal if "
+                                     "force_equal_illumination_scanning is set to True")
         if sensor.is_confocal:
             raise NotImplementedError("1x1 confocal sensors (original_film_width/height) are not implemented; use "
                                       "capture_type='confocal' on the integrator")

@@ -22,6 +22,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import _abi
+from . import colour_mode as _variant
 from .transforms import ScalarTransform4f, parse_fov, perspective_projection
 
 
@@ -318,14 +319,15 @@ class Scene:
         bsdfs = (_abi.TrBsdfDesc * max(1, len(self.bsdfs_)))()
         for i, b in enumerate(self.bsdfs_):
             bsdfs[i].type, bsdfs[i].flags = b["type"], b["flags"]
-            bsdfs[i].reflectance[:] = [float(x) for x in b["reflectance"]]
+            bsdfs[i].reflectance[:] = [float(x) for x in _variant.colour(b["reflectance"])]
         emitters = (_abi.TrEmitterDesc * max(1, len(self.emitters_)))()
         for i, e in enumerate(self.emitters_):
             emitters[i].type, emitters[i].shape = e["type"], e["shape"]
-            emitters[i].radiance[:] = [float(x) for x in e["radiance"]]
+            emitters[i].radiance[:] = [float(x) for x in _variant.colour(e["radiance"])]
             spec = e.get("spec")
             if spec is not None:      # projector: read the CURRENT state (nlos.focus_* may have re-aimed it)
-                emitters[i].radiance[:] = [float(x) for x in _rgb(spec.get("irradiance"), 1.0) * float(spec.get("scale", 1.0))]
+                emitters[i].radiance[:] = [float(x) for x in
+                                           _variant.colour(_rgb(spec.get("irradiance"), 1.0) * float(spec.get("scale", 1.0)))]
                 emitters[i].fov_x = float(parse_fov(float(spec.get("fov", 45.0)), spec.get("fov_axis", "x"), 1.0))
                 tw = _to_transform(spec.get("to_world"))
                 emitters[i].to_world[:] = tw.affine3x4().reshape(-1).tolist()
@@ -334,8 +336,8 @@ class Scene:
                 emitters[i].camera_to_sample[:] = c2s.matrix.astype(np.float32).reshape(-1).tolist()
         media = (_abi.TrMediumDesc * max(1, len(self.media_)))()
         for i, m in enumerate(self.media_):
-            media[i].sigma_t[:] = [float(x) for x in m["sigma_t"]]
-            media[i].albedo[:] = [float(x) for x in m["albedo"]]
+            media[i].sigma_t[:] = [float(x) for x in _variant.colour(m["sigma_t"])]
+            media[i].albedo[:] = [float(x) for x in _variant.colour(m["albedo"])]
             media[i].g, media[i].scale = float(m["g"]), float(m.get("scale", 1.0))
 
         desc = _abi.TrSceneDesc()
@@ -349,14 +351,14 @@ class Scene:
         desc.n_media, desc.media = len(self.media_), media
         desc.sensor = sensor.describe(self)
         desc.film = film.describe()
-        self._keepalive = [prim_verts, prim_types, shapes, bsdfs, emitters, media]
+        self._keepalive = [prim_verts, prim_types, shapes, bsdfs, emitters, media, film]
         return desc
 
     def description_key(self, sensor):
         f = sensor.film()
         em = tuple(_to_transform(e["spec"].get("to_world")).matrix.tobytes() for e in self.emitters_ if e.get("spec"))
         return (id(sensor), f.size(), f.temporal_bins, float(f.start_opl), float(f.bin_width_opl),
-                sensor.state_key(), em)
+                sensor.state_key(), em, _variant.is_monochromatic(), f.state_key())
 
     def __repr__(self):
         return (f"Scene[shapes={len(self.shapes_)}, primitives={sum(len(s.prims) for s in self.shapes_)}, "

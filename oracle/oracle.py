@@ -79,12 +79,20 @@ def render(scene, integrator, sensor=0, seed=0, spp=0, raw=True, n_threads=0, ra
         s.set_sample_count(spp)
     spp = s.sample_count()
     desc = scene.describe(sensor)
-    params = integrator.make_params(spp, spp, (int(seed) + s.base_seed) & 0xFFFFFFFF, rank=rank, world=world,
-                                    film_channels=4 if raw else 3)
-    integrator.fill_params_(params, scene, sensor)
     w, h = film.size()
-    C_ = 4 if raw else 3
-    out = np.zeros((h, w, film.temporal_bins, C_), dtype=np.float32)
+    if desc.film.type == _abi.TR_FILM_PHASOR_HDR:      # (H, W, 2F + 1), always raw
+        C_ = film.raw_channels()
+        shape = (h, w, C_)
+    elif desc.film.laser_scan_width:                   # exhaustive_scan: (H, W, Lh, Lw, T, C)
+        C_ = 4 if raw else 3
+        shape = (h, w, film.laser_scan_height, film.laser_scan_width, film.temporal_bins, C_)
+    else:
+        C_ = 4 if raw else 3
+        shape = (h, w, film.temporal_bins, C_)
+    params = integrator.make_params(spp, spp, (int(seed) + s.base_seed) & 0xFFFFFFFF, rank=rank, world=world,
+                                    film_channels=C_)
+    integrator.fill_params_(params, scene, sensor)
+    out = np.zeros(shape, dtype=np.float32)
     steady = np.zeros((h, w, 3), dtype=np.float32)
     cnt = _abi.TrCounters()
     log = np.zeros((max(1, log_deposits), 6), dtype=np.float32)

@@ -527,23 +527,47 @@ inline float area_pdf_direction(const Scene &sc, const TrEmitterDesc &em, V3 d, 
 struct Film {
     const TrFilmDesc &fd; float *data; int C;
     TrCounters *cnt; std::vector<TrDeposit> *log;
-    // add_transient_f + add_transient_data + put_ (box filter path)
-    inline void add_transient(float px, float py, V3 spec, float distance, float sample_scale, float ray_weight) {
+    // add_transient_f + add_transient_data + put_ (box filter path); laser_x / laser_y address the
+    // exhaustive_scan layout (transient_image_block.py:134-140) and are ignored by a plain film (:141-144)
+    inline void add_transient(float px, float py, V3 spec, float distance, float sample_scale, float ray_weight,
+                              uint32_t laser_x = 0, uint32_t laser_y = 0) {
         V3 value = (spec * sample_scale) * ray_weight;
         if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) return;  // x + 0 == x: skipping is exact
         cnt->deposits++;
         if (log) log->push_back(TrDeposit{px, py, distance, value.x, value.y, value.z});
+        if (fd.type == TR_FILM_PHASOR_HDR) { add_phasor(px, py, value, distance); return; }
         float pos_distance = (distance - fd.start_opl) / fd.bin_width_opl;
         bool mask = (pos_distance >= 0.0f) && (pos_distance < (float) fd.temporal_bins);
         if (!mask) return;
         uint32_t x = (uint32_t) floorf(px), y = (uint32_t) floorf(py), z = (uint32_t) floorf(pos_distance);
         if (!(x < fd.width && y < fd.height && z < fd.temporal_bins)) return;
         uint64_t pix = (uint64_t) y * fd.width + x;
+        if (fd.laser_scan_width && fd.laser_scan_height)                                     // :134-138
+            pix = (pix * fd.laser_scan_width + laser_x) * fd.laser_scan_height + laser_y;
         uint64_t index = (pix * fd.temporal_bins + z) * (uint64_t) C;
         data[index + 0] += value.x; data[index + 1] += value.y; data[index + 2] += value.z;
         // channel 3 (W) receives alpha = 0.0 in the reference (transient_image_block.py:99,148): no-op
         cnt->deposits_in_range++;
         cnt->bin_checksum += pix * fd.temporal_bins + z;
+    }
+    // PhasorHDRFilm.add_transient_data (phasor_hdr_film.py:241-264) + PhasorImageBlock.put
+    // (phasor_image_block.py:43-67) + ImageBlock.put (box): monochromatic, two channels per frequency
+    inline void add_phasor(float px, float py, V3 value, float distance) {
+        float opl = distance - fd.start_opl;                                                 // :255
+        if (!std::isfinite(opl)) return;                                                     // phasor_image_block.py:50
+        uint32_t x = (uint32_t) floorf(px), y = (uint32_t) floorf(py);
+        if (!(x < fd.width && y < fd.height)) return;
+        uint64_t pix = (uint64_t) y * fd.width + x;
+        float *o = data + pix * (2ull * fd.n_frequencies + 1ull);
+        const float two_pi = 6.283185307179586f, neg_two_pi = -6.283185307179586f;
+        for (uint32_t f = 0; f < fd.n_frequencies; ++f) {
+            float xx = (neg_two_pi * fd.frequencies[f]) * opl;                               // :56  -2 * pi * freq * opl
+            float phase = xx - two_pi * floorf(xx / two_pi);                                 // :52-53 fmod
+            float sn, cs; sincos_cephes(phase, &sn, &cs);
+            o[2 * f] += value.x * cs; o[2 * f + 1] += value.x * sn;                          // :57-58
+        }
+        cnt->deposits_in_range++;
+        cnt->bin_checksum += pix;
     }
 };
 
@@ -704,8 +728,8 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
 
 // =============================================================================================
 //  transient_nlos_path  (mitransient/integrators/transientnlospath.py) + nlos_capture_meter
-//  (mitransient/sensors/nloscapturemeter.py).  Single and Confocal captures; Exhaustive and AD
-//  are out of scope.
+//  (mitransient/sensors/nloscapturemeter.py).  Single, Confocal and Exhaustive (equal grids) captures;
+//  AD is out of scope.
 // =============================================================================================
 constexpr float kEps = 5.9604644775390625e-08f;   // dr.epsilon(Float) = 2^-24
 
@@ -714,6 +738,7 @@ struct NlosCtx {
     std::vector<V3> sensor_targets; V3 laser_target_single; bool laser_single_valid;
     std::vector<float> hg_pmf, hg_cdf; float hg_sum, hg_norm;   // DiscreteDistribution over shapes (:277-292)
     uint32_t sensor_shape;
+    uint32_t laser_res_x = 0, laser_res_y = 0;                  // Exhaustive capture: illumination grid (:340-348)
 };
 
 // NLOSCaptureMeter._sample_direction + sample_ray(_differential)   nloscapturemeter.py:136-202
@@ -734,7 +759,16 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
     if (sc.emitters.size() != 1 || sc.emitters[0].type != TR_EMITTER_PROJECTOR) { err = "transient_nlos_path needs exactly one projector emitter"; return false; }
     if (sc.sensor.type != TR_SENSOR_NLOS_CAPTURE_METER || sc.sensor.shape < 0 || (uint32_t) sc.sensor.shape >= sc.shapes.size() ||
         sc.shapes[sc.sensor.shape].d.type != TR_SHAPE_RECTANGLE) { err = "transient_nlos_path needs an nlos_capture_meter on a rectangle"; return false; }
-    if (rp.capture_type != TR_CAPTURE_SINGLE && rp.capture_type != TR_CAPTURE_CONFOCAL) { err = "capture type not implemented"; return false; }
+    if (rp.capture_type != TR_CAPTURE_SINGLE && rp.capture_type != TR_CAPTURE_CONFOCAL && rp.capture_type != TR_CAPTURE_EXHAUSTIVE) {
+        err = "unknown capture type"; return false;
+    }
+    if (rp.capture_type == TR_CAPTURE_EXHAUSTIVE) {
+        // force_equal_illumination_scanning = True (:345-348): the laser grid is the sensor grid
+        ctx.laser_res_x = sc.film.width; ctx.laser_res_y = sc.film.height;
+        if (sc.film.laser_scan_width && (sc.film.laser_scan_width != sc.film.width || sc.film.laser_scan_height != sc.film.height)) {
+            err = "Sensor and laser scan resolution must be equal if force_equal_illumination_scanning is set to True"; return false;
+        }
+    }
     ctx.em = &sc.emitters[0];
     const float *m = ctx.em->to_world;
     ctx.em_origin = v3(m[3], m[7], m[11]);
@@ -800,12 +834,12 @@ struct NlosVertex { V3 p, n; float cos_i; const TrBsdfDesc *bsdf; };
 // emitter_nee_sample   transientnlospath.py:433-509
 V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
                            V3 beta, float distance, float eta, uint32_t depth, bool active_e, bool focus_laser,
-                           float px, float py, float sample_scale, Film &film) {
+                           float px, float py, float sample_scale, Film &film, uint32_t laser_x = 0, uint32_t laser_y = 0) {
     if (!active_e) return v3(0, 0, 0);
     film.cnt->shadow_rays++;
     if (ray_test(sc, spawn_ray_to(vx.p, vx.n, ctx.em_origin))) return v3(0, 0, 0);             // :442
     V3 query = vx.p;
-    if (focus_laser && rp.capture_type == TR_CAPTURE_CONFOCAL) {                              // :448-458
+    if (focus_laser && (rp.capture_type == TR_CAPTURE_CONFOCAL || rp.capture_type == TR_CAPTURE_EXHAUSTIVE)) {   // :448-458
         V3 rel = ctx.em_origin - vx.p;
         float dte = sqrtf(dot(rel, rel));
         query = fma3(ctx.em_forward, dte, ctx.em_origin);
@@ -819,17 +853,14 @@ V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const Nlos
     if (rp.flags & TR_FLAG_DISCARD_DIRECT_PATHS) active_e = active_e && (depth > 2);          // :491-492
     V3 Lr = active_e ? (beta * bsdf_spec) * em_weight : v3(0, 0, 0);                          // :493
     if (rp.flags & TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES) distance += ds_dist * eta;         // :497-498
-    film.add_transient(px, py, Lr, distance, sample_scale, 1.0f);                             // :506-507
+    film.add_transient(px, py, Lr, distance, sample_scale, 1.0f, laser_x, laser_y);           // :500-507
     return Lr;
 }
 
-// emitter_laser_sample -> emitter_laser_targets_sample   transientnlospath.py:567-635, 512-564
-V3 nlos_emitter_laser_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
-                             V3 beta, float distance, float eta, uint32_t depth, bool active_e, uint32_t pixel_index,
-                             float px, float py, float sample_scale, Film &film) {
-    if (!active_e) return v3(0, 0, 0);
-    V3 target = (rp.capture_type == TR_CAPTURE_CONFOCAL) ? ctx.sensor_targets[pixel_index] : ctx.laser_target_single;  // :588-596
-    depth += 1;                                                                               // :635 (depth+1)
+// emitter_laser_targets_sample   transientnlospath.py:512-564   (depth: already incremented by the caller, :635)
+V3 nlos_emitter_laser_targets_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
+                                     V3 target, V3 beta, float distance, float eta, uint32_t depth, float px, float py,
+                                     float sample_scale, Film &film, uint32_t laser_x, uint32_t laser_y) {
     V3 d = target - vx.p;                                                                     // :526
     float dl = sqrtf(dot(d, d));
     if (!(dl > 0.0f)) return v3(0, 0, 0);     // confocal depth-0 vertex: target == si.p, NaN direction in the reference (:526-528, :545)
@@ -848,7 +879,29 @@ V3 nlos_emitter_laser_sample(const Scene &sc, const TrRenderParams &rp, const Nl
     bsdf_spec = v3(bsdf_spec.x / pdf_ls, bsdf_spec.y / pdf_ls, bsdf_spec.z / pdf_ls);         // :551
     NlosVertex vb{sb.p, sb.n, -dot(ray_bsdf.d, sb.n), &sc.bsdfs[sc.shapes[sb.shape].d.bsdf]}; // :553
     return nlos_emitter_nee_sample(sc, rp, ctx, rng, vb, beta * bsdf_spec, distance + dl * eta, eta, depth + 1, true, true,
-                                   px, py, sample_scale, film);                               // :560-564
+                                   px, py, sample_scale, film, laser_x, laser_y);             // :560-564
+}
+
+// emitter_laser_sample   transientnlospath.py:567-635
+V3 nlos_emitter_laser_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
+                             V3 beta, float distance, float eta, uint32_t depth, bool active_e, uint32_t pixel_index,
+                             float px, float py, float sample_scale, Film &film) {
+    if (!active_e) return v3(0, 0, 0);
+    if (rp.capture_type == TR_CAPTURE_EXHAUSTIVE) {                                           // :597-627
+        // every scanned point is illuminated by every laser point; the illuminated points are the sensor's
+        const uint32_t n = ctx.laser_res_x * ctx.laser_res_y;
+        V3 sum = v3(0, 0, 0);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t laser_x = (uint32_t) ((float) i / (float) ctx.laser_res_y);              // :618  UInt(i / Float(res_y))
+            uint32_t laser_y = i % ctx.laser_res_y;                                           // :619
+            sum = sum + nlos_emitter_laser_targets_sample(sc, rp, ctx, rng, vx, ctx.sensor_targets[i], beta, distance, eta,
+                                                          depth + 1, px, py, sample_scale, film, laser_x, laser_y);
+        }
+        return sum * (1.0f / (float) n);                                                      // :627
+    }
+    V3 target = (rp.capture_type == TR_CAPTURE_CONFOCAL) ? ctx.sensor_targets[pixel_index] : ctx.laser_target_single;  // :588-596
+    return nlos_emitter_laser_targets_sample(sc, rp, ctx, rng, vx, target, beta, distance, eta, depth + 1, px, py, sample_scale,
+                                             film, 0, 0);                                     // :631-635
 }
 
 V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, Ray ray, uint32_t pixel_index,
@@ -1297,14 +1350,21 @@ int oracle_render(const TrSceneDesc *desc, const TrRenderParams *params, float *
     } else if (sc.sensor.type != TR_SENSOR_PERSPECTIVE) {
         g_err = "oracle: transient_path / transient_prbvolpath need a perspective sensor"; return TR_ERR_UNSUPPORTED;
     }
-    if (params->film_channels != 3 && params->film_channels != 4) { g_err = "film_channels must be 3 or 4"; return TR_ERR_INVALID_ARGUMENT; }
+    const bool phasor = sc.film.type == TR_FILM_PHASOR_HDR;
+    if (phasor) {
+        if (!sc.film.frequencies || sc.film.n_frequencies == 0) { g_err = "phasor film without frequencies"; return TR_ERR_INVALID_ARGUMENT; }
+        if (params->film_channels != (int) (2 * sc.film.n_frequencies + 1)) { g_err = "phasor film: film_channels must be 2F + 1"; return TR_ERR_INVALID_ARGUMENT; }
+    } else if (params->film_channels != 3 && params->film_channels != 4) { g_err = "film_channels must be 3 or 4"; return TR_ERR_INVALID_ARGUMENT; }
     if (params->spp == 0 || params->total_spp == 0) { g_err = "spp must be > 0"; return TR_ERR_INVALID_ARGUMENT; }
     const uint32_t W = sc.film.width, H = sc.film.height, T = sc.film.temporal_bins;
     const int C = params->film_channels;
+    // floats per pixel: T*C (plain), Lw*Lh*T*C (exhaustive_scan), 2F+1 (phasor)
+    const size_t n_laser = (sc.film.laser_scan_width && sc.film.laser_scan_height) ? (size_t) sc.film.laser_scan_width * sc.film.laser_scan_height : 1;
+    const size_t pixel_floats = phasor ? (size_t) C : n_laser * T * C;
     if (!params->accumulate) {
         for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x)
             if (pixel_owned(*params, W, x, y))
-                memset(film + ((size_t) y * W + x) * T * C, 0, sizeof(float) * (size_t) T * C);
+                memset(film + ((size_t) y * W + x) * pixel_floats, 0, sizeof(float) * pixel_floats);
     }
     RenderJob job; job.sc = &sc; job.rp = params; job.film = film; job.steady = steady; job.C = C;
     if (params->integrator == TR_INTEGRATOR_TRANSIENT_NLOS_PATH) job.nlos = &nctx;

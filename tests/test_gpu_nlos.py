@@ -70,7 +70,7 @@ def test_nlos_rejections(mitr):
         scene.integrator().render(scene, spp=1)
     with pytest.raises(AssertionError, match="Only use one"):
         mitr.load_dict({"type": "transient_nlos_path", "filter_depth": 2, "filter_bounces": 1})
-    d = mitr.nlos_z_scene(8, 8, 16, 1, capture_type="exhaustive")
+    d = mitr.nlos_z_scene(8, 8, 16, 1, capture_type="exhaustive")     # Exhaustive needs an exhaustive_scan film
     scene = mitr.load_dict(d)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="exhaustive_scan"):
         scene.integrator().render(scene, spp=1)

@@ -183,3 +183,53 @@ def test_merge_quads(mitr):
     trap = v[np.array([[0, 1, 2], [0, 2, 3]])].copy()
     trap[1, 2] = [0.5, 1, 0]                                      # a trapezoid is not a parallelogram: not merged
     assert merge_quads(trap)[1].tolist() == [0, 0]
+
+
+def test_phasor_film_frequencies_match_reference_formula(mitr):
+    """phasor_hdr_film.py:125-137 on the documented example (400 bins x 6.5, wl_mean = wl_sigma = 100)."""
+    film = mitr.load_dict({"type": "phasor_hdr_film", "wl_mean": 100, "wl_sigma": 100, "width": 256, "height": 256,
+                           "temporal_bins": 400, "start_opl": 1000, "bin_width_opl": 6.5, "rfilter": {"type": "box"}})
+    nt, bw = 400, 6.5
+    mean_idx, sigma_idx = nt * bw / 100, nt * bw / 600
+    lo, hi = max(0, int(np.floor(mean_idx - 3 * sigma_idx))), min(nt // 2, int(np.ceil(mean_idx + 3 * sigma_idx)))
+    want = np.fft.fftfreq(nt, d=bw)[lo:hi + 1].astype(np.float32)
+    np.testing.assert_array_equal(film.frequencies, want)
+    assert len(want) == 27 and film.raw_channels() == 55 and film.channels[0] == "L_fq000_Re" and film.channels[-1] == "W"
+    d = film.describe()
+    assert d.type == mitr._abi.TR_FILM_PHASOR_HDR and d.n_frequencies == 27 and d.frequencies[26] == want[26]
+    defaults = mitr.load_dict({"type": "phasor_hdr_film"})
+    assert defaults.temporal_bins == 4096 and defaults.wl_mean == 100.0 and defaults.wl_sigma == 1000.0
+    with pytest.raises(NotImplementedError):
+        film.create_block()
+
+
+def test_variant_selects_colour_mode(mitr):
+    from mitransient_b200 import colour_mode
+    try:
+        assert mitr.set_variant("llvm_ad_mono") == "cuda_mono" and colour_mode.is_monochromatic()
+        scene = mitr.load_dict(mitr.cornell_box_config(8, 8, 16, 1))
+        desc = scene.describe(scene.sensors()[0])
+        for i in range(desc.n_bsdfs):
+            r = list(desc.bsdfs[i].reflectance)
+            assert r[0] == r[1] == r[2]
+        green = np.float32(0.212671) * np.float32(0.105421) + np.float32(0.715160) * np.float32(0.37798) \
+            + np.float32(0.072169) * np.float32(0.076425)
+        assert any(abs(desc.bsdfs[i].reflectance[0] - green) < 1e-7 for i in range(desc.n_bsdfs))
+        assert mitr.set_variant("cuda_ad_rgb", "llvm_ad_rgb") == "cuda_rgb" and not colour_mode.is_monochromatic()
+        desc = scene.describe(scene.sensors()[0])
+        assert any(desc.bsdfs[i].reflectance[0] != desc.bsdfs[i].reflectance[1] for i in range(desc.n_bsdfs))
+    finally:
+        mitr.set_variant("cuda_rgb")
+
+
+def test_exhaustive_scan_film_descriptor(mitr):
+    film = mitr.load_dict({"type": "transient_hdr_film", "width": 4, "height": 4, "temporal_bins": 8,
+                           "exhaustive_scan": True, "laser_scan_width": 4, "laser_scan_height": 4})
+    d = film.describe()
+    assert (d.laser_scan_width, d.laser_scan_height, d.type) == (4, 4, mitr._abi.TR_FILM_TRANSIENT_HDR)
+    assert film.needs_zeroed_accumulate() and film.raw_channels() == 4
+    plain = mitr.load_dict({"type": "transient_hdr_film", "width": 4, "height": 4, "temporal_bins": 8})
+    assert plain.describe().laser_scan_width == 0 and not plain.needs_zeroed_accumulate()
+    bad = mitr.load_dict({"type": "transient_hdr_film", "width": 4, "height": 4, "exhaustive_scan": True})
+    with pytest.raises(ValueError, match="laser_scan"):
+        bad.check_supported()

@@ -253,3 +253,64 @@ def test_oracle_matches_committed_golden(oracle, mitr):
         assert r["counters"][k] == int(g["counter_" + k]), k
     np.testing.assert_allclose(r["steady"], g["steady"], rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(r["transient"][..., :3].sum(axis=(0, 1)), g["temporal_profile"], rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------- phasor film / exhaustive scan
+@pytest.fixture
+def mono(mitr):
+    mitr.set_variant("llvm_ad_mono")
+    yield
+    mitr.set_variant("cuda_rgb")
+
+
+def test_phasor_film_is_the_fourier_transform_of_the_histogram(oracle, mitr, mono):
+    """KAT: with a window covering every path length, the phasor at frequency f equals the DFT of the time
+    histogram up to the bin-centre phase error pi*f*bin_width (phasor_image_block.py:52-58 vs
+    transient_hdr_film.py:263)."""
+    T, window, spp, n = 4096, (0.0, 60.0), 32, 12
+    d = mitr.cornell_box_config(n, n, T, spp, window=window)
+    s0 = mitr.load_dict(d)
+    hist = oracle.render(s0, s0.integrator(), spp=spp)
+    assert hist["counters"]["deposits"] == hist["counters"]["deposits_in_range"]      # nothing outside the window
+    d = mitr.cornell_box_config(n, n, T, spp, window=window)
+    d["sensor"]["film"] = {"type": "phasor_hdr_film", "width": n, "height": n, "temporal_bins": T, "start_opl": window[0],
+                           "bin_width_opl": (window[1] - window[0]) / T, "wl_mean": 4.0, "wl_sigma": 2.0}
+    s1 = mitr.load_dict(d)
+    film = s1.sensors()[0].film()
+    F = len(film.frequencies)
+    ph = oracle.render(s1, s1.integrator(), spp=spp)
+    assert ph["transient"].shape == (n, n, 2 * F + 1) and ph["counters"]["vertices"] == hist["counters"]["vertices"]
+    assert ph["counters"]["deposits_in_range"] == hist["counters"]["deposits"]
+    np.testing.assert_array_equal(ph["steady"], hist["steady"])
+    t = (np.arange(T) + 0.5) * (window[1] - window[0]) / T
+    h = hist["transient"][..., 0].astype(np.float64)
+    got = ph["transient"][..., :2 * F].reshape(n, n, F, 2).astype(np.float64)
+    for j in range(F):
+        f = float(film.frequencies[j])
+        ref = (h * np.exp(-2j * np.pi * f * t)).sum(-1)
+        err = np.abs(got[..., j, 0] + 1j * got[..., j, 1] - ref).sum() / np.abs(ref).sum()
+        assert err < 3.0 * np.pi * f * (window[1] - window[0]) / T + 1e-3, (j, f, err)
+    assert np.abs(ph["transient"][..., -1]).sum() == 0
+
+
+def test_exhaustive_capture_energy_and_layout(oracle, mitr):
+    """KAT: an Exhaustive capture deposits Lr of EVERY illuminated point while the path's radiance is their mean
+    (transientnlospath.py:621-627): sum(film) == n_laser * sum(steady) when the window holds everything; the
+    confocal-like diagonal is populated and the film has the reference's (H, W, Lh, Lw, T, C) shape."""
+    res, T, spp = 4, 64, 32
+    d = mitr.nlos_z_scene(res, res, T, spp, start_opl=0.0, window=10.0, capture_type="exhaustive")
+    f = d["relay_wall"]["nlos_sensor"]["transient_film"]
+    f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, res, res
+    scene = mitr.load_dict(d)
+    r = oracle.render(scene, scene.integrator(), spp=spp)
+    film, steady = r["transient"].astype(np.float64), r["steady"].astype(np.float64)
+    assert film.shape == (res, res, res, res, T, 4)
+    assert r["counters"]["deposits"] == r["counters"]["deposits_in_range"] > 0
+    per_pixel = film[..., :3].sum(axis=(2, 3, 4))
+    np.testing.assert_allclose(per_pixel, steady * res * res, rtol=2e-4, atol=1e-7)
+    assert (film.sum(axis=(0, 1, 4, 5)) > 0).all()          # every illuminated point receives light from somewhere
+    # the same scene under a confocal capture = only the laser point that coincides with the scanned point
+    d2 = mitr.nlos_z_scene(res, res, T, spp, start_opl=0.0, window=10.0, capture_type="confocal")
+    s2 = mitr.load_dict(d2)
+    r2 = oracle.render(s2, s2.integrator(), spp=spp)
+    assert r2["transient"].shape == (res, res, T, 4) and r2["counters"]["shadow_rays"] < r["counters"]["shadow_rays"]
