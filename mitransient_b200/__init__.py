@@ -21,6 +21,7 @@ from .integrators.transientnlospath import CaptureType, TransientNLOSPath
 from .integrators.transientpath import TransientPath
 from .integrators.transient_prbvolpath import TransientPRBVolpathIntegrator
 from . import nlos
+from . import vis
 from .plugins import register_film, register_integrator, register_sensor
 from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
 from .sensors.nloscapturemeter import NLOSCaptureMeter

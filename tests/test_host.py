@@ -233,3 +233,13 @@ def test_exhaustive_scan_film_descriptor(mitr):
     bad = mitr.load_dict({"type": "transient_hdr_film", "width": 4, "height": 4, "exhaustive_scan": True})
     with pytest.raises(ValueError, match="laser_scan"):
         bad.check_supported()
+
+
+def test_tonemap_transient_matches_numpy_quantile(mitr):
+    import torch
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((6, 5, 7, 3)) ** 3).astype(np.float32)
+    want = x / np.quantile(np.abs(x), 0.99) * 2.0
+    np.testing.assert_allclose(mitr.vis.tonemap_transient(x, scaling=2.0), want, rtol=1e-6)
+    got = mitr.vis.tonemap_transient(torch.from_numpy(x), scaling=2.0)
+    np.testing.assert_allclose(got.numpy(), want, rtol=1e-5)
