@@ -256,7 +256,11 @@ def run_ours(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = sum(a.elapsed_time(b) for a, b in kern) / args.steps
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
+    kern_ms_per_rank = [kern_ms]
     if n > 1:
+        per_rank = [torch.zeros_like(t) for _ in range(n)]
+        dist.all_gather(per_rank, t)
+        kern_ms_per_rank = [float(x[1]) for x in per_rank]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = t.tolist()
     ms_per_step = total_ms / args.steps
@@ -320,7 +324,7 @@ def run_ours(args):
     traffic = ncu_traffic_per_launch() if n == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "render_transient_path_kernel",
-                "kernel_ms": kern_ms, "algorithmic_bytes": b_alg, "live_path_vertices": n_v_rank,
+                "kernel_ms": kern_ms, "kernel_ms_per_rank": [round(x, 3) for x in kern_ms_per_rank], "algorithmic_bytes": b_alg, "live_path_vertices": n_v_rank,
                 "model": "SURVEY 8d: 128 B x N_v + 16 B x H*W*T + 12 B x H*W (wavefront byte model; this kernel "
                          "keeps path state in registers, so its DRAM traffic is ~ the film write only)"}
 
@@ -344,7 +348,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2 cornell_box transient_path {W}x{H}x{T} bins, {spp} spp, max_depth 8, seed 0"
-                               + (f" (weak scaling: 256 spp x {n} GPUs, pixel tiles 32x32 round-robin, film assembled on "
+                               + (f" (weak scaling: 256 spp x {n} GPUs, pixel tiles 16x16 skewed round-robin, film assembled on "
                                   f"rank 0 inside the step, mode={mode}: " +
                                   ("kernel flushes into rank 0's film over NVLink peer memory + all-reduce fence)"
                                    if mode == "peer" else "NCCL reduce of film+steady to rank 0)") if n > 1 else ""),

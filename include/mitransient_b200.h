@@ -186,7 +186,8 @@ typedef struct TrRenderParams {
                                (mitransient/integrators/common.py:150-155,173)              */
     uint32_t seed;          /* sampler seed of this pass (common.py:52,72)                  */
     /* pixel-tile sharding: tiles of tile_size x tile_size pixels are dealt
-       round-robin; this call renders the tiles t with t % world == rank.  world == 1
+       round-robin with a one-tile skew per tile row; this call renders the tiles t (row-major
+       index, tile row ty) with (t + ty) % world == rank.  world == 1
        renders everything.  RNG streams are indexed by the GLOBAL sample index, so the
        film does not depend on `world`.                                                    */
     uint32_t tile_size;

@@ -16,7 +16,7 @@ def tile_owner_map(width: int, height: int, tile_size: int, world: int) -> np.nd
     """(H, W) int array: rank owning each pixel (same rule as csrc/tr_render.cu ensure_pixel_list)."""
     tiles_x = (width + tile_size - 1) // tile_size
     ty, tx = np.meshgrid(np.arange(height) // tile_size, np.arange(width) // tile_size, indexing="ij")
-    return ((ty * tiles_x + tx) % world).astype(np.int64)
+    return ((ty * tiles_x + tx + ty) % world).astype(np.int64)     # round-robin, skewed by one tile per tile row
 
 
 def reduce_film(film, steady=None, dst: int = 0):

@@ -87,7 +87,7 @@ class TransientADIntegrator:
         return f
 
     def make_params(self, spp_i: int, total_spp: int, seed_i: int, rank: int = 0, world: int = 1,
-                    film_channels: int = 4, accumulate: bool = False, tile_size: int = 32) -> _abi.TrRenderParams:
+                    film_channels: int = 4, accumulate: bool = False, tile_size: int = 16) -> _abi.TrRenderParams:
         p = _abi.TrRenderParams()
         p.integrator = self.integrator_id
         p.max_depth, p.rr_depth, p.flags = self.max_depth, self.rr_depth, self.render_flags()

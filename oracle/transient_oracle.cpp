@@ -1274,7 +1274,7 @@ inline bool pixel_owned(const TrRenderParams &rp, uint32_t W, uint32_t x, uint32
     uint32_t ts = rp.tile_size ? rp.tile_size : 32;
     uint32_t tiles_x = (W + ts - 1) / ts;
     uint32_t tile = (y / ts) * tiles_x + (x / ts);
-    return tile % rp.world == rp.rank;
+    return (tile + y / ts) % rp.world == rp.rank;     // round-robin, skewed by one tile per tile row
 }
 
 void render_rows(RenderJob *job) {

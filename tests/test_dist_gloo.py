@@ -33,7 +33,7 @@ def _worker(rank, world, port, outdir):
     r = oracle.render(scene, scene.integrator(), spp=4, seed=0, rank=rank, world=world, n_threads=2)
     film = torch.from_numpy(r["transient"])
     steady = torch.from_numpy(r["steady"])
-    own = tile_owner_map(40, 24, 32, world) == rank
+    own = tile_owner_map(40, 24, 16, world) == rank
     assert np.all(r["transient"][~own] == 0)                     # nothing written outside the owned tiles
     reduce_film(film, steady, dst=0)
     cnt = torch.tensor([r["counters"]["paths"], r["counters"]["vertices"]], dtype=torch.int64)
@@ -65,8 +65,8 @@ def test_two_rank_tile_sharding_reduces_to_single_rank_film(tmp_path):
 def test_tile_owner_map():
     sys.path.insert(0, ROOT)
     from mitransient_b200.distributed import tile_owner_map
-    m = tile_owner_map(70, 40, 32, 4)
+    m = tile_owner_map(70, 40, 16, 4)
     assert m.shape == (40, 70)
-    assert m[0, 0] == 0 and m[0, 32] == 1 and m[0, 64] == 2 and m[32, 0] == 3 and m[32, 32] == 0
+    assert m[0, 0] == 0 and m[0, 16] == 1 and m[0, 32] == 2 and m[16, 0] == 2 and m[16, 16] == 3     # (tile + tile_row) % world, 5 tiles per row
     counts = np.bincount(m.reshape(-1), minlength=4)
     assert counts.sum() == 70 * 40 and np.all(counts > 0)

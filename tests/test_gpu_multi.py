@@ -32,7 +32,7 @@ def _worker(rank, world, port, outdir):
     integ = scene.integrator()
     integ.render(scene, seed=0, spp=8, rank=rank, world=world)
     part = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
-    own = tile_owner_map(96, 64, 32, world) == rank
+    own = tile_owner_map(96, 64, 16, world) == rank
     assert np.all(part[~own] == 0) and np.abs(part[own]).sum() > 0
     steady, raw = render_distributed(scene, seed=0, spp=8, dst=0, raw=True)
     torch.cuda.synchronize()
