@@ -266,15 +266,19 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = paths_total / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e: host buffers, scene upload + render + film to pinned host memory inside the timed region
+    # ---- e2e: host buffers, scene upload + render + film to pinned host memory inside the timed region.
+    # N > 1: the SAME job as `value` (one film, spp = 256 * N, pixel tiles sharded over the ranks); every rank
+    # renders its tiles and moves its share of the developed film to its own pinned host buffer over its own
+    # PCIe link (tr_render_to_host with world = N: compact (n_owned, T, 3) output in tr_owned_pixels order).
     e2e = None
     try:
-        host_T = torch.empty((H, W, T, 3), dtype=torch.float32, pin_memory=True)
-        host_S = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
-        p_e2e = integ.make_params(C2["spp"], C2["spp"], 0, film_channels=3)      # each rank: the full C2 job
+        from mitransient_b200.distributed import owned_pixels
+        n_owned = len(owned_pixels(W, H, 16, rank, n)) if n > 1 else W * H
+        host_T = torch.empty((n_owned, T, 3), dtype=torch.float32, pin_memory=True)
+        host_S = torch.empty((n_owned, 3), dtype=torch.float32, pin_memory=True)
+        p_e2e = integ.make_params(spp, spp, 0, film_channels=3, rank=rank, world=n, tile_size=16)
         desc = scene.describe(sensor)
         blob_bytes = dev.info()["blob_bytes"]
-        cnt_h = _abi.TrCounters()
 
         def e2e_step():
             h = C.c_void_p()
@@ -293,20 +297,25 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(k_e2e):
             e2e_step()
+            if n > 1:
+                dist.barrier()                                  # a step ends when every rank's shard is on the host
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if n > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = te.item()
-        e2e_paths = W * H * C2["spp"] * n                       # every rank renders one full C2 film to ITS host buffer
-        e2e = {"value": e2e_paths * k_e2e / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int(blob_bytes + W * H * 4),
-               "d2h_bytes_per_step": int(host_T.numel() * 4 + host_S.numel() * 4),
+        nb = torch.tensor([float(host_T.numel() * 4 + host_S.numel() * 4)], dtype=torch.float64, device="cuda")
+        if n > 1:
+            dist.all_reduce(nb)
+        e2e = {"value": W * H * spp * k_e2e / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int((blob_bytes + n_owned * 4) * n),
+               "d2h_bytes_per_step": int(nb.item()),
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
                "what": "tr_scene_create + tr_render_to_host: developed (H,W,T,3) film + steady into pinned host "
                        "memory, D2H overlapped with rendering band by band" +
-                       ("; at N>1 every rank renders a full C2 film into its own host buffer" if n > 1 else "")}
+                       (f"; the film is sharded by pixel tiles: each of the {n} ranks renders its tiles and copies its "
+                        "share to its own pinned host buffer over its own PCIe link (bytes summed over ranks)" if n > 1 else "")}
         del host_T, host_S
     except Exception as exc:  # keep the headline line even if the host path fails
         e2e = {"value": None, "unit": UNIT, "error": str(exc)}

@@ -259,6 +259,13 @@ int tr_render(const TrScene *scene, const TrRenderParams *params,
 int tr_render_to_host(const TrScene *scene, const TrRenderParams *params,
                       float *film_host, float *steady_host, TrCounters *counters_host,
                       void *stream);
+/* With params->world > 1 tr_render_to_host renders only the pixels this rank owns and film_host /
+ * steady_host are the COMPACT arrays float[n_owned][T][film_channels] / float[n_owned][3], pixels in the
+ * order tr_owned_pixels reports (owned tiles row-major, pixels row-major inside a tile): every GPU of a
+ * node then moves only its share of the film over its own PCIe link.  tr_owned_pixels needs no GPU:
+ * out == NULL only counts; otherwise *n_out holds the capacity of `out` on entry.                     */
+int tr_owned_pixels(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t rank, uint32_t world,
+                    uint32_t *out, uint64_t *n_out);
 
 /* K4 on its own: TransientImageBlock.put_ for a stream of deposits
  * (transient_hdr_film.py:263-276 + transient_image_block.py:130-149).  `deposits` is a

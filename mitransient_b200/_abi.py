@@ -105,7 +105,7 @@ class TrDeposit(C.Structure):
 # every symbol include/mitransient_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
     "tr_device_check", "tr_abi_version", "tr_last_error", "tr_scene_create", "tr_scene_destroy",
-    "tr_scene_info", "tr_render", "tr_render_to_host", "tr_film_scatter_add", "tr_film_develop",
+    "tr_scene_info", "tr_render", "tr_render_to_host", "tr_owned_pixels", "tr_film_scatter_add", "tr_film_develop",
     "tr_peer_alloc", "tr_peer_open", "tr_peer_close", "tr_peer_free",
 )
 TR_PEER_HANDLE_BYTES = 64

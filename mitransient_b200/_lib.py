@@ -56,6 +56,8 @@ def load() -> C.CDLL:
         lib.tr_render.argtypes = [vp, C.POINTER(_abi.TrRenderParams), vp, vp, vp, vp]
         lib.tr_render_to_host.restype = C.c_int
         lib.tr_render_to_host.argtypes = [vp, C.POINTER(_abi.TrRenderParams), vp, vp, C.POINTER(_abi.TrCounters), vp]
+        lib.tr_owned_pixels.restype = C.c_int
+        lib.tr_owned_pixels.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_uint64)]
         lib.tr_film_scatter_add.restype = C.c_int
         lib.tr_film_scatter_add.argtypes = [vp, C.POINTER(_abi.TrFilmDesc), C.c_int32, vp, C.c_uint64, vp]
         lib.tr_film_develop.restype = C.c_int

@@ -81,7 +81,6 @@ extern "C" int tr_render_to_host(const TrScene *scene_c, const TrRenderParams *p
     SceneImpl &sc = scene->impl;
     int rc = validate_params(sc, params);
     if (rc != TR_OK) return rc;
-    if (params->world != 1) return fail(TR_ERR_UNSUPPORTED, "tr_render_to_host renders the whole film (world must be 1)");
     if (params->accumulate) return fail(TR_ERR_UNSUPPORTED, "tr_render_to_host does not accumulate");
     cudaStream_t stream = (cudaStream_t) stream_v;
 
@@ -90,38 +89,66 @@ extern "C" int tr_render_to_host(const TrScene *scene_c, const TrRenderParams *p
     // floats per pixel: T * C (time histogram) or 2F + 1 (phasor film, film_channels = 2F + 1)
     const uint32_t T = sc.film.type == TR_FILM_PHASOR_HDR ? 1u : sc.film.temporal_bins;
     const int C = params->film_channels;
-    const size_t row_floats = (size_t) W * T * C;
-    // band height: ~96 MiB of film per band (the first copy starts early, the last one ends soon after the last kernel)
-    uint32_t rows = (uint32_t) std::max<size_t>(1, ((size_t) 96 << 20) / (row_floats * 4));
-    rows = std::min(rows, H);
-    const uint32_t n_bands = (H + rows - 1) / rows;
-    const size_t band_bytes = (size_t) rows * row_floats * 4;
+    const size_t pixel_floats = (size_t) T * C;
+    const bool sharded = params->world > 1;
+    // world == 1: bands of whole rows, the host film is indexed by pixel id.  world > 1: bands of consecutive OWNED
+    // pixels (tr_owned_pixels order), the host film is the compact float[n_owned][T][C] array of this rank.
+    const uint32_t *d_list = nullptr; uint32_t n_list = W * H;
+    if (sharded) {
+        rc = owned_pixels(sc, params, stream, &d_list, &n_list);
+        if (rc != TR_OK) return rc;
+        if (n_list == 0) return TR_OK;
+    }
+    // band size: ~96 MiB of film per band (the first copy starts early, the last one ends soon after the last kernel)
+    uint32_t band_pix = (uint32_t) std::max<size_t>(1, ((size_t) 96 << 20) / (pixel_floats * 4));
+    if (!sharded) band_pix = std::max(1u, band_pix / W) * W;          // whole rows
+    band_pix = std::min(band_pix, n_list);
+    const uint32_t n_bands = (n_list + band_pix - 1) / band_pix;
+    const size_t band_bytes = (size_t) band_pix * pixel_floats * 4;
 
     std::lock_guard<std::mutex> guard(g_ws_mutex);
     HostWorkspace *ws = nullptr;
     rc = get_workspace(band_bytes, (size_t) W * H * 3 * 4, (size_t) W * H, stream, &ws);
     if (rc != TR_OK) return rc;
+    if (!sharded) d_list = ws->d_pix;
     if (counters_host) TR_CUDA(cudaMemsetAsync(ws->d_cnt, 0, sizeof(TrCounters), stream));
 
     for (uint32_t b = 0; b < n_bands; ++b) {
         const int buf = (int) (b % kBandBuffers);
-        const uint32_t y0 = b * rows, nrows = std::min(rows, H - y0);
-        const size_t first_pix = (size_t) y0 * W, npix = (size_t) nrows * W;
+        const size_t first = (size_t) b * band_pix, npix = std::min<size_t>(band_pix, n_list - first);
         if (b >= (uint32_t) kBandBuffers) TR_CUDA(cudaStreamWaitEvent(stream, ws->copied[buf], 0));   // buffer is free again
-        // the kernel indexes the film by global pixel id: bias the band buffer accordingly
-        float *film_biased = ws->d_film[buf] - first_pix * (size_t) T * C;
-        rc = render_device(scene, params, film_biased, steady_host ? ws->d_steady : nullptr, counters_host ? ws->d_cnt : nullptr,
-                           stream, ws->d_pix + first_pix, (uint32_t) npix);
+        // whole-film mode: the kernel indexes the film by global pixel id (= position in the identity list): bias the
+        // band buffer.  Sharded mode: the kernel writes pixel j of the band at position j (compact).
+        float *film_dst = sharded ? ws->d_film[buf] : ws->d_film[buf] - first * pixel_floats;
+        float *steady_dst = !steady_host ? nullptr : (sharded ? ws->d_steady + first * 3 : ws->d_steady);
+        rc = render_device(scene, params, film_dst, steady_dst, counters_host ? ws->d_cnt : nullptr, stream, d_list + first,
+                           (uint32_t) npix, sharded);
         if (rc != TR_OK) { cudaStreamSynchronize(stream); cudaStreamSynchronize(ws->copy_stream); return rc; }
         TR_CUDA(cudaEventRecord(ws->rendered[buf], stream));
         TR_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->rendered[buf], 0));
-        TR_CUDA(cudaMemcpyAsync(film_host + first_pix * (size_t) T * C, ws->d_film[buf], npix * (size_t) T * C * 4,
+        TR_CUDA(cudaMemcpyAsync(film_host + first * pixel_floats, ws->d_film[buf], npix * pixel_floats * 4,
                                 cudaMemcpyDeviceToHost, ws->copy_stream));
         TR_CUDA(cudaEventRecord(ws->copied[buf], ws->copy_stream));
     }
-    if (steady_host) TR_CUDA(cudaMemcpyAsync(steady_host, ws->d_steady, (size_t) W * H * 3 * 4, cudaMemcpyDeviceToHost, stream));
+    if (steady_host) TR_CUDA(cudaMemcpyAsync(steady_host, ws->d_steady, (size_t) n_list * 3 * 4, cudaMemcpyDeviceToHost, stream));
     if (counters_host) TR_CUDA(cudaMemcpyAsync(counters_host, ws->d_cnt, sizeof(TrCounters), cudaMemcpyDeviceToHost, stream));
     TR_CUDA(cudaStreamSynchronize(stream));
     TR_CUDA(cudaStreamSynchronize(ws->copy_stream));
+    return TR_OK;
+}
+
+// Host-side helper (no GPU): the pixels (y * W + x) owned by `rank`, in the order tr_render_to_host lays them out.
+extern "C" int tr_owned_pixels(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t rank, uint32_t world,
+                               uint32_t *out, uint64_t *n_out) {
+    using namespace tr;
+    if (width == 0 || height == 0 || world == 0 || rank >= world || !n_out)
+        return fail(TR_ERR_INVALID_ARGUMENT, "tr_owned_pixels: bad argument");
+    std::vector<uint32_t> px;
+    list_owned_pixels(width, height, tile_size ? tile_size : 32u, rank, world, px);
+    if (out) {
+        if (*n_out < px.size()) return fail(TR_ERR_INVALID_ARGUMENT, "tr_owned_pixels: output array too small");
+        std::copy(px.begin(), px.end(), out);
+    }
+    *n_out = px.size();
     return TR_OK;
 }

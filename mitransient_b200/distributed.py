@@ -19,6 +19,20 @@ def tile_owner_map(width: int, height: int, tile_size: int, world: int) -> np.nd
     return ((ty * tiles_x + tx + ty) % world).astype(np.int64)     # round-robin, skewed by one tile per tile row
 
 
+def owned_pixels(width: int, height: int, tile_size: int, rank: int, world: int) -> np.ndarray:
+    """Pixel ids ``y * W + x`` owned by ``rank`` in the order ``tr_render_to_host`` lays out its compact per-rank
+    film (``tr_owned_pixels``: owned tiles row-major, pixels row-major inside a tile).  Needs no GPU."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    n = C.c_uint64(0)
+    _lib.check(lib.tr_owned_pixels(width, height, tile_size, rank, world, None, C.byref(n)))
+    out = np.zeros(int(n.value), dtype=np.uint32)
+    _lib.check(lib.tr_owned_pixels(width, height, tile_size, rank, world, out.ctypes.data, C.byref(n)))
+    return out
+
+
 def reduce_film(film, steady=None, dst: int = 0):
     """The single collective of the job: sum-reduce the raw film (and steady image) to ``dst``.
     NCCL when the tensors are on the GPU, gloo on the CPU."""

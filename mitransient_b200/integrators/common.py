@@ -146,10 +146,14 @@ class TransientADIntegrator:
         return steady, transient
 
     def render_to_host(self, scene: Scene, sensor=0, seed: int = 0, spp: int = 0, raw: bool = False,
-                       out_transient=None, out_steady=None):
+                       out_transient=None, out_steady=None, rank: int = 0, world: int = 1, tile_size: int = 16):
         """Render straight into HOST (ideally pinned) tensors with the device->host copy of the film
         overlapped with rendering (``tr_render_to_host``).  Returns ``(steady, transient)`` CPU tensors:
-        transient is (H,W,T,3) developed, or (H,W,T,4) raw."""
+        transient is (H,W,T,3) developed, or (H,W,T,4) raw.
+
+        ``world > 1``: this rank renders only the pixels it owns and the outputs are the COMPACT arrays
+        ``(n_owned, T, C)`` / ``(n_owned, 3)`` in ``distributed.owned_pixels(...)`` order, so that every GPU of a
+        node moves only its share of the film over its own PCIe link."""
         import torch
         if isinstance(sensor, int):
             sensor = scene.sensors()[sensor]
@@ -165,12 +169,21 @@ class TransientADIntegrator:
         spp = s.sample_count()
         w, h = film.size()
         ch = 4 if raw else 3
+        if world > 1:
+            from ..distributed import owned_pixels
+            n_owned = len(owned_pixels(w, h, tile_size, rank, world))
+            shape_t, shape_s = (n_owned, film.temporal_bins, ch), (n_owned, 3)
+        else:
+            shape_t, shape_s = (h, w, film.temporal_bins, ch), (h, w, 3)
         if out_transient is None:
-            out_transient = torch.empty((h, w, film.temporal_bins, ch), dtype=torch.float32, pin_memory=True)
+            out_transient = torch.empty(shape_t, dtype=torch.float32, pin_memory=True)
         if out_steady is None:
-            out_steady = torch.empty((h, w, 3), dtype=torch.float32, pin_memory=True)
+            out_steady = torch.empty(shape_s, dtype=torch.float32, pin_memory=True)
+        if tuple(out_transient.shape) != shape_t or tuple(out_steady.shape) != shape_s:
+            raise ValueError(f"output tensors must have shapes {shape_t} and {shape_s}")
         dev = self.device_scene(scene, sensor)
-        params = self.make_params(spp, spp, (int(seed) + s.base_seed) & 0xFFFFFFFF, film_channels=ch)
+        params = self.make_params(spp, spp, (int(seed) + s.base_seed) & 0xFFFFFFFF, film_channels=ch, rank=rank,
+                                  world=world, tile_size=tile_size)
         self.fill_params_(params, scene, sensor)
         cnt = _abi.TrCounters() if self.collect_counters else None
         _lib.check(_lib.load().tr_render_to_host(dev.handle, C.byref(params), out_transient.data_ptr(),

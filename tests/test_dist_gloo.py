@@ -70,3 +70,22 @@ def test_tile_owner_map():
     assert m[0, 0] == 0 and m[0, 16] == 1 and m[0, 32] == 2 and m[16, 0] == 2 and m[16, 16] == 3     # (tile + tile_row) % world, 5 tiles per row
     counts = np.bincount(m.reshape(-1), minlength=4)
     assert counts.sum() == 70 * 40 and np.all(counts > 0)
+
+
+def test_owned_pixels_is_the_owner_map_in_tile_order():
+    """tr_owned_pixels (the layout of the sharded tr_render_to_host output) partitions the film exactly like
+    tile_owner_map; no GPU needed."""
+    sys.path.insert(0, ROOT)
+    from mitransient_b200.distributed import owned_pixels, tile_owner_map
+    W, H, tile, world = 70, 40, 16, 3
+    m = tile_owner_map(W, H, tile, world).reshape(-1)
+    seen = np.zeros(W * H, dtype=np.int64)
+    for rank in range(world):
+        px = owned_pixels(W, H, tile, rank, world)
+        assert np.array_equal(np.sort(px), np.nonzero(m == rank)[0])
+        seen[px] += 1
+        # tile-major order: the first pixels are the first owned tile, row by row
+        first_tile = np.nonzero((m == rank))[0][0]
+        assert px[0] == first_tile and px[1] == first_tile + 1
+    assert (seen == 1).all()
+    assert len(owned_pixels(W, H, tile, 0, 1)) == W * H
