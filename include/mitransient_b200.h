@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 8
+#define TR_ABI_VERSION 9
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -70,14 +70,21 @@ typedef struct TrShapeDesc {
     float to_world[12];  /* row-major 3x4 affine; meaningful for rectangles                 */
 } TrShapeDesc;
 
-enum { TR_BSDF_DIFFUSE = 0, TR_BSDF_NULL = 1 };
+/* BSDFs (the per-bounce bsdf.sample / bsdf.eval_pdf of transientpath.py:207-227).  diffuse, null: every integrator.
+ * conductor (Mitsuba `conductor`: perfect mirror weighted by the complex-IOR Fresnel term) and dielectric (Mitsuba
+ * `dielectric`: delta reflection / refraction, radiance scaled by eta_ti^2, optical path length scaled by the
+ * accumulated relative IOR, transientpath.py:154,233): transient_path only.                                       */
+enum { TR_BSDF_DIFFUSE = 0, TR_BSDF_NULL = 1, TR_BSDF_CONDUCTOR = 2, TR_BSDF_DIELECTRIC = 3 };
 enum { TR_BSDF_FLAG_TWOSIDED = 1 };
 
 typedef struct TrBsdfDesc {
     int32_t type;        /* TR_BSDF_*                                                       */
     int32_t flags;       /* TR_BSDF_FLAG_*                                                  */
-    float reflectance[3];
-    float _pad[3];
+    float reflectance[3];             /* diffuse: reflectance; conductor / dielectric: specular_reflectance */
+    float eta[3];                     /* conductor: real part of the IOR; dielectric: eta[0] = int_ior / ext_ior */
+    float k[3];                       /* conductor: extinction coefficient                  */
+    float specular_transmittance[3];  /* dielectric                                         */
+    float _pad[2];
 } TrBsdfDesc;
 
 enum { TR_EMITTER_AREA = 0, TR_EMITTER_PROJECTOR = 1 };

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 8
+TR_ABI_VERSION = 9
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -15,7 +15,7 @@ TR_ERR_OUT_OF_MEMORY = -5
 TR_SHAPE_MESH, TR_SHAPE_RECTANGLE = 0, 1
 TR_PRIM_TRIANGLE, TR_PRIM_QUAD, TR_PRIM_BOX = 0, 1, 2
 TR_SHAPE_FLAG_SENSOR = 1
-TR_BSDF_DIFFUSE, TR_BSDF_NULL = 0, 1
+TR_BSDF_DIFFUSE, TR_BSDF_NULL, TR_BSDF_CONDUCTOR, TR_BSDF_DIELECTRIC = 0, 1, 2, 3
 TR_BSDF_FLAG_TWOSIDED = 1
 TR_EMITTER_AREA, TR_EMITTER_PROJECTOR = 0, 1
 TR_SENSOR_PERSPECTIVE, TR_SENSOR_NLOS_CAPTURE_METER = 0, 1
@@ -42,7 +42,8 @@ class TrShapeDesc(C.Structure):
 
 
 class TrBsdfDesc(C.Structure):
-    _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("reflectance", C.c_float * 3), ("_pad", C.c_float * 3)]
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("reflectance", C.c_float * 3), ("eta", C.c_float * 3),
+                ("k", C.c_float * 3), ("specular_transmittance", C.c_float * 3), ("_pad", C.c_float * 2)]
 
 
 class TrEmitterDesc(C.Structure):

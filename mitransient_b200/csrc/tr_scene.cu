@@ -313,8 +313,14 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     for (uint32_t i = 0; i < desc->n_bsdfs; ++i) {
         memset(&bsdfs[i], 0, sizeof(DevBsdf));
         bsdfs[i].type = desc->bsdfs[i].type; bsdfs[i].flags = desc->bsdfs[i].flags;
-        if (bsdfs[i].type != TR_BSDF_DIFFUSE && bsdfs[i].type != TR_BSDF_NULL) { err = "unknown bsdf type"; return false; }
-        for (int c = 0; c < 3; ++c) bsdfs[i].r[c] = desc->bsdfs[i].reflectance[c];
+        if (bsdfs[i].type < TR_BSDF_DIFFUSE || bsdfs[i].type > TR_BSDF_DIELECTRIC) { err = "unknown bsdf type"; return false; }
+        if (bsdfs[i].type == TR_BSDF_DIELECTRIC && !(desc->bsdfs[i].eta[0] > 0.0f)) { err = "dielectric needs eta = int_ior / ext_ior > 0"; return false; }
+        if (bsdfs[i].type == TR_BSDF_DIELECTRIC && (bsdfs[i].flags & TR_BSDF_FLAG_TWOSIDED)) { err = "twosided cannot wrap a transmissive bsdf"; return false; }
+        for (int c = 0; c < 3; ++c) {
+            bsdfs[i].r[c] = desc->bsdfs[i].reflectance[c]; bsdfs[i].eta[c] = desc->bsdfs[i].eta[c];
+            bsdfs[i].k[c] = desc->bsdfs[i].k[c]; bsdfs[i].tr[c] = desc->bsdfs[i].specular_transmittance[c];
+        }
+        if (bsdfs[i].type >= TR_BSDF_CONDUCTOR) out.has_delta_bsdfs = true;
     }
     std::vector<DevEmitter> emitters(std::max(1u, desc->n_emitters));
     memset(emitters.data(), 0, emitters.size() * sizeof(DevEmitter));

@@ -79,8 +79,8 @@ struct DevShape {              // 128 bytes
 };
 static_assert(sizeof(DevShape) == 128, "DevShape must be 128 bytes");
 
-struct DevBsdf { int32_t type, flags; float r[3]; float _pad[3]; };          // 32 bytes
-static_assert(sizeof(DevBsdf) == 32, "DevBsdf must be 32 bytes");
+struct DevBsdf { int32_t type, flags; float r[3]; float eta[3]; float k[3]; float tr[3]; float _pad[2]; };   // 64 bytes = 4 x float4
+static_assert(sizeof(DevBsdf) == 64, "DevBsdf must be 64 bytes");
 
 struct DevEmitter {            // 96 bytes
     int32_t type, shape; float radiance[3]; float fov_x;   // 24
@@ -98,6 +98,7 @@ struct SceneImpl {
     TrSensorDesc sensor;
     TrFilmDesc film;
     uint32_t n_nodes = 0, n_prims = 0;
+    bool has_delta_bsdfs = false;        // conductor / dielectric present: the general-material kernel instantiation is used
     int device = -1;
     // cached owned-pixel list (tile sharding), rebuilt when (tile, rank, world) changes
     void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;

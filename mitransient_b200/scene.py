@@ -191,7 +191,23 @@ def _to_transform(v) -> ScalarTransform4f:
 
 # ------------------------------------------------------------------------------------ deferred plugins
 _SHAPE_TYPES = ("rectangle", "cube", "obj", "trimesh")
-_BSDF_TYPES = ("diffuse", "twosided", "null")
+_BSDF_TYPES = ("diffuse", "twosided", "null", "conductor", "dielectric")
+
+# Named indices of refraction accepted by `dielectric` (int_ior / ext_ior), Mitsuba's ior.h table [upstream]
+_IOR_TABLE = {"vacuum": 1.0, "helium": 1.00004, "hydrogen": 1.00013, "air": 1.000277, "carbon dioxide": 1.00045,
+              "water": 1.3330, "acetone": 1.36, "ethanol": 1.361, "carbon tetrachloride": 1.461, "glycerol": 1.4729,
+              "benzene": 1.501, "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458,
+              "pyrex": 1.470, "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544,
+              "amber": 1.55, "pet": 1.575, "diamond": 2.419}
+
+
+def _ior(v, default: str) -> float:
+    v = default if v is None else v
+    if isinstance(v, str):
+        if v.lower() not in _IOR_TABLE:
+            raise ValueError(f"unknown index of refraction name {v!r}")
+        return float(_IOR_TABLE[v.lower()])
+    return float(v)
 
 
 class PluginSpec(dict):
@@ -320,6 +336,12 @@ class Scene:
         for i, b in enumerate(self.bsdfs_):
             bsdfs[i].type, bsdfs[i].flags = b["type"], b["flags"]
             bsdfs[i].reflectance[:] = [float(x) for x in _variant.colour(b["reflectance"])]
+            if "eta" in b:
+                bsdfs[i].eta[:] = [float(x) for x in _variant.colour(b["eta"])]
+            if "k" in b:
+                bsdfs[i].k[:] = [float(x) for x in _variant.colour(b["k"])]
+            if "specular_transmittance" in b:
+                bsdfs[i].specular_transmittance[:] = [float(x) for x in _variant.colour(b["specular_transmittance"])]
         emitters = (_abi.TrEmitterDesc * max(1, len(self.emitters_)))()
         for i, e in enumerate(self.emitters_):
             emitters[i].type, emitters[i].shape = e["type"], e["shape"]
@@ -463,8 +485,26 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
             entry = {"type": _abi.TR_BSDF_DIFFUSE, "flags": flags, "reflectance": _rgb(spec.get("reflectance"), 0.5)}
         elif bt == "null":
             entry = {"type": _abi.TR_BSDF_NULL, "flags": flags, "reflectance": ScalarColor3d(0.0)}
+        elif bt == "conductor":      # Mitsuba `conductor`: material "none" = perfect mirror (eta 0, k 1), or explicit eta / k
+            material = spec.get("material", None)
+            if material is not None and str(material).lower() != "none":
+                raise ValueError(f"conductor material {material!r}: only 'none' or explicit eta / k are supported "
+                                 "(the measured spectral IOR tables are not shipped)")
+            has_ior = "eta" in spec or "k" in spec
+            entry = {"type": _abi.TR_BSDF_CONDUCTOR, "flags": flags,
+                     "reflectance": _rgb(spec.get("specular_reflectance"), 1.0),
+                     "eta": _rgb(spec.get("eta"), 0.0) if has_ior else ScalarColor3d(0.0),
+                     "k": _rgb(spec.get("k"), 1.0) if has_ior else ScalarColor3d(1.0)}
+        elif bt == "dielectric":     # Mitsuba `dielectric`: int_ior "bk7", ext_ior "air" by default
+            if flags & _abi.TR_BSDF_FLAG_TWOSIDED:
+                raise ValueError("twosided cannot wrap a transmissive bsdf (dielectric)")
+            eta = _ior(spec.get("int_ior"), "bk7") / _ior(spec.get("ext_ior"), "air")
+            entry = {"type": _abi.TR_BSDF_DIELECTRIC, "flags": flags,
+                     "reflectance": _rgb(spec.get("specular_reflectance"), 1.0), "eta": ScalarColor3d(eta),
+                     "specular_transmittance": _rgb(spec.get("specular_transmittance"), 1.0)}
         else:
-            raise ValueError(f"unsupported bsdf type {bt!r} (supported: diffuse, twosided(diffuse), null)")
+            raise ValueError(f"unsupported bsdf type {bt!r} (supported: diffuse, conductor, dielectric, null, "
+                             "twosided(diffuse | conductor))")
         scene.bsdfs_.append(entry)
         return len(scene.bsdfs_) - 1
 
@@ -488,7 +528,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
     default_bsdf = None
     # first pass: named bsdfs / media keep their dictionary order (ids are the dict keys)
     for key, val in d.items():
-        if isinstance(val, dict) and val.get("type") in ("diffuse", "twosided", "null"):
+        if isinstance(val, dict) and val.get("type") in _BSDF_TYPES:
             named_bsdf[key] = add_bsdf(val)
         elif isinstance(val, dict) and val.get("type") == "homogeneous":
             named_medium[key] = add_medium(val)
@@ -524,7 +564,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 if ct is not None and ck not in ("interior", "exterior") and ct not in _BSDF_TYPES + (
                         "ref", "area", "homogeneous") + tuple(plugins.SENSORS):
                     raise ValueError(f"shape {key!r}: unsupported nested plugin type {ct!r} (supported bsdfs: diffuse, "
-                                     "twosided(diffuse), null; emitters: area; sensors: nlos_capture_meter)")
+                                     "conductor, dielectric, twosided, null; emitters: area; sensors: nlos_capture_meter)")
             _, bspec = _find_child(val, _BSDF_TYPES + ("ref",))
             if bspec is None:
                 if default_bsdf is None:

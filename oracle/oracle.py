@@ -48,6 +48,9 @@ def load() -> C.CDLL:
         lib.oracle_tea32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.oracle_sampler_floats.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         lib.oracle_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.oracle_fresnel_conductor.restype = C.c_float
+        lib.oracle_fresnel_conductor.argtypes = [C.c_float, C.c_float, C.c_float]
+        lib.oracle_fresnel_dielectric.argtypes = [C.c_float, C.c_float, C.c_void_p]
         lib.oracle_exp.restype = C.c_float; lib.oracle_exp.argtypes = [C.c_float]
         lib.oracle_log.restype = C.c_float; lib.oracle_log.argtypes = [C.c_float]
         lib.oracle_cosine_hemisphere.argtypes = [C.c_float, C.c_float, C.c_void_p]
@@ -140,6 +143,17 @@ def sincos(x):
     s, c = C.c_float(), C.c_float()
     load().oracle_sincos(x, C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def fresnel_conductor(cos_theta_i, eta, k):
+    return load().oracle_fresnel_conductor(cos_theta_i, eta, k)
+
+
+def fresnel_dielectric(cos_theta_i, eta):
+    """-> (r, cos_theta_t, eta_it, eta_ti) like mitsuba's fresnel()"""
+    out = np.zeros(4, dtype=np.float32)
+    load().oracle_fresnel_dielectric(cos_theta_i, eta, out.ctypes.data)
+    return tuple(float(x) for x in out)
 
 
 def cosine_hemisphere(u0, u1):

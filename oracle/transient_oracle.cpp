@@ -593,6 +593,36 @@ inline Ray sample_camera_ray(const Scene &sc, uint32_t px, uint32_t py, float jx
 }
 
 // ------------------------------------------------------------------------------ transient_path
+// ---- Mitsuba 3 fresnel.h [upstream], restated ------------------------------------------------------------------
+// fresnel_conductor(cos_theta_i, eta + i k): unpolarized reflectance of a conductor ("Optics", K.D. Moeller)
+inline float safe_sqrt(float x) { return sqrtf(fmaxf(x, 0.0f)); }
+inline float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
+    float cos_theta_i_2 = cos_theta_i * cos_theta_i, sin_theta_i_2 = 1.0f - cos_theta_i_2, sin_theta_i_4 = sin_theta_i_2 * sin_theta_i_2;
+    float temp_1 = eta_r * eta_r - eta_i * eta_i - sin_theta_i_2;
+    float a_2_pb_2 = safe_sqrt(temp_1 * temp_1 + 4.0f * eta_i * eta_i * eta_r * eta_r);
+    float a = safe_sqrt(0.5f * (a_2_pb_2 + temp_1));
+    float term_1 = a_2_pb_2 + cos_theta_i_2, term_2 = 2.0f * cos_theta_i * a;
+    float r_s = (term_1 - term_2) / (term_1 + term_2);
+    float term_3 = a_2_pb_2 * cos_theta_i_2 + sin_theta_i_4, term_4 = term_2 * sin_theta_i_2;
+    float r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return 0.5f * (r_s + r_p);
+}
+// fresnel(cos_theta_i, eta) of a dielectric interface -> (r, cos_theta_t, eta_it, eta_ti)
+inline void fresnel_dielectric(float cos_theta_i, float eta, float *r_out, float *cos_theta_t_out, float *eta_it_out, float *eta_ti_out) {
+    bool outside = cos_theta_i >= 0.0f;
+    float rcp_eta = 1.0f / eta, eta_it = outside ? eta : rcp_eta, eta_ti = outside ? rcp_eta : eta;
+    float cos_theta_t_sqr = fmaf(-fmaf(-cos_theta_i, cos_theta_i, 1.0f), eta_ti * eta_ti, 1.0f);
+    float cos_theta_i_abs = fabsf(cos_theta_i), cos_theta_t_abs = safe_sqrt(cos_theta_t_sqr);
+    bool index_matched = eta == 1.0f, special_case = index_matched || cos_theta_i_abs == 0.0f;
+    float r_sc = index_matched ? 0.0f : 1.0f;
+    float a_s = fmaf(-eta_it, cos_theta_t_abs, cos_theta_i_abs) / fmaf(eta_it, cos_theta_t_abs, cos_theta_i_abs);
+    float a_p = fmaf(-eta_it, cos_theta_i_abs, cos_theta_t_abs) / fmaf(eta_it, cos_theta_i_abs, cos_theta_t_abs);
+    float r = 0.5f * (a_s * a_s + a_p * a_p);
+    if (special_case) r = r_sc;
+    *r_out = r; *cos_theta_t_out = cos_theta_i >= 0.0f ? -cos_theta_t_abs : cos_theta_t_abs;   // mulsign_neg
+    *eta_it_out = eta_it; *eta_ti_out = eta_ti;
+}
+
 // mitransient/integrators/transientpath.py:109-326 (primal branch).  Returns L.
 V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
                         float px, float py, float sample_scale, float ray_weight, Film &film) {
@@ -690,9 +720,44 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
         film.add_transient(px, py, Lr_dir, distance + ds_dist * eta, sample_scale, ray_weight);  // :217-219
 
         // ---------------- BSDF sampling :223-228
-        float s1 = rng.next_1d(); (void) s1;                       // sampler.next_1d() (unused by diffuse)
+        float s1 = rng.next_1d();                                  // sampler.next_1d() (lobe selection of `dielectric`)
         float s2x = rng.next_1d(), s2y = rng.next_1d();            // sampler.next_2d()
         V3 bsdf_weight = v3(0, 0, 0); float bs_pdf = 0.0f; V3 wo_world = v3(0, 0, 0);
+        float bs_eta = 1.0f; bool bs_delta = false;
+        if (active_next && (bsdf->type == TR_BSDF_CONDUCTOR || bsdf->type == TR_BSDF_DIELECTRIC)) {
+            // si.wi = si.to_local(-ray.d); the samplers below work in the local frame like conductor.cpp / dielectric.cpp
+            V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));
+            V3 wo;
+            if (bsdf->type == TR_BSDF_CONDUCTOR) {                 // SmoothConductor::sample (+ TwoSided::sample)
+                bool flip = twosided && wi.z < 0.0f;
+                if (flip) wi.z = -wi.z;
+                wo = v3(-wi.x, -wi.y, wi.z);                       // reflect(wi)
+                bs_pdf = 1.0f;
+                if (wi.z > 0.0f)
+                    bsdf_weight = v3(bsdf->reflectance[0] * fresnel_conductor(wi.z, bsdf->eta[0], bsdf->k[0]),
+                                     bsdf->reflectance[1] * fresnel_conductor(wi.z, bsdf->eta[1], bsdf->k[1]),
+                                     bsdf->reflectance[2] * fresnel_conductor(wi.z, bsdf->eta[2], bsdf->k[2]));
+                if (flip) wo.z = -wo.z;
+            } else {                                               // SmoothDielectric::sample
+                float r_i, cos_theta_t, eta_it, eta_ti;
+                fresnel_dielectric(wi.z, bsdf->eta[0], &r_i, &cos_theta_t, &eta_it, &eta_ti);
+                float t_i = 1.0f - r_i;
+                bool selected_r = s1 <= r_i;
+                bs_pdf = selected_r ? r_i : t_i;
+                if (selected_r) {
+                    wo = v3(-wi.x, -wi.y, wi.z);
+                    bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
+                } else {
+                    wo = v3(-eta_ti * wi.x, -eta_ti * wi.y, cos_theta_t);      // refract(wi, cos_theta_t, eta_ti)
+                    bs_eta = eta_it;
+                    float f2 = eta_ti * eta_ti;                    // radiance transport: scale by eta_ti^2
+                    bsdf_weight = v3(bsdf->specular_transmittance[0] * f2, bsdf->specular_transmittance[1] * f2,
+                                     bsdf->specular_transmittance[2] * f2);
+                }
+            }
+            bs_delta = true;
+            wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));       // si.to_world(wo)
+        }
         if (active_next && smooth) {
             V3 wo = square_to_cosine_hemisphere(s2x, s2y);
             bs_pdf = kInvPi * wo.z;
@@ -705,9 +770,9 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
         // ---------------- update loop variables :231-241
         L = L + Le + Lr_dir;                                       // :231
         if (si.valid) ray = spawn_ray(si.p, si.n, wo_world);       // :232
-        // eta *= bs.eta (== 1 for diffuse)                        // :233
+        eta *= bs_eta;                                             // :233 (== 1 except for a refraction)
         beta = beta * bsdf_weight;                                 // :234
-        prev_p = si.p; prev_bsdf_pdf = bs_pdf; prev_bsdf_delta = false;   // :238-241
+        prev_p = si.p; prev_bsdf_pdf = bs_pdf; prev_bsdf_delta = bs_delta;   // :238-241
 
         // ---------------- stopping criterion :246-258
         float beta_max = max3(beta);
@@ -1414,6 +1479,10 @@ void oracle_sampler_floats(uint32_t seed, uint32_t lane, float *out, int n) {
     for (int i = 0; i < n; ++i) out[i] = r.next_1d();
 }
 void oracle_sincos(float x, float *s, float *c) { sincos_cephes(x, s, c); }
+float oracle_fresnel_conductor(float cos_theta_i, float eta, float k) { return fresnel_conductor(cos_theta_i, eta, k); }
+void oracle_fresnel_dielectric(float cos_theta_i, float eta, float *out4) {
+    fresnel_dielectric(cos_theta_i, eta, out4, out4 + 1, out4 + 2, out4 + 3);
+}
 float oracle_exp(float x) { return exp_cephes(x); }
 float oracle_log(float x) { return log_cephes(x); }
 void oracle_cosine_hemisphere(float u0, float u1, float *xyz) {

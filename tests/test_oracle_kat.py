@@ -314,3 +314,80 @@ def test_exhaustive_capture_energy_and_layout(oracle, mitr):
     s2 = mitr.load_dict(d2)
     r2 = oracle.render(s2, s2.integrator(), spp=spp)
     assert r2["transient"].shape == (res, res, T, 4) and r2["counters"]["shadow_rays"] < r["counters"]["shadow_rays"]
+
+
+# ---------------------------------------------------------------- conductor / dielectric (delta lobes, eta-scaled OPL)
+def test_fresnel_known_answers(oracle):
+    for c in (1.0, 0.7, 0.3, 0.05):
+        assert abs(oracle.fresnel_conductor(c, 0.0, 1.0) - 1.0) < 1e-6               # material "none": perfect mirror
+    n, k = 0.2, 3.5
+    assert abs(oracle.fresnel_conductor(1.0, n, k) - ((n - 1) ** 2 + k * k) / ((n + 1) ** 2 + k * k)) < 1e-6
+    r, cos_t, eta_it, eta_ti = oracle.fresnel_dielectric(1.0, 1.5)
+    assert abs(r - 0.04) < 1e-6 and abs(cos_t + 1.0) < 1e-6 and abs(eta_it - 1.5) < 1e-7 and abs(eta_ti - 1 / 1.5) < 1e-7
+    r, cos_t, eta_it, eta_ti = oracle.fresnel_dielectric(-1.0, 1.5)                  # from the inside
+    assert abs(r - 0.04) < 1e-6 and abs(cos_t - 1.0) < 1e-6 and abs(eta_it - 1 / 1.5) < 1e-7
+    r, cos_t, _, _ = oracle.fresnel_dielectric(-0.5, 1.5)                            # beyond the critical angle (41.8 deg)
+    assert r == 1.0 and cos_t == 0.0
+    c = 0.6                                                                          # Snell: sin_t = sin_i / eta
+    r, cos_t, _, _ = oracle.fresnel_dielectric(c, 1.5)
+    assert abs(-cos_t - math.sqrt(1 - (1 - c * c) / 2.25)) < 1e-6 and 0.04 < r < 1.0
+    assert oracle.fresnel_dielectric(0.3, 1.0)[0] == 0.0                             # index matched
+
+
+def _delta_scene(mitr, middle, T=512, window=(0.0, 16.0), spp=64, max_depth=8):
+    """Pinhole at the origin looking down +z through a tiny field of view; `middle` = extra shapes; an area light
+    (radiance 2) either behind the camera (mirror test) or far in front (glass test)."""
+    TT = mitr.ScalarTransform4f
+    d = {"type": "scene",
+         "integrator": {"type": "transient_path", "max_depth": max_depth, "rr_depth": 1000},
+         "sensor": {"type": "perspective", "fov": 0.5, "near_clip": 0.01, "far_clip": 100.0,
+                    "to_world": TT().look_at(origin=[0, 0, 0], target=[0, 0, 1], up=[0, 1, 0]),
+                    "sampler": {"type": "independent", "sample_count": spp},
+                    "film": {"type": "transient_hdr_film", "width": 2, "height": 2, "temporal_bins": T,
+                             "start_opl": window[0], "bin_width_opl": (window[1] - window[0]) / T,
+                             "rfilter": {"type": "box"}}}}
+    d.update(middle)
+    return d
+
+
+def test_mirror_time_of_flight(oracle, mitr):
+    """KAT: a perfect mirror at z = 2 shows the light at z = -1: every pixel holds exactly the radiance, in the bin
+    of OPL 2 + 3 (delta lobe: MIS weight 1, no emitter sampling at the mirror)."""
+    TT = mitr.ScalarTransform4f
+    d = _delta_scene(mitr, {
+        "mirror": {"type": "rectangle", "to_world": TT().translate([0, 0, 2]).rotate([0, 1, 0], 180),
+                   "bsdf": {"type": "conductor", "material": "none"}},
+        "light": {"type": "rectangle", "to_world": TT().translate([0, 0, -1]),
+                  "bsdf": {"type": "diffuse", "reflectance": 0.0}, "emitter": {"type": "area", "radiance": 2.0}}})
+    scene = mitr.load_dict(d)
+    r = oracle.render(scene, scene.integrator(), spp=64)
+    T = 512
+    film = r["transient"][..., :3]
+    b = int(math.floor(5.0 / (16.0 / T)))
+    got = film[:, :, b - 1:b + 2].sum(axis=2)
+    np.testing.assert_allclose(got, 2.0, rtol=1e-4)
+    assert np.abs(film).sum() == pytest.approx(got.sum(), rel=1e-6)
+    assert r["counters"]["shadow_rays"] == 0                                         # nothing smooth was ever hit
+
+
+def test_glass_slab_optical_path_length(oracle, mitr):
+    """KAT: light at z = 4 seen through a 1-thick glass slab (eta 1.5) at normal incidence: the direct image arrives
+    at OPL 1 + 1.5 + 2 = 4.5 with weight T^2 (T = 0.96, the eta^2 radiance factors cancel), the first internal
+    double reflection at 4.5 + 3 with weight T^2 R^2 (transientpath.py:154: distance += si.t * eta)."""
+    TT = mitr.ScalarTransform4f
+    d = _delta_scene(mitr, {
+        "slab": {"type": "cube", "to_world": TT().translate([0, 0, 1.5]).scale([5, 5, 0.5]),
+                 "bsdf": {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0}},
+        "light": {"type": "rectangle", "to_world": TT().translate([0, 0, 4]).rotate([0, 1, 0], 180),
+                  "bsdf": {"type": "diffuse", "reflectance": 0.0}, "emitter": {"type": "area", "radiance": 2.0}}},
+        spp=4096, max_depth=12)
+    scene = mitr.load_dict(d)
+    r = oracle.render(scene, scene.integrator(), spp=4096)
+    T, bw = 512, 16.0 / 512
+    film = r["transient"][..., 0].astype(np.float64).mean(axis=(0, 1))
+    b0, b1 = int(4.5 / bw), int(7.5 / bw)
+    direct = film[b0 - 1:b0 + 2].sum()
+    bounce = film[b1 - 1:b1 + 2].sum()
+    assert direct == pytest.approx(2.0 * 0.96 ** 2, rel=0.02)
+    assert bounce == pytest.approx(2.0 * 0.96 ** 2 * 0.04 ** 2, rel=0.25)
+    assert film[:b0 - 1].sum() == 0.0                                                # nothing arrives earlier
