@@ -204,3 +204,32 @@ def test_sharded_render_to_host_assembles_to_the_full_film(mitr):
     err = (full - ref).abs().sum() / ref.abs().sum()
     assert err <= 1e-5, err
     np.testing.assert_allclose(full_s.numpy(), steady.cpu().reshape(h * w, 3).numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("w,h,t,spp", [(1, 1, 1, 1), (1, 1, 64, 33), (5, 3, 1, 7), (3, 2, 20000, 8), (33, 17, 7, 1)])
+def test_edge_sizes(mitr, oracle, w, h, t, spp):
+    """Degenerate and extreme film sizes: one pixel, one bin, one sample, ragged sizes, and a histogram too large
+    for shared memory (20000 bins -> global vector-reduction path, cleared by the library)."""
+    steady, transient, raw, counters, ref = _render_both(mitr, oracle, (w, h, t), spp, seed=9)
+    assert counters == ref["counters"]
+    assert raw.shape == (h, w, t, 4)
+    err = film_l1(raw, ref["transient"])
+    assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL, err
+    np.testing.assert_allclose(steady, ref["steady"], rtol=1e-4, atol=1e-6)
+
+
+def test_too_many_samples_is_rejected_like_the_reference_splits(mitr):
+    """width*height*spp > 2^32 never reaches the kernel in one pass: prepare() splits it (common.py:51-85) and the
+    C ABI rejects a single oversized pass."""
+    import ctypes as C
+    from mitransient_b200 import _lib
+    scene = mitr.load_dict(mitr.cornell_box_config(512, 512, 8, 1))
+    integ = scene.integrator()
+    passes = integ.prepare(scene, scene.sensors()[0], 0, 2 ** 15)                    # 2^33 samples
+    assert len(passes) > 1 and sum(s for _, s in passes) == 2 ** 15 and all(s * 512 * 512 < 2 ** 26 + 1 for _, s in passes)
+    dev = integ.device_scene(scene, scene.sensors()[0])
+    film = scene.sensors()[0].film()
+    p = integ.make_params(2 ** 15, 2 ** 15, 0)
+    rc = _lib.load().tr_render(dev.handle, C.byref(p), film.transient_storage.data_ptr(), film.steady_storage.data_ptr(),
+                               None, _lib.current_stream_ptr())
+    assert rc == mitr._abi.TR_ERR_INVALID_ARGUMENT and b"2^32" in _lib.load().tr_last_error()
