@@ -23,7 +23,7 @@ from .integrators.transient_prbvolpath import TransientPRBVolpathIntegrator
 from . import nlos
 from . import vis
 from .plugins import register_film, register_integrator, register_sensor
-from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj
+from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, load_dict, load_obj, load_ply
 from .sensors.nloscapturemeter import NLOSCaptureMeter
 from .transforms import ScalarTransform4f
 from .xml import load_file, xml_to_dict

@@ -63,8 +63,9 @@ class TransientNLOSPath(TransientADIntegrator):
         if self.camera_unwarp:                                                              # :725-727
             raise AssertionError("Do not use camera_unwarp with TransientNLOSPath. Use "
                                  "account_first_and_last_bounces instead for the same purpose.")
-        if not isinstance(sensor, NLOSCaptureMeter):
-            raise NotImplementedError("transient_nlos_path is implemented for the nlos_capture_meter sensor")
+        from ..scene import PerspectiveSensor
+        if not isinstance(sensor, (NLOSCaptureMeter, PerspectiveSensor)):
+            raise NotImplementedError("transient_nlos_path is implemented for nlos_capture_meter and perspective sensors")
         ems = scene.emitters()
         if len(ems) != 1:                                                                   # :257-260
             raise ValueError(f"You have defined multiple ({len(ems)}) emitters in the scene with a NLOS capture "
@@ -82,7 +83,7 @@ class TransientNLOSPath(TransientADIntegrator):
             if (film.laser_scan_width, film.laser_scan_height) != tuple(film.size()):           # :345-348
                 raise AssertionError("Sensor and laser scan resolution must be equal if "
                                      "force_equal_illumination_scanning is set to True")
-        if sensor.is_confocal:
+        if getattr(sensor, "is_confocal", False):
             raise NotImplementedError("1x1 confocal sensors (original_film_width/height) are not implemented; use "
                                       "capture_type='confocal' on the integrator")
         if self.hg_sampling:                                                                # :277-289

@@ -113,6 +113,89 @@ def load_obj(path: str) -> np.ndarray:
     return v[t]
 
 
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2",
+              "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4",
+              "double": "f8", "float64": "f8"}
+
+
+def load_ply(path: str) -> np.ndarray:
+    """Stanford PLY (ascii, binary_little_endian or binary_big_endian) -> float64 [n_tris, 3, 3] triangle primitives.
+    Vertex properties other than x, y, z (normals, uv, colours) are skipped -- face normals are used, as for OBJ; polygon
+    faces are fan-triangulated; elements other than `vertex` and `face` are skipped."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt, elements = None, []
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: unterminated PLY header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] in ("comment", "obj_info"):
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append({"name": tok[1], "count": int(tok[2]), "props": []})
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    elements[-1]["props"].append(("list", _PLY_TYPES[tok[2]], _PLY_TYPES[tok[3]], tok[4]))
+                else:
+                    elements[-1]["props"].append(("scalar", _PLY_TYPES[tok[1]], None, tok[2]))
+            elif tok[0] == "end_header":
+                break
+        if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: unsupported PLY format {fmt!r}")
+        verts, tris = None, []
+        if fmt == "ascii":
+            tokens = f.read().split()
+            pos = 0
+            for el in elements:
+                rows = []
+                for _ in range(el["count"]):
+                    row = {}
+                    for kind, t0, t1, name in el["props"]:
+                        if kind == "scalar":
+                            row[name] = float(tokens[pos]); pos += 1
+                        else:
+                            n = int(tokens[pos]); pos += 1
+                            row[name] = [int(x) for x in tokens[pos:pos + n]]; pos += n
+                    rows.append(row)
+                if el["name"] == "vertex":
+                    verts = np.array([[r["x"], r["y"], r["z"]] for r in rows], dtype=np.float64).reshape(-1, 3)
+                elif el["name"] == "face":
+                    key = next(n for k, _, _, n in el["props"] if k == "list")
+                    for r in rows:
+                        idx = r[key]
+                        tris.extend([idx[0], idx[k], idx[k + 1]] for k in range(1, len(idx) - 1))
+        else:
+            e = "<" if fmt == "binary_little_endian" else ">"
+            for el in elements:
+                if all(k == "scalar" for k, _, _, _ in el["props"]):
+                    dt = np.dtype([(name, e + t0) for _, t0, _, name in el["props"]])
+                    data = np.frombuffer(f.read(dt.itemsize * el["count"]), dtype=dt, count=el["count"])
+                    if el["name"] == "vertex":
+                        verts = np.stack([data["x"], data["y"], data["z"]], axis=1).astype(np.float64)
+                    continue
+                for _ in range(el["count"]):           # an element with list properties: row by row
+                    for kind, t0, t1, name in el["props"]:
+                        if kind == "scalar":
+                            f.read(np.dtype(t0).itemsize)
+                            continue
+                        n = int(np.frombuffer(f.read(np.dtype(t0).itemsize), dtype=e + t0)[0])
+                        idx = np.frombuffer(f.read(np.dtype(t1).itemsize * n), dtype=e + t1).astype(np.int64)
+                        if el["name"] == "face" and name in ("vertex_indices", "vertex_index"):
+                            tris.extend([idx[0], idx[k], idx[k + 1]] for k in range(1, n - 1))
+    if verts is None:
+        raise ValueError(f"{path}: PLY file without a vertex element")
+    t = np.asarray(tris, dtype=np.int64).reshape(-1, 3)
+    if t.size == 0:
+        return np.zeros((0, 3, 3))
+    if t.min() < 0 or t.max() >= len(verts):
+        raise ValueError(f"{path}: face index out of range")
+    return verts[t]
+
+
 def merge_quads(tris: np.ndarray, rel_eps: float = 1e-6):
     """Greedily merge pairs of triangles that share an edge and together form a parallelogram into one
     TR_PRIM_QUAD (p0, p1, p2 with the fourth corner p1 + p2 - p0).  Geometry and orientation are unchanged;
@@ -190,7 +273,7 @@ def _to_transform(v) -> ScalarTransform4f:
 
 
 # ------------------------------------------------------------------------------------ deferred plugins
-_SHAPE_TYPES = ("rectangle", "cube", "obj", "trimesh")
+_SHAPE_TYPES = ("rectangle", "cube", "obj", "ply", "trimesh")
 _BSDF_TYPES = ("diffuse", "twosided", "null", "conductor", "dielectric")
 
 # Named indices of refraction accepted by `dielectric` (int_ior / ext_ior), Mitsuba's ior.h table [upstream]
@@ -553,9 +636,9 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 fn = val["filename"]
                 if not os.path.isabs(fn) and base_dir:
                     fn = os.path.join(base_dir, fn)
-                base = load_obj(fn)
+                base = load_ply(fn) if t == "ply" else load_obj(fn)
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
-            if t in ("obj", "trimesh") and bool(val.get("merge_quads", True)) and len(base) > 1:
+            if t in ("obj", "ply", "trimesh") and bool(val.get("merge_quads", True)) and len(base) > 1:
                 base, ptypes = merge_quads(base)     # coplanar triangle pairs -> parallelogram primitives
             if base.shape[1] == 3:
                 base = _with_p3(base, ptypes)

@@ -822,8 +822,10 @@ inline Ray nlos_sensor_ray(const Scene &sc, float sx, float sy) {
 // TransientNLOSPath.prepare   transientnlospath.py:251-383
 bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::string &err) {
     if (sc.emitters.size() != 1 || sc.emitters[0].type != TR_EMITTER_PROJECTOR) { err = "transient_nlos_path needs exactly one projector emitter"; return false; }
-    if (sc.sensor.type != TR_SENSOR_NLOS_CAPTURE_METER || sc.sensor.shape < 0 || (uint32_t) sc.sensor.shape >= sc.shapes.size() ||
-        sc.shapes[sc.sensor.shape].d.type != TR_SHAPE_RECTANGLE) { err = "transient_nlos_path needs an nlos_capture_meter on a rectangle"; return false; }
+    const bool meter = sc.sensor.type == TR_SENSOR_NLOS_CAPTURE_METER;
+    if (meter && (sc.sensor.shape < 0 || (uint32_t) sc.sensor.shape >= sc.shapes.size() ||
+                  sc.shapes[sc.sensor.shape].d.type != TR_SHAPE_RECTANGLE)) { err = "transient_nlos_path needs an nlos_capture_meter on a rectangle"; return false; }
+    if (!meter && sc.sensor.type != TR_SENSOR_PERSPECTIVE) { err = "transient_nlos_path: unknown sensor"; return false; }
     if (rp.capture_type != TR_CAPTURE_SINGLE && rp.capture_type != TR_CAPTURE_CONFOCAL && rp.capture_type != TR_CAPTURE_EXHAUSTIVE) {
         err = "unknown capture type"; return false;
     }
@@ -838,7 +840,7 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
     const float *m = ctx.em->to_world;
     ctx.em_origin = v3(m[3], m[7], m[11]);
     ctx.em_forward = v3(m[2], m[6], m[10]);                   // trafo @ Vector3f(0, 0, 1)
-    ctx.sensor_shape = (uint32_t) sc.sensor.shape;
+    ctx.sensor_shape = meter ? (uint32_t) sc.sensor.shape : 0xffffffffu;
     // hidden-geometry area distribution :277-292
     ctx.hg_pmf.clear(); ctx.hg_cdf.clear();
     double acc = 0.0;
@@ -854,7 +856,10 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
     ctx.sensor_targets.resize((size_t) W * H);
     float stepx = 1.0f / (float) W, stepy = 1.0f / (float) H;     // dr.linspace(0, 1, n, endpoint=False)
     for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x) {
-        Hit h = ray_intersect(sc, nlos_sensor_ray(sc, fmaf((float) x, stepx, 0.0f), fmaf((float) y, stepy, 0.0f)));
+        // sensor.sample_ray at the film position (x / W, y / H): the capture meter snaps to the pixel centre, a
+        // perspective camera shoots through the pixel corner
+        Hit h = ray_intersect(sc, meter ? nlos_sensor_ray(sc, fmaf((float) x, stepx, 0.0f), fmaf((float) y, stepy, 0.0f))
+                                        : sample_camera_ray(sc, x, y, 0.0f, 0.0f));
         ctx.sensor_targets[(size_t) y * W + x] = h.p;             // si.p (zeros when the ray misses)
     }
     // Single capture: where the laser axis meets the scene :328-336
@@ -1366,8 +1371,8 @@ void render_rows(RenderJob *job) {
                     L = trace_volpath(sc, rp, rng, sample_camera_ray(sc, x, y, jx, jy), (float) x, (float) y, sample_scale, film);
                 } else if (job->nlos) {
                     float sx = ((float) x + jx) * (1.0f / (float) W), sy = ((float) y + jy) * (1.0f / (float) H);
-                    L = trace_nlos_path(sc, rp, *job->nlos, rng, nlos_sensor_ray(sc, sx, sy), y * W + x, (float) x, (float) y,
-                                        sample_scale, film);
+                    Ray sray = sc.sensor.type == TR_SENSOR_PERSPECTIVE ? sample_camera_ray(sc, x, y, jx, jy) : nlos_sensor_ray(sc, sx, sy);
+                    L = trace_nlos_path(sc, rp, *job->nlos, rng, sray, y * W + x, (float) x, (float) y, sample_scale, film);
                 } else {
                     Ray ray = sample_camera_ray(sc, x, y, jx, jy);
                     L = trace_transient_path(sc, rp, rng, ray, (float) x, (float) y, sample_scale, 1.0f, film);

@@ -74,3 +74,26 @@ def test_nlos_rejections(mitr):
     scene = mitr.load_dict(d)
     with pytest.raises(ValueError, match="exhaustive_scan"):
         scene.integrator().render(scene, spp=1)
+
+
+@pytest.mark.parametrize("capture", ["single", "confocal"])
+def test_nlos_path_with_a_perspective_camera(mitr, oracle, capture):
+    """transient_nlos_path looking at the relay wall through an ordinary perspective camera (the setup of
+    examples/transient-nlos/nlos-z-simple.xml) instead of an nlos_capture_meter."""
+    T = mitr.ScalarTransform4f
+    v, f = mitr.letter_z_mesh()
+    cam = T().look_at(origin=[-1.2, 0.0, 1.6], target=[0.0, 0.0, 0.0], up=[0, 1, 0])
+    d = {"type": "scene",
+         "integrator": {"type": "transient_nlos_path", "nlos_laser_sampling": True, "nlos_hidden_geometry_sampling": True,
+                        "capture_type": capture, "account_first_and_last_bounces": capture == "single", "max_depth": 5},
+         "sensor": {"type": "perspective", "fov": 40.0, "near_clip": 0.1, "far_clip": 100.0, "to_world": cam,
+                    "sampler": {"type": "independent", "sample_count": 32},
+                    "film": {"type": "transient_hdr_film", "width": 16, "height": 12, "temporal_bins": 256,
+                             "start_opl": 0.0, "bin_width_opl": 12.0 / 256, "rfilter": {"type": "box"}}},
+         "emitter": {"type": "projector", "irradiance": 100.0, "fov": 0.2, "to_world": cam},
+         "relay_wall": {"type": "rectangle", "to_world": T().scale([2.0, 2.0, 1.0]),
+                        "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.8}}},
+         "hidden": {"type": "trimesh", "vertices": v, "faces": f, "to_world": T().translate([0.0, 0.0, 1.0]),
+                    "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 1.0}}}}
+    raw, ref = _both(mitr, oracle, d, 32, seed=4)
+    assert ref["counters"]["shadow_rays"] > 0

@@ -243,3 +243,36 @@ def test_tonemap_transient_matches_numpy_quantile(mitr):
     np.testing.assert_allclose(mitr.vis.tonemap_transient(x, scaling=2.0), want, rtol=1e-6)
     got = mitr.vis.tonemap_transient(torch.from_numpy(x), scaling=2.0)
     np.testing.assert_allclose(got.numpy(), want, rtol=1e-5)
+
+
+def test_ply_loader_ascii_and_binary(mitr, tmp_path):
+    """`ply` shapes (examples/transient-nlos/nlos-z-room.xml): binary little/big endian and ascii, extra vertex
+    properties skipped, polygons fan-triangulated."""
+    import struct
+    verts = [(-1.0, -1.0, 0.0, 0.0, 0.0), (1.0, -1.0, 0.0, 1.0, 0.0), (1.0, 1.0, 0.0, 1.0, 1.0), (-1.0, 1.0, 0.0, 0.0, 1.0),
+             (0.0, 2.0, 0.5, 0.5, 0.5)]
+    faces = [(0, 1, 2, 3), (3, 2, 4)]
+    header = ("ply\nformat {fmt} 1.0\ncomment made by a test\nelement vertex 5\nproperty float x\nproperty float y\n"
+              "property float z\nproperty float s\nproperty float t\nelement face 2\n"
+              "property list uchar int vertex_indices\nend_header\n")
+    want = np.array([[verts[a][:3], verts[b][:3], verts[c][:3]] for a, b, c in ((0, 1, 2), (0, 2, 3), (3, 2, 4))])
+    for fmt, e in (("binary_little_endian", "<"), ("binary_big_endian", ">")):
+        path = tmp_path / f"{fmt}.ply"
+        with open(path, "wb") as f:
+            f.write(header.format(fmt=fmt).encode())
+            for v in verts:
+                f.write(struct.pack(e + "5f", *v))
+            for fc in faces:
+                f.write(struct.pack(e + "B" + f"{len(fc)}i", len(fc), *fc))
+        np.testing.assert_allclose(mitr.load_ply(str(path)), want)
+    path = tmp_path / "ascii.ply"
+    with open(path, "w") as f:
+        f.write(header.format(fmt="ascii"))
+        for v in verts:
+            f.write(" ".join(str(x) for x in v) + "\n")
+        for fc in faces:
+            f.write(f"{len(fc)} " + " ".join(str(i) for i in fc) + "\n")
+    np.testing.assert_allclose(mitr.load_ply(str(path)), want)
+    scene = mitr.load_dict({"type": "scene", "m": {"type": "ply", "filename": str(path), "bsdf": {"type": "diffuse"}}})
+    shape = scene.shapes()[0]
+    assert len(shape.prims) == 2 and sorted(shape.prim_types.tolist()) == [0, 1]     # the quad was merged, the triangle kept
