@@ -138,6 +138,8 @@ class TransientHDRFilm:
     # ---- develop (transient_hdr_film.py:210-248)
     def develop(self, raw: bool = False):
         steady, transient = self.steady_storage, self.develop_transient_(raw=raw)
+        if self.exhaustive_scan:               # the reference's quirk: steady = mean over the CHANNEL axis (:213-214)
+            steady = transient.mean(dim=-1)
         if _variant.is_monochromatic():        # "L" instead of "RGB" (transient_hdr_film.py:174, hdrfilm luminance)
             steady = steady[..., :1]
             if not raw:

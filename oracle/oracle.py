@@ -42,6 +42,9 @@ def load() -> C.CDLL:
                                       C.POINTER(C.c_uint64)]
         lib.oracle_film_scatter_add.restype = C.c_int
         lib.oracle_film_scatter_add.argtypes = [C.c_void_p, C.POINTER(_abi.TrFilmDesc), C.c_int, C.c_void_p, C.c_uint64]
+        lib.oracle_film_scatter_add_laser.restype = C.c_int
+        lib.oracle_film_scatter_add_laser.argtypes = [C.c_void_p, C.POINTER(_abi.TrFilmDesc), C.c_int, C.c_void_p, C.c_void_p,
+                                                      C.c_uint64]
         lib.oracle_film_develop.restype = C.c_int
         lib.oracle_film_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
         lib.oracle_pcg32.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
@@ -112,6 +115,14 @@ def film_scatter_add(film: np.ndarray, film_desc: _abi.TrFilmDesc, deposits: np.
     dep = np.ascontiguousarray(deposits, dtype=np.float32)
     _check(load().oracle_film_scatter_add(film.ctypes.data, C.byref(film_desc), film.shape[-1], dep.ctypes.data,
                                           dep.shape[0]))
+
+
+def film_scatter_add_laser(film: np.ndarray, film_desc: _abi.TrFilmDesc, deposits: np.ndarray, laser_xy: np.ndarray):
+    assert film.dtype == np.float32 and film.flags.c_contiguous
+    dep = np.ascontiguousarray(deposits, dtype=np.float32)
+    lxy = np.ascontiguousarray(laser_xy, dtype=np.uint32)
+    _check(load().oracle_film_scatter_add_laser(film.ctypes.data, C.byref(film_desc), film.shape[-1], dep.ctypes.data,
+                                                lxy.ctypes.data, dep.shape[0]))
 
 
 def film_develop(raw: np.ndarray) -> np.ndarray:

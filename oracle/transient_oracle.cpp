@@ -6,13 +6,19 @@
 //  only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 //  may load it.  Nothing under mitransient_b200/ links, imports or calls it.
 //
-//  PARITY STATUS: *unpinned*.  The reference's arithmetic for this path lives in two
-//  third-party, un-vendored dependencies -- mitsuba (pinned >=3.6.0,<3.9.0,
-//  mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the notebooks) -- which are
-//  not installable here (no wheel, no network), and the reference's only test is stale and
-//  shape-only (tests/integration/test_nlos.py:81-118).  So there are no golden vectors to pin
-//  against; the oracle restates the published Mitsuba 3 algorithms and is validated by the
-//  analytic known-answer tests in tests/test_oracle_kat.py.
+//  PARITY STATUS: *partially pinned*.
+//   - PINNED against the reference's own code, executed: the film half of the path -- add_transient_data,
+//     TransientImageBlock.put_/accum (plain and exhaustive_scan index), develop_transient_, the phasor film
+//     (frequency selection, PhasorImageBlock.put, develop_phasors_) -- plus the benchmark scene dictionary, the
+//     integrators' parameter parsing and pass split.  tests/golden/make_reference_golden.py runs the UNMODIFIED
+//     Python of /root/reference/mitransient over a NumPy stand-in for drjit/mitsuba (tests/golden/refshim.py) and
+//     commits the outputs; tests/test_reference_golden.py requires this oracle to match them (the time-histogram
+//     films bit for bit).
+//   - UNPINNED: the ray-tracing half.  Its arithmetic lives in two third-party, un-vendored dependencies --
+//     mitsuba (pinned >=3.6.0,<3.9.0, mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the
+//     notebooks) -- which are not installable here (no wheel, no network), and the reference's only test is stale
+//     and shape-only (tests/integration/test_nlos.py:81-118).  For that half the oracle restates the published
+//     Mitsuba 3 algorithms and is validated by the analytic known-answer tests in tests/test_oracle_kat.py.
 //
 //  What is restated (file:line relative to the mitransient tree):
 //    render driver        mitransient/integrators/common.py:122-213   -> oracle_render
@@ -1457,6 +1463,18 @@ int oracle_film_scatter_add(float *film, const TrFilmDesc *fd, int channels, con
     Film f{*fd, film, channels, &cnt, nullptr};
     for (uint64_t i = 0; i < n; ++i)
         f.add_transient(dep[i].x, dep[i].y, v3(dep[i].r, dep[i].g, dep[i].b), dep[i].opl, 1.0f, 1.0f);
+    return TR_OK;
+}
+
+// Same with the illuminated-point coordinates of an exhaustive_scan film (transient_image_block.py:134-140);
+// laser_xy: uint32[n][2].
+int oracle_film_scatter_add_laser(float *film, const TrFilmDesc *fd, int channels, const TrDeposit *dep, const uint32_t *laser_xy,
+                                  uint64_t n) {
+    if (!film || !fd || !dep || !laser_xy) { g_err = "null argument"; return TR_ERR_INVALID_ARGUMENT; }
+    TrCounters cnt{};
+    Film f{*fd, film, channels, &cnt, nullptr};
+    for (uint64_t i = 0; i < n; ++i)
+        f.add_transient(dep[i].x, dep[i].y, v3(dep[i].r, dep[i].g, dep[i].b), dep[i].opl, 1.0f, 1.0f, laser_xy[2 * i], laser_xy[2 * i + 1]);
     return TR_OK;
 }
 

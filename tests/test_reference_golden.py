@@ -1,0 +1,148 @@
+"""Pins against the REFERENCE'S OWN CODE: tests/golden/reference_host_golden.* were produced by executing the
+unmodified host-side Python of /root/reference/mitransient (film, image blocks, phasor film, scene dictionary,
+integrator parameters, pass split, tonemapping) over the NumPy stand-in tests/golden/refshim.py
+(tests/golden/make_reference_golden.py).  The oracle, the host mirror and -- on the GPU -- the film kernels must
+reproduce them.  Deposits go in sequentially on both sides, so the film tensors match BIT FOR BIT on the CPU."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "reference_host_golden.npz"))
+META = json.load(open(os.path.join(HERE, "golden", "reference_host_golden.json")))
+
+
+def _film_desc(mitr, props, frequencies=None):
+    fd = mitr._abi.TrFilmDesc()
+    fd.width, fd.height, fd.temporal_bins = props["width"], props["height"], props["temporal_bins"]
+    fd.start_opl, fd.bin_width_opl = props["start_opl"], props["bin_width_opl"]
+    if props.get("exhaustive_scan"):
+        fd.laser_scan_width, fd.laser_scan_height = props["laser_scan_width"], props["laser_scan_height"]
+    if frequencies is not None:
+        fd.type, fd.n_frequencies = mitr._abi.TR_FILM_PHASOR_HDR, len(frequencies)
+        fd.frequencies = frequencies.ctypes.data_as(C.POINTER(C.c_float))
+    return fd
+
+
+@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c"])
+def test_oracle_film_equals_reference_film_bit_for_bit(mitr, oracle, tag):
+    """add_transient_data + TransientImageBlock.put_ + accum + develop_transient_ (transient_hdr_film.py:250-276,
+    220-248; transient_image_block.py:83-151): window edges, inf / nan distances, zero deposits, W channel."""
+    props = META[tag]
+    film = np.zeros(G[tag + "_raw"].shape, dtype=np.float32)
+    oracle.film_scatter_add(film, _film_desc(mitr, props), G[tag + "_deposits"])
+    assert np.array_equal(film, G[tag + "_raw"])
+    assert np.all(film[..., 3] == 0)
+    assert np.array_equal(oracle.film_develop(film), G[tag + "_developed"])
+
+
+def test_oracle_exhaustive_index_equals_reference(mitr, oracle):
+    """exhaustive_scan with a NON-square laser grid: the flat index of transient_image_block.py:134-140 exactly as
+    written (laser_scan_width multiplies before laser_x, laser_scan_height before laser_y) inside the
+    (H, W, Lh, Lw, T, C) tensor of :63-66."""
+    props = META["film_exh"]
+    film = np.zeros(G["film_exh_raw"].shape, dtype=np.float32)
+    assert film.shape == (props["height"], props["width"], props["laser_scan_height"], props["laser_scan_width"],
+                          props["temporal_bins"], 4)
+    oracle.film_scatter_add_laser(film, _film_desc(mitr, props), G["film_exh_deposits"], G["film_exh_laser"])
+    assert np.array_equal(film, G["film_exh_raw"])
+
+
+@pytest.mark.parametrize("tag", ["phasor_a", "phasor_b", "phasor_c"])
+def test_phasor_film_equals_reference(mitr, oracle, tag):
+    """PhasorHDRFilm frequency selection (phasor_hdr_film.py:125-137) bit for bit; PhasorImageBlock.put
+    (phasor_image_block.py:43-67) within the accuracy of the cos / sin implementations (NumPy there, Cephes
+    polynomial here; the phase itself is computed with the reference's fp32 fmod formula)."""
+    props = META["phasor"][tag]
+    want_f = G[tag + "_frequencies"]
+    film_plugin = mitr.load_dict({"type": "phasor_hdr_film", **{k: v for k, v in props.items() if k not in ("channels", "n_channels")}})
+    assert np.array_equal(film_plugin.frequencies, want_f)
+    assert film_plugin.raw_channels() == props["n_channels"] == 2 * len(want_f) + 1
+    assert film_plugin.channels[:2] + film_plugin.channels[-1:] == props["channels"]
+    film = np.zeros(G[tag + "_raw"].shape, dtype=np.float32)
+    oracle.film_scatter_add(film, _film_desc(mitr, props, np.ascontiguousarray(want_f)), G[tag + "_deposits"])
+    ref = G[tag + "_raw"]
+    scale = np.abs(G[tag + "_deposits"][:, 3]).sum() / film[..., 0].size
+    assert np.abs(film - ref).max() <= 2e-5 * max(scale, 1.0), np.abs(film - ref).max()
+    assert np.all(film[..., -1] == 0)
+    dev = oracle.film_develop(film).reshape(ref.shape[:-1] + (len(want_f), 2))
+    assert np.abs(dev - G[tag + "_developed"]).max() <= 2e-5 * max(scale, 1.0)
+
+
+def _same(a, b, path=""):
+    if isinstance(b, dict) and "__transform__" in b:
+        np.testing.assert_allclose(np.asarray(a.matrix, dtype=np.float64), np.array(b["__transform__"]), atol=1e-12, err_msg=path)
+    elif isinstance(b, dict) and "__array__" in b:
+        np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.array(b["__array__"]), atol=0, err_msg=path)
+    elif isinstance(b, dict):
+        assert isinstance(a, dict) and set(a) == set(b), (path, sorted(a), sorted(b))
+        for k in b:
+            _same(a[k], b[k], path + "/" + k)
+    elif isinstance(b, list):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, f"{path}[{i}]")
+    else:
+        assert a == b, (path, a, b)
+
+
+def test_cornell_box_dictionary_equals_reference(mitr):
+    """mitr.cornell_box() == mitransient.utils.cornell_box() (utils.py:78-220): every key, value, colour and
+    transform matrix of the benchmark scene."""
+    _same(mitr.cornell_box(), META["cornell_box"])
+    assert mitr.speed_of_light == META["speed_of_light"]
+
+
+def test_nlos_integrator_parameters_equal_reference(mitr):
+    """TransientNLOSPath.__init__ (transientnlospath.py:201-249) + TransientADIntegrator.__init__ (common.py:22-30)."""
+    for case in META["nlos_params"]:
+        it = mitr.load_dict({"type": "transient_nlos_path", **case["props"]})
+        for k, v in case["attrs"].items():
+            got = getattr(it, k)
+            assert (int(got) if not isinstance(v, float) else float(got)) == v, (case["props"], k, got, v)
+    with pytest.raises(AssertionError) as e:
+        mitr.load_dict({"type": "transient_nlos_path", "filter_depth": 2, "filter_bounces": 1})
+    assert str(e.value) == META["nlos_both_filters_error"]
+    it = mitr.load_dict({"type": "transient_path", "max_depth": 8, "camera_unwarp": True, "gaussian_stddev": 2.0,
+                         "temporal_filter": "box"})
+    for k, v in META["path_params"].items():
+        assert getattr(it, k) == v
+
+
+def test_pass_split_equals_reference(mitr, monkeypatch):
+    """TransientADIntegrator.prepare (common.py:32-85): one pass up to 2^32 samples, else int((2^26-1)/(W*H)) spp
+    per pass plus a remainder pass."""
+    from mitransient_b200.films.transient_hdr_film import TransientHDRFilm
+    monkeypatch.setattr(TransientHDRFilm, "prepare", lambda self, aovs=(): 4)        # no device allocation here
+    for case in META["prepare_split"]:
+        d = mitr.cornell_box_config(case["width"], case["height"], 2, case["film_spp"])
+        scene = mitr.load_dict(d)
+        passes = scene.integrator().prepare(scene, scene.sensors()[0], 0, case["spp"])
+        assert [s for _, s in passes] == case["passes"], case
+
+
+def test_tonemap_equals_reference(mitr):
+    np.testing.assert_allclose(mitr.vis.tonemap_transient(G["tonemap_in"], scaling=2.0), G["tonemap_out"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ GPU kernels
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c"])
+def test_gpu_film_kernels_equal_reference(mitr, tag):
+    """tr_film_scatter_add + tr_film_develop through the host mirror's add_transient_data / develop against the
+    reference film (only the order of the fp32 additions differs)."""
+    import torch
+    props = META[tag]
+    film = mitr.load_dict({"type": "transient_hdr_film", **props})
+    film.prepare()
+    dep = torch.from_numpy(G[tag + "_deposits"]).cuda()
+    film.add_transient_data(dep[:, 0:2], dep[:, 2], None, dep[:, 3:6])
+    raw = film.develop(raw=True)[1].cpu().numpy()
+    ref = G[tag + "_raw"]
+    assert np.array_equal(raw != 0, ref != 0)
+    assert np.abs(raw - ref).sum() <= 1e-6 * np.abs(ref).sum()
+    dev = film.develop()[1].cpu().numpy()
+    assert np.abs(dev - G[tag + "_developed"]).sum() <= 1e-6 * np.abs(ref).sum()
