@@ -519,6 +519,23 @@ inline V3 area_sample_direction(const Scene &sc, const TrEmitterDesc &em, V3 ref
     return v3(em.radiance[0], em.radiance[1], em.radiance[2]) * inv;
 }
 
+// Scene::sample_emitter_direction without the visibility test [upstream scene.cpp]: uniform emitter choice with
+// sample reuse, Emitter::sample_direction, pdf scaled by the pick probability, weight by its inverse.
+inline V3 scene_sample_emitter_direction(const Scene &sc, V3 ref_p, float u0, float u1, DirectionSample *ds, uint32_t *em_index) {
+    const uint32_t n_em = (uint32_t) sc.emitters.size();
+    uint32_t ei = 0; float emw = 1.0f, pdf_pick = 1.0f;
+    if (n_em > 1) {
+        float fi = u0 * (float) n_em;
+        ei = (uint32_t) fi; if (ei > n_em - 1) ei = n_em - 1;
+        u0 = fi - (float) ei; emw = (float) n_em; pdf_pick = 1.0f / (float) n_em;
+    }
+    const TrEmitterDesc &em = sc.emitters[ei];
+    V3 em_weight = area_sample_direction(sc, em, ref_p, u0, u1, ds);
+    ds->pdf *= pdf_pick; em_weight = em_weight * emw;
+    *em_index = ei;
+    return em_weight;
+}
+
 // Scene::pdf_emitter_direction for an area emitter hit by BSDF sampling.
 inline float area_pdf_direction(const Scene &sc, const TrEmitterDesc &em, V3 d, V3 n_light, float dist) {
     float dp = dot(d, n_light);
@@ -629,6 +646,61 @@ inline void fresnel_dielectric(float cos_theta_i, float eta, float *r_out, float
     *eta_it_out = eta_it; *eta_ti_out = eta_ti;
 }
 
+// ---- BSDFs in the local shading frame (wi = si.to_local(-ray.d)), as Mitsuba's plugins state them [upstream] -------
+struct BsdfSampleRec { V3 wo, weight; float pdf, eta; bool delta; };
+inline bool bsdf_is_smooth(const TrBsdfDesc &b) { return b.type == TR_BSDF_DIFFUSE; }
+// bsdf.eval_pdf: diffuse (optionally two-sided): R/pi * cos_o, pdf cos_o/pi, iff both cosines are positive; 0 for delta lobes
+inline V3 bsdf_eval_pdf(const TrBsdfDesc &b, V3 wi, V3 wo, float *pdf) {
+    *pdf = 0.0f;
+    if (b.type != TR_BSDF_DIFFUSE) return v3(0, 0, 0);
+    float cos_i = wi.z, cos_o = wo.z;
+    if ((b.flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f) { cos_i = -cos_i; cos_o = -cos_o; }
+    if (!(cos_i > 0.0f && cos_o > 0.0f)) return v3(0, 0, 0);
+    *pdf = kInvPi * cos_o;
+    return (v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * kInvPi) * cos_o;
+}
+// bsdf.sample(ctx, si, sample1, sample2): diffuse.cpp, conductor.cpp, dielectric.cpp (+ twosided.cpp)
+inline BsdfSampleRec bsdf_sample(const TrBsdfDesc &b, V3 wi, float s1, float s2x, float s2y) {
+    BsdfSampleRec r; r.wo = v3(0, 0, 0); r.weight = v3(0, 0, 0); r.pdf = 0.0f; r.eta = 1.0f; r.delta = false;
+    const bool twosided = (b.flags & TR_BSDF_FLAG_TWOSIDED) != 0;
+    if (b.type == TR_BSDF_DIFFUSE) {
+        const bool flip = twosided && wi.z < 0.0f;
+        const float cos_i_eff = flip ? -wi.z : wi.z;
+        V3 wo = square_to_cosine_hemisphere(s2x, s2y);
+        r.pdf = kInvPi * wo.z;
+        if (cos_i_eff > 0.0f && r.pdf > 0.0f) r.weight = v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+        if (flip) wo.z = -wo.z;
+        r.wo = wo;
+    } else if (b.type == TR_BSDF_CONDUCTOR) {                  // SmoothConductor::sample (+ TwoSided::sample)
+        const bool flip = twosided && wi.z < 0.0f;
+        if (flip) wi.z = -wi.z;
+        V3 wo = v3(-wi.x, -wi.y, wi.z);                        // reflect(wi)
+        r.pdf = 1.0f; r.delta = true;
+        if (wi.z > 0.0f)
+            r.weight = v3(b.reflectance[0] * fresnel_conductor(wi.z, b.eta[0], b.k[0]),
+                          b.reflectance[1] * fresnel_conductor(wi.z, b.eta[1], b.k[1]),
+                          b.reflectance[2] * fresnel_conductor(wi.z, b.eta[2], b.k[2]));
+        if (flip) wo.z = -wo.z;
+        r.wo = wo;
+    } else if (b.type == TR_BSDF_DIELECTRIC) {                 // SmoothDielectric::sample
+        float r_i, cos_theta_t, eta_it, eta_ti;
+        fresnel_dielectric(wi.z, b.eta[0], &r_i, &cos_theta_t, &eta_it, &eta_ti);
+        const float t_i = 1.0f - r_i;
+        const bool selected_r = s1 <= r_i;
+        r.pdf = selected_r ? r_i : t_i; r.delta = true;
+        if (selected_r) {
+            r.wo = v3(-wi.x, -wi.y, wi.z);
+            r.weight = v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+        } else {
+            r.wo = v3(-eta_ti * wi.x, -eta_ti * wi.y, cos_theta_t);            // refract(wi, cos_theta_t, eta_ti)
+            r.eta = eta_it;
+            const float f2 = eta_ti * eta_ti;                  // radiance transport: scale by eta_ti^2
+            r.weight = v3(b.specular_transmittance[0] * f2, b.specular_transmittance[1] * f2, b.specular_transmittance[2] * f2);
+        }
+    }
+    return r;
+}
+
 // mitransient/integrators/transientpath.py:109-326 (primal branch).  Returns L.
 V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
                         float px, float py, float sample_scale, float ray_weight, Film &film) {
@@ -693,17 +765,8 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
         float cos_i_eff = (twosided && back) ? -cos_i : cos_i;
         float ds_dist = 0.0f;
         if (active_em && n_em > 0) {
-            // Scene::sample_emitter_direction: uniform emitter choice with sample reuse
-            uint32_t ei = 0; float emw = 1.0f, pdf_pick = 1.0f;
-            if (n_em > 1) {
-                float fi = u0 * (float) n_em;
-                ei = (uint32_t) fi; if (ei > n_em - 1) ei = n_em - 1;
-                u0 = fi - (float) ei; emw = (float) n_em; pdf_pick = 1.0f / (float) n_em;
-            }
-            const TrEmitterDesc &em = sc.emitters[ei];
-            DirectionSample ds;
-            V3 em_weight = area_sample_direction(sc, em, si.p, u0, u1, &ds);
-            ds.pdf *= pdf_pick; em_weight = em_weight * emw;
+            DirectionSample ds; uint32_t ei;
+            V3 em_weight = scene_sample_emitter_direction(sc, si.p, u0, u1, &ds, &ei);
             ds_dist = ds.dist;
             bool nz = (em_weight.x != 0.0f || em_weight.y != 0.0f || em_weight.z != 0.0f);
             if (ds.pdf != 0.0f && nz) {
@@ -714,9 +777,8 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
                     film.cnt->shadow_rays++;
                     bool occluded = ray_test(sc, spawn_ray_to(si.p, si.n, ds.p));
                     if (!occluded) {
-                        V3 R = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
-                        V3 bsdf_val = (R * kInvPi) * cos_o_eff;
-                        float bsdf_pdf = kInvPi * cos_o_eff;
+                        float bsdf_pdf;       // only the z components of wi / wo matter to a diffuse lobe
+                        V3 bsdf_val = bsdf_eval_pdf(*bsdf, v3(0.0f, 0.0f, cos_i), v3(0.0f, 0.0f, cos_o), &bsdf_pdf);
                         float mis_em = ds.delta ? 1.0f : mis_weight(ds.pdf, bsdf_pdf);  // :212-213
                         Lr_dir = ((beta * mis_em) * bsdf_val) * em_weight;              // :214
                     }
@@ -730,47 +792,12 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
         float s2x = rng.next_1d(), s2y = rng.next_1d();            // sampler.next_2d()
         V3 bsdf_weight = v3(0, 0, 0); float bs_pdf = 0.0f; V3 wo_world = v3(0, 0, 0);
         float bs_eta = 1.0f; bool bs_delta = false;
-        if (active_next && (bsdf->type == TR_BSDF_CONDUCTOR || bsdf->type == TR_BSDF_DIELECTRIC)) {
-            // si.wi = si.to_local(-ray.d); the samplers below work in the local frame like conductor.cpp / dielectric.cpp
+        if (active_next && bsdf->type != TR_BSDF_NULL) {
+            // si.wi = si.to_local(-ray.d); the plugins sample in the local frame (diffuse.cpp / conductor.cpp / dielectric.cpp)
             V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));
-            V3 wo;
-            if (bsdf->type == TR_BSDF_CONDUCTOR) {                 // SmoothConductor::sample (+ TwoSided::sample)
-                bool flip = twosided && wi.z < 0.0f;
-                if (flip) wi.z = -wi.z;
-                wo = v3(-wi.x, -wi.y, wi.z);                       // reflect(wi)
-                bs_pdf = 1.0f;
-                if (wi.z > 0.0f)
-                    bsdf_weight = v3(bsdf->reflectance[0] * fresnel_conductor(wi.z, bsdf->eta[0], bsdf->k[0]),
-                                     bsdf->reflectance[1] * fresnel_conductor(wi.z, bsdf->eta[1], bsdf->k[1]),
-                                     bsdf->reflectance[2] * fresnel_conductor(wi.z, bsdf->eta[2], bsdf->k[2]));
-                if (flip) wo.z = -wo.z;
-            } else {                                               // SmoothDielectric::sample
-                float r_i, cos_theta_t, eta_it, eta_ti;
-                fresnel_dielectric(wi.z, bsdf->eta[0], &r_i, &cos_theta_t, &eta_it, &eta_ti);
-                float t_i = 1.0f - r_i;
-                bool selected_r = s1 <= r_i;
-                bs_pdf = selected_r ? r_i : t_i;
-                if (selected_r) {
-                    wo = v3(-wi.x, -wi.y, wi.z);
-                    bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
-                } else {
-                    wo = v3(-eta_ti * wi.x, -eta_ti * wi.y, cos_theta_t);      // refract(wi, cos_theta_t, eta_ti)
-                    bs_eta = eta_it;
-                    float f2 = eta_ti * eta_ti;                    // radiance transport: scale by eta_ti^2
-                    bsdf_weight = v3(bsdf->specular_transmittance[0] * f2, bsdf->specular_transmittance[1] * f2,
-                                     bsdf->specular_transmittance[2] * f2);
-                }
-            }
-            bs_delta = true;
-            wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));       // si.to_world(wo)
-        }
-        if (active_next && smooth) {
-            V3 wo = square_to_cosine_hemisphere(s2x, s2y);
-            bs_pdf = kInvPi * wo.z;
-            if (cos_i_eff > 0.0f && bs_pdf > 0.0f)
-                bsdf_weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
-            if (twosided && back) wo.z = -wo.z;
-            wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));   // si.to_world(wo)
+            BsdfSampleRec bs = bsdf_sample(*bsdf, wi, s1, s2x, s2y);
+            bsdf_weight = bs.weight; bs_pdf = bs.pdf; bs_eta = bs.eta; bs_delta = bs.delta;
+            wo_world = fma3(si.n, bs.wo.z, fma3(si.tt, bs.wo.y, si.s * bs.wo.x));      // si.to_world(wo)
         }
 
         // ---------------- update loop variables :231-241
@@ -1529,6 +1556,136 @@ int oracle_ray_intersect(const TrSceneDesc *desc, const float *o, const float *d
     *out_t = h.t; out_p[0] = h.p.x; out_p[1] = h.p.y; out_p[2] = h.p.z;
     out_n[0] = h.n.x; out_n[1] = h.n.y; out_n[2] = h.n.z; *out_shape = h.shape; *out_prim = h.prim;
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scene services ("osv_*"): the Mitsuba-level primitives the path loops above are built from -- scene.ray_intersect /
+// ray_test, si.spawn_ray(_to) / to_local / to_world, Scene::sample_emitter_direction / pdf_emitter_direction,
+// Emitter::eval, BSDF::flags / eval_pdf / sample, the perspective sensor -- exported lane-wise so that the
+// REFERENCE'S OWN integrator code (transientpath.py ...) can be executed over them (tests/golden/refshim.py).  Each
+// entry calls exactly the function the trace loops call, so both walk bit-identical arithmetic.
+struct OsvScene { Scene sc; };
+
+void *osv_open(const TrSceneDesc *desc) {
+    OsvScene *h = new OsvScene(); std::string err;
+    if (!build_scene(desc, h->sc, err)) { g_err = err; delete h; return nullptr; }
+    return h;
+}
+void osv_close(void *h) { delete (OsvScene *) h; }
+
+inline V3 ld3(const float *a, uint64_t i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+inline void st3(float *a, uint64_t i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+
+void osv_camera_rays(void *h, uint64_t n, const uint32_t *px, const uint32_t *py, const float *jitter, float *o, float *d, float *maxt) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r = sample_camera_ray(sc, px[i], py[i], jitter[2 * i], jitter[2 * i + 1]);
+        st3(o, i, r.o); st3(d, i, r.d); maxt[i] = r.maxt;
+    }
+}
+// scene.ray_intersect: valid, t (inf on a miss), p, n, shading frame (s, tt), shape index, wi = to_local(-d)
+void osv_ray_intersect(void *h, uint64_t n, const float *o, const float *d, const float *maxt, uint8_t *valid, float *t, float *p,
+                       float *nrm, float *s, float *tt, int32_t *shape, float *wi) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 rd = ld3(d, i);
+        Hit hit = ray_intersect(sc, Ray{ld3(o, i), rd, maxt[i]});
+        valid[i] = hit.valid; t[i] = hit.t; shape[i] = hit.valid ? (int32_t) hit.shape : -1;
+        st3(p, i, hit.valid ? hit.p : v3(0, 0, 0)); st3(nrm, i, hit.valid ? hit.n : v3(0, 0, 0));
+        st3(s, i, hit.valid ? hit.s : v3(0, 0, 0)); st3(tt, i, hit.valid ? hit.tt : v3(0, 0, 0));
+        st3(wi, i, hit.valid ? v3(-dot(rd, hit.s), -dot(rd, hit.tt), -dot(rd, hit.n)) : v3(0, 0, 0));
+    }
+}
+void osv_ray_test(void *h, uint64_t n, const float *o, const float *d, const float *maxt, uint8_t *hit) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) hit[i] = ray_test(sc, Ray{ld3(o, i), ld3(d, i), maxt[i]});
+}
+void osv_spawn_ray(void *, uint64_t n, const float *p, const float *nrm, const float *dir, float *o, float *maxt) {
+    for (uint64_t i = 0; i < n; ++i) { Ray r = spawn_ray(ld3(p, i), ld3(nrm, i), ld3(dir, i)); st3(o, i, r.o); maxt[i] = r.maxt; }
+}
+void osv_spawn_ray_to(void *, uint64_t n, const float *p, const float *nrm, const float *target, float *o, float *d, float *maxt) {
+    for (uint64_t i = 0; i < n; ++i) { Ray r = spawn_ray_to(ld3(p, i), ld3(nrm, i), ld3(target, i)); st3(o, i, r.o); st3(d, i, r.d); maxt[i] = r.maxt; }
+}
+void osv_to_world(void *, uint64_t n, const float *s, const float *tt, const float *nrm, const float *v, float *out) {
+    for (uint64_t i = 0; i < n; ++i) { V3 w = ld3(v, i); st3(out, i, fma3(ld3(nrm, i), w.z, fma3(ld3(tt, i), w.y, ld3(s, i) * w.x))); }
+}
+void osv_to_local(void *, uint64_t n, const float *s, const float *tt, const float *nrm, const float *v, float *out) {
+    for (uint64_t i = 0; i < n; ++i) { V3 w = ld3(v, i); st3(out, i, v3(dot(w, ld3(s, i)), dot(w, ld3(tt, i)), dot(w, ld3(nrm, i)))); }
+}
+// DirectionSample3f(scene, si, ref): d = normalize(si.p - ref.p), dist
+void osv_direction_to(void *, uint64_t n, const float *p, const float *ref, float *d, float *dist) {
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 rel = ld3(p, i) - ld3(ref, i);
+        float l = sqrtf(dot(rel, rel));
+        st3(d, i, rel * (1.0f / l)); dist[i] = l;
+    }
+}
+// scene.sample_emitter_direction(ref, sample, test_visibility, active) -> ds (p, n, d, dist, pdf), weight
+void osv_sample_emitter_direction(void *h, uint64_t n, const float *ref_p, const float *ref_n, const float *u, int test_visibility,
+                                  const uint8_t *active, float *ds_p, float *ds_n, float *ds_d, float *ds_dist, float *ds_pdf,
+                                  float *weight) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        DirectionSample ds; ds.p = ds.n = ds.d = v3(0, 0, 0); ds.dist = ds.pdf = 0.0f; ds.delta = false;
+        V3 w = v3(0, 0, 0);
+        if (active[i] && !sc.emitters.empty()) {
+            uint32_t ei;
+            w = scene_sample_emitter_direction(sc, ld3(ref_p, i), u[2 * i], u[2 * i + 1], &ds, &ei);
+            bool nz = w.x != 0.0f || w.y != 0.0f || w.z != 0.0f;
+            if (test_visibility && nz && ray_test(sc, spawn_ray_to(ld3(ref_p, i), ld3(ref_n, i), ds.p))) w = v3(0, 0, 0);
+        }
+        st3(ds_p, i, ds.p); st3(ds_n, i, ds.n); st3(ds_d, i, ds.d); ds_dist[i] = ds.dist; ds_pdf[i] = ds.pdf; st3(weight, i, w);
+    }
+}
+// scene.pdf_emitter_direction(ref, ds, active) for the emitter attached to `shape` (the shape that was hit)
+void osv_pdf_emitter_direction(void *h, uint64_t n, const int32_t *shape, const float *ds_d, const float *ds_n, const float *ds_dist,
+                               const uint8_t *active, float *pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    const uint32_t n_em = (uint32_t) sc.emitters.size();
+    for (uint64_t i = 0; i < n; ++i) {
+        pdf[i] = 0.0f;
+        if (!active[i] || shape[i] < 0 || sc.shapes[shape[i]].d.emitter < 0) continue;
+        float v = area_pdf_direction(sc, sc.emitters[sc.shapes[shape[i]].d.emitter], ld3(ds_d, i), ld3(ds_n, i), ds_dist[i]);
+        if (n_em > 1) v *= 1.0f / (float) n_em;
+        pdf[i] = v;
+    }
+}
+// si.emitter(scene).eval(si, active): area light radiance on the front side (cos_theta(si.wi) > 0)
+void osv_emitter_eval(void *h, uint64_t n, const int32_t *shape, const float *wi, const uint8_t *active, float *rgb) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 r = v3(0, 0, 0);
+        if (active[i] && shape[i] >= 0 && sc.shapes[shape[i]].d.emitter >= 0 && wi[3 * i + 2] > 0.0f) {
+            const TrEmitterDesc &em = sc.emitters[sc.shapes[shape[i]].d.emitter];
+            r = v3(em.radiance[0], em.radiance[1], em.radiance[2]);
+        }
+        st3(rgb, i, r);
+    }
+}
+void osv_bsdf_smooth(void *h, uint64_t n, const int32_t *shape, uint8_t *smooth, uint8_t *is_null) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        const TrBsdfDesc *b = shape[i] >= 0 ? &sc.bsdfs[sc.shapes[shape[i]].d.bsdf] : nullptr;
+        smooth[i] = b && bsdf_is_smooth(*b); is_null[i] = b && b->type == TR_BSDF_NULL;
+    }
+}
+void osv_bsdf_eval_pdf(void *h, uint64_t n, const int32_t *shape, const float *wi, const float *wo, const uint8_t *active, float *value,
+                       float *pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 v = v3(0, 0, 0); pdf[i] = 0.0f;
+        if (active[i] && shape[i] >= 0) v = bsdf_eval_pdf(sc.bsdfs[sc.shapes[shape[i]].d.bsdf], ld3(wi, i), ld3(wo, i), &pdf[i]);
+        st3(value, i, v);
+    }
+}
+void osv_bsdf_sample(void *h, uint64_t n, const int32_t *shape, const float *wi, const float *s1, const float *s2, const uint8_t *active,
+                     float *wo, float *pdf, float *eta, uint8_t *delta, float *weight) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        BsdfSampleRec r; r.wo = r.weight = v3(0, 0, 0); r.pdf = 0.0f; r.eta = 1.0f; r.delta = false;
+        if (active[i] && shape[i] >= 0) r = bsdf_sample(sc.bsdfs[sc.shapes[shape[i]].d.bsdf], ld3(wi, i), s1[i], s2[2 * i], s2[2 * i + 1]);
+        st3(wo, i, r.wo); st3(weight, i, r.weight); pdf[i] = r.pdf; eta[i] = r.eta; delta[i] = r.delta;
+    }
 }
 
 }  // extern "C"

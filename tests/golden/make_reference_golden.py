@@ -174,6 +174,22 @@ vis = refshim.ref_module("mitransient.unpolarized_visualization")
 x = (np.random.default_rng(5).standard_normal((6, 5, 7, 3)) ** 3).astype(np.float32)
 out["tonemap_in"], out["tonemap_out"] = x, vis.tonemap_transient(x, scaling=2.0).astype(np.float32)
 
+# ------------------------------------------------------------------ H: the integrator loop itself
+# The reference's render() (integrators/common.py:122-213) and TransientPath.sample() (transientpath.py:88-326),
+# UNMODIFIED, executed lane-wise over refshim's scene services (whose Mitsuba primitives are the oracle's osv_*
+# exports).  Stored: every non-zero deposit (x, y, opl, r, g, b), sorted; the raw film; the steady image.
+from path_cases import PATH_CASES, path_case_scene, sort_rows  # noqa: E402
+
+if __name__ == "__main__":
+    path_out = {}
+    for name in PATH_CASES:
+        scene, cfg, props = path_case_scene(name)
+        steady, raw, dep = refshim.reference_render(scene, "mitransient.integrators.transientpath", "TransientPath", props,
+                                                    spp=cfg[3], seed=3)
+        path_out[name + "_deposits"], path_out[name + "_raw"], path_out[name + "_steady"] = sort_rows(dep), raw, steady.astype(np.float32)
+        print(name, cfg, props, "deposits:", len(dep))
+    np.savez_compressed(os.path.join(HERE, "reference_path_golden.npz"), **path_out)
+
 np.savez_compressed(os.path.join(HERE, "reference_host_golden.npz"), **out)
 with open(os.path.join(HERE, "reference_host_golden.json"), "w") as f:
     json.dump(meta, f, indent=1, sort_keys=True)

@@ -343,3 +343,419 @@ def ref_module(dotted: str):
     """Import a module of the reference (e.g. 'mitransient.films.transient_hdr_film') from where it lies."""
     import importlib
     return importlib.import_module(dotted)
+
+
+# ==========================================================================================================
+#  Part 2 -- scene services: enough of mi.Scene / SurfaceInteraction3f / BSDF / Emitter / Sampler / Ray3f for
+#  the reference's INTEGRATOR code (integrators/common.py render(), transientpath.py sample()) to run lane-wise.
+#  The Mitsuba primitives behind these objects (ray casting, emitter / BSDF sampling, sensor rays) are the CPU
+#  oracle's own functions, called through its osv_* exports -- so executing the reference integrator over this
+#  module checks OUR READING OF MITRANSIENT'S LOOP (draw order, masks, MIS, roulette, depth and OPL bookkeeping,
+#  deposit conditions) against the reference code itself; the primitives stay the oracle's (unpinned) restatement
+#  of published Mitsuba algorithms.
+# ==========================================================================================================
+import ctypes as C
+
+LANES = None          # wavefront width while an integrator runs (set by ShimADIntegrator.sample_rays)
+
+
+class DrArray(np.ndarray):
+    """A Dr.Jit-flavoured ndarray: x[mask] is a full-width masked view (so `x[mask] += 1`, `x[mask] = y` work lane-wise)
+    and float & mask selects (dr.rcp(p) & (p > 0))."""
+    def __new__(cls, a):
+        return np.asarray(a).view(cls)
+
+    @staticmethod
+    def _is_mask(k):
+        return isinstance(k, np.ndarray) and k.dtype == bool
+
+    def __getitem__(self, k):
+        if DrArray._is_mask(k):
+            return np.array(self).view(DrArray)
+        return np.ndarray.__getitem__(self, k)
+
+    def __setitem__(self, k, v):
+        if DrArray._is_mask(k):
+            np.copyto(self, np.asarray(v, dtype=self.dtype), where=np.asarray(k))
+        else:
+            np.ndarray.__setitem__(self, k, v)
+
+    def __and__(self, o):
+        if self.dtype.kind == "f":
+            return np.where(np.asarray(o, dtype=bool), np.asarray(self), np.zeros((), self.dtype)).view(DrArray)
+        return np.ndarray.__and__(self, o)
+
+
+def _lanes(v, dtype):
+    a = np.array(v, dtype=dtype, copy=True)
+    if LANES is not None and a.ndim == 0:
+        a = np.full(LANES, a, dtype=dtype)
+    return a.view(DrArray)
+
+
+def LFloat(v=0.0): return _lanes(v, np.float32)
+def LUInt(v=0): return _lanes(v, np.int64)
+def LBool(v=True): return _lanes(v, bool)
+
+
+class LVec(Vec):
+    """Vec with lane-wide components and Dr.Jit masked assignment."""
+    caster = staticmethod(lambda c: _lanes(c, np.float32))
+
+    def __getitem__(self, k):
+        if DrArray._is_mask(k):
+            out = type(self).__new__(type(self)); out.c = tuple(np.array(x).view(DrArray) for x in self.c); return out
+        return self.c[k]
+
+    def __setitem__(self, k, v):
+        vc = v.c if isinstance(v, Vec) else (v,) * len(self.c)
+        self.c = tuple(np.where(np.asarray(k), np.asarray(b, dtype=np.float32), np.asarray(a)).view(DrArray)
+                       for a, b in zip(self.c, vc))
+
+    def __neg__(self):
+        out = type(self).__new__(type(self)); out.c = tuple((-x).view(DrArray) for x in self.c); return out
+
+    def _zip(self, o, f):
+        oc = o.c if isinstance(o, Vec) else (o,) * len(self.c)
+        out = type(self).__new__(type(self))
+        out.c = tuple(np.asarray(f(a, b)).view(DrArray) for a, b in zip(self.c, oc))
+        return out
+
+    def arr(self):                                         # (n, dim) float32, contiguous: what the osv_* calls take
+        return np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(x, dtype=np.float32), (LANES,)) for x in self.c], axis=1))
+
+    @classmethod
+    def from_arr(cls, a):
+        out = cls.__new__(cls); out.c = tuple(np.ascontiguousarray(a[:, k]).view(DrArray) for k in range(a.shape[1])); return out
+
+
+class LVec2(LVec):
+    dim = 2
+
+
+class Osv:
+    """ctypes face of the oracle's scene services (oracle/transient_oracle.cpp, osv_*)."""
+    def __init__(self, desc):
+        from oracle import oracle
+        self.lib = oracle.load()
+        self.lib.osv_open.restype = C.c_void_p
+        self.lib.osv_open.argtypes = [C.c_void_p]
+        self.h = self.lib.osv_open(C.byref(desc))
+        if not self.h:
+            raise RuntimeError("osv_open failed: " + self.lib.oracle_last_error().decode())
+        self._desc = desc
+
+    def call(self, name, *args):
+        fn = getattr(self.lib, name)
+        fn.restype = None
+        conv = [C.c_void_p(self.h), C.c_uint64(LANES)]
+        for a in args:
+            conv.append(C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_int(int(a)))
+        fn(*conv)
+
+
+def _f(n, k=None): return np.zeros((n,) if k is None else (n, k), dtype=np.float32)
+def _mask(m): return np.ascontiguousarray(np.broadcast_to(np.asarray(m, dtype=bool), (LANES,))).astype(np.uint8)
+def _flt(a): return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), (LANES,)))
+
+
+class Ray3f:
+    def __init__(self, o=None, d=None, maxt=None):
+        if isinstance(o, Ray3f):
+            o, d, maxt = o.o, o.d, o.maxt
+        self.o, self.d, self.maxt = o, d, maxt
+        self.time, self.wavelengths = LFloat(0.0), None
+
+
+class BSDFPtr:
+    Smooth, Delta = 0x1, 0x2                       # stand-ins for the BSDFFlags unions the integrators test
+
+    def __init__(self, osv, shape): self.osv, self.shape = osv, shape
+
+    def flags(self):
+        sm, nl = np.zeros(LANES, np.uint8), np.zeros(LANES, np.uint8)
+        self.osv.call("osv_bsdf_smooth", self.shape, sm, nl)
+        return np.where(sm != 0, BSDFPtr.Smooth, BSDFPtr.Delta).astype(np.int64).view(DrArray)
+
+    def eval_pdf(self, ctx, si, wo, active=True):
+        val, pdf = _f(LANES, 3), _f(LANES)
+        self.osv.call("osv_bsdf_eval_pdf", self.shape, si.wi.arr(), wo.arr(), _mask(active), val, pdf)
+        return LVec.from_arr(val), pdf.view(DrArray)
+
+    def sample(self, ctx, si, sample1, sample2, active=True):
+        wo, pdf, eta, delta, w = _f(LANES, 3), _f(LANES), _f(LANES), np.zeros(LANES, np.uint8), _f(LANES, 3)
+        self.osv.call("osv_bsdf_sample", self.shape, si.wi.arr(), _flt(sample1), sample2.arr(), _mask(active), wo, pdf, eta, delta, w)
+        bs = types.SimpleNamespace(wo=LVec.from_arr(wo), pdf=pdf.view(DrArray), eta=eta.view(DrArray),
+                                   sampled_type=np.where(delta != 0, BSDFPtr.Delta, BSDFPtr.Smooth).astype(np.int64).view(DrArray))
+        return bs, LVec.from_arr(w)
+
+
+class EmitterPtr:
+    def __init__(self, osv, shape): self.osv, self.shape = osv, shape
+
+    def eval(self, si, active=True):
+        rgb = _f(LANES, 3)
+        self.osv.call("osv_emitter_eval", self.shape, si.wi.arr(), _mask(active), rgb)
+        return LVec.from_arr(rgb)
+
+
+class SurfaceInteraction3f:
+    wavelengths = None
+
+    def is_valid(self): return self.valid
+    def bsdf(self, ray=None): return BSDFPtr(self.osv, self.shape)
+    def emitter(self, scene=None): return EmitterPtr(self.osv, self.shape)
+
+    def spawn_ray(self, d):
+        o, maxt = _f(LANES, 3), _f(LANES)
+        self.osv.call("osv_spawn_ray", self.p.arr(), self.n.arr(), d.arr(), o, maxt)
+        return Ray3f(LVec.from_arr(o), d, maxt.view(DrArray))
+
+    def to_world(self, v):
+        out = _f(LANES, 3); self.osv.call("osv_to_world", self.s.arr(), self.tt.arr(), self.n.arr(), v.arr(), out); return LVec.from_arr(out)
+
+    def to_local(self, v):
+        out = _f(LANES, 3); self.osv.call("osv_to_local", self.s.arr(), self.tt.arr(), self.n.arr(), v.arr(), out); return LVec.from_arr(out)
+
+    def to_world_mueller(self, m, a, b): return m       # unpolarized: identity
+
+
+def _zero_si(osv):
+    si = SurfaceInteraction3f(); si.osv = osv
+    si.valid, si.t, si.shape = LBool(False), LFloat(np.inf), np.full(LANES, -1, np.int32)
+    si.p = si.n = si.s = si.tt = si.wi = LVec(0.0)
+    return si
+
+
+class DirectionSample3f:
+    def __init__(self, scene=None, si=None, ref=None):
+        if scene is None:
+            return
+        d, dist = _f(LANES, 3), _f(LANES)
+        scene.osv.call("osv_direction_to", si.p.arr(), ref.p.arr(), d, dist)
+        self.p, self.n, self.d, self.dist = si.p, si.n, LVec.from_arr(d), dist.view(DrArray)
+        self.pdf, self.delta, self.emitter = LFloat(0.0), LBool(False), si.emitter(scene)
+        self._shape = si.shape
+
+
+class ShimScene:
+    """mi.Scene over the oracle's scene services."""
+    def __init__(self, our_scene, sensor):
+        self.our_scene, self.our_sensor = our_scene, sensor
+        self.osv = Osv(our_scene.describe(sensor))
+
+    def ray_intersect(self, ray, ray_flags=None, coherent=None, active=True):
+        n = LANES
+        valid, t, p, nr, s, tt, shape, wi = np.zeros(n, np.uint8), _f(n), _f(n, 3), _f(n, 3), _f(n, 3), _f(n, 3), np.zeros(n, np.int32), _f(n, 3)
+        self.osv.call("osv_ray_intersect", ray.o.arr(), ray.d.arr(), _flt(ray.maxt), valid, t, p, nr, s, tt, shape, wi)
+        si = SurfaceInteraction3f(); si.osv = self.osv
+        si.valid, si.t, si.shape = (valid != 0).view(DrArray), t.view(DrArray), shape
+        si.p, si.n, si.s, si.tt, si.wi = (LVec.from_arr(x) for x in (p, nr, s, tt, wi))
+        return si
+
+    def sample_emitter_direction(self, ref, sample, test_visibility=True, active=True):
+        n = LANES
+        dp, dn, dd, dist, pdf, w = _f(n, 3), _f(n, 3), _f(n, 3), _f(n), _f(n), _f(n, 3)
+        self.osv.call("osv_sample_emitter_direction", ref.p.arr(), ref.n.arr(), sample.arr(), 1 if test_visibility else 0, _mask(active),
+                      dp, dn, dd, dist, pdf, w)
+        ds = DirectionSample3f()
+        ds.p, ds.n, ds.d = LVec.from_arr(dp), LVec.from_arr(dn), LVec.from_arr(dd)
+        ds.dist, ds.pdf, ds.delta, ds.emitter = dist.view(DrArray), pdf.view(DrArray), LBool(False), None
+        return ds, LVec.from_arr(w)
+
+    def pdf_emitter_direction(self, ref, ds, active=True):
+        pdf = _f(LANES)
+        self.osv.call("osv_pdf_emitter_direction", ds._shape, ds.d.arr(), ds.n.arr(), _flt(ds.dist), _mask(active), pdf)
+        return pdf.view(DrArray)
+
+
+class ShimSampler:
+    """Mitsuba's `independent` sampler [upstream]: one PCG32 stream per lane, seeded through TEA from (seed, lane)."""
+    MULT = np.uint64(0x5851F42D4C957F2D)
+
+    def __init__(self, spp=4, base_seed=0): self.spp, self.base_seed = spp, base_seed
+    def clone(self): return ShimSampler(self.spp, self.base_seed)
+    def set_sample_count(self, n): self.spp = int(n)
+    def sample_count(self): return self.spp
+    def set_samples_per_wavefront(self, n): pass
+    def wavefront_size(self): return len(self.state)
+
+    def seed(self, seed, wavefront_size):
+        idx = np.arange(int(wavefront_size), dtype=np.uint64)
+        v0 = np.full(idx.shape, (int(seed) + self.base_seed) & 0xFFFFFFFF, dtype=np.uint64); v1 = idx.copy()
+        s, M = np.uint64(0), np.uint64(0xFFFFFFFF)
+        for _ in range(4):                                   # sample_tea_32
+            s = (s + np.uint64(0x9E3779B9)) & M
+            v0 = (v0 + ((((v1 << np.uint64(4)) & M) + np.uint64(0xA341316C)) ^ ((v1 + s) & M) ^ ((v1 >> np.uint64(5)) + np.uint64(0xC8013EA4)))) & M
+            v1 = (v1 + ((((v0 << np.uint64(4)) & M) + np.uint64(0xAD90777D)) ^ ((v0 + s) & M) ^ ((v0 >> np.uint64(5)) + np.uint64(0x7E95761E)))) & M
+        with np.errstate(over="ignore"):
+            self.inc = (v1 << np.uint64(1)) | np.uint64(1)
+            self.state = np.zeros_like(idx)
+            self.state = self.state * self.MULT + self.inc
+            self.state = self.state + v0
+            self.state = self.state * self.MULT + self.inc
+
+    def next_1d(self, active=True):
+        old = self.state
+        with np.errstate(over="ignore"):
+            new = old * self.MULT + self.inc
+        self.state = np.where(np.broadcast_to(np.asarray(active, dtype=bool), old.shape), new, old)
+        xorshifted = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)) & np.uint64(0xFFFFFFFF)
+        rot = (old >> np.uint64(59)).astype(np.uint64)
+        out = ((xorshifted >> rot) | (xorshifted << ((np.uint64(32) - rot) & np.uint64(31)))) & np.uint64(0xFFFFFFFF)
+        bits = ((out >> np.uint64(9)) | np.uint64(0x3F800000)).astype(np.uint32)
+        return (bits.view(np.float32) - np.float32(1.0)).view(DrArray)
+
+    def next_2d(self, active=True):
+        x = self.next_1d(active); y = self.next_1d(active)
+        out = LVec2.__new__(LVec2); out.c = (x, y); return out
+
+
+class ShimSteadyBlock:
+    def __init__(self, film): self.film = film; self.data = np.zeros((film.h, film.w, 4), dtype=np.float32)
+    def coalesce(self): return False
+    def set_coalesce(self, v): pass
+
+
+class ShimSteadyFilm:
+    """hdrfilm + ImageBlock (box): put accumulates [R, G, B, weight] at floor(pos); develop = colour / weight."""
+    def __init__(self, w, h): self.w, self.h, self.acc = w, h, np.zeros((h, w, 4), dtype=np.float32)
+    def prepare(self, aovs): self.acc[...] = 0; return 3
+    def clear(self): self.acc[...] = 0
+    def base_channels_count(self): return 3
+    def create_block(self): return ShimSteadyBlock(self)
+    def put_block(self, block): self.acc += block.data
+
+    def develop(self, raw=False):
+        w = self.acc[..., 3:4]
+        return self.acc[..., :3] / np.where(w == 0, 1, w)
+
+
+class ShimSensor:
+    def __init__(self, film, spp): self._film, self._sampler = film, ShimSampler(spp)
+    def film(self): return self._film
+    def sampler(self): return self._sampler
+
+
+class ShimADIntegrator(ADIntegrator):
+    """mitsuba.ad.integrators.common.ADIntegrator [upstream]: __init__ (max_depth, rr_depth, hide_emitters),
+    sample_rays (one lane per sample: idx // spp = pixel, pos + next_2d jitter, sensor.sample_ray_differential) and
+    _splat_to_block (box filter: accumulate value and weight at the pixel)."""
+    def __init__(self, props=Properties()):
+        super().__init__(props)
+        self.hide_emitters = props.get("hide_emitters", False)
+
+    def aov_names(self): return []
+
+    def sample_rays(self, scene, sensor, sampler, reparam=None):
+        global LANES
+        w, h = int(sensor.film().size().x), int(sensor.film().size().y)
+        spp = sampler.sample_count()
+        LANES = w * h * spp
+        idx = np.arange(LANES, dtype=np.int64) // spp
+        py, px = idx // w, idx % w
+        jitter = sampler.next_2d()
+        o, d, maxt = _f(LANES, 3), _f(LANES, 3), _f(LANES)
+        scene.osv.call("osv_camera_rays", px.astype(np.uint32), py.astype(np.uint32), jitter.arr(), o, d, maxt)
+        ray = Ray3f(LVec.from_arr(o), LVec.from_arr(d), maxt.view(DrArray))
+        pos = LVec2.__new__(LVec2); pos.c = (px.astype(np.float32).view(DrArray), py.astype(np.float32).view(DrArray))
+        return ray, LVec(1.0), pos
+
+    @staticmethod
+    def _splat_to_block(block, film, pos, value, weight, alpha, aovs, wavelengths):
+        x, y = np.asarray(pos.x).astype(np.int64), np.asarray(pos.y).astype(np.int64)
+        for k, v in enumerate((value.x, value.y, value.z, np.full(LANES, weight, dtype=np.float32))):
+            np.add.at(block.data[..., k], (y, x), np.asarray(v, dtype=np.float32))
+
+
+def install_scene_services(monochromatic=False, transform_cls=None, color_fn=None):
+    """install() + the lane-wise array types and scene objects of part 2."""
+    mi, dr = install(monochromatic, transform_cls, color_fn)
+    mi.Float, mi.UInt32, mi.UInt, mi.Int32, mi.Bool, mi.Mask = LFloat, LUInt, LUInt, LUInt, LBool, LBool
+    LFloat.__module__ = "drjit.llvm.ad"
+    for n in ("Point3f", "Vector3f", "Normal3f", "Color3f", "Spectrum", "UnpolarizedSpectrum"):
+        setattr(mi, n, LVec)
+    for n in ("Point2f", "Vector2f"):
+        setattr(mi, n, LVec2)
+    mi.Ray3f, mi.SurfaceInteraction3f, mi.DirectionSample3f = Ray3f, SurfaceInteraction3f, DirectionSample3f
+    mi.BSDFContext = lambda *a, **k: None
+    mi.RayFlags = types.SimpleNamespace(All=0)
+    mi.BSDFFlags = types.SimpleNamespace(Smooth=BSDFPtr.Smooth, Delta=BSDFPtr.Delta)
+    mi.has_flag = lambda flags, f: ((np.asarray(flags) & int(f)) != 0).view(DrArray) if isinstance(flags, np.ndarray) else bool(int(flags) & int(f))
+    mi.Sampler = ShimSampler
+    common = sys.modules["mitsuba.ad.integrators.common"]
+    common.ADIntegrator = ShimADIntegrator
+
+    def mis_weight(a, b):
+        a2, b2 = np.asarray(a, dtype=np.float32) ** 2, np.asarray(b, dtype=np.float32) ** 2
+        with np.errstate(invalid="ignore", divide="ignore"):
+            w = a2 / (a2 + b2)
+        return np.where(np.isfinite(w), w, np.float32(0)).view(DrArray)
+    common.mis_weight = mis_weight
+
+    def select(m, a, b):
+        if isinstance(a, Vec) or isinstance(b, Vec):
+            ref = a if isinstance(a, Vec) else b
+            ac = a.c if isinstance(a, Vec) else (a,) * len(ref.c)
+            bc = b.c if isinstance(b, Vec) else (b,) * len(ref.c)
+            out = type(ref).__new__(type(ref))
+            out.c = tuple(np.where(m, np.asarray(x, dtype=np.float32), np.asarray(y, dtype=np.float32)).view(DrArray) for x, y in zip(ac, bc))
+            return out
+        return np.where(m, np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)).view(DrArray)
+    dr.select = select
+    dr.max = lambda v: np.maximum(np.maximum(v.x, v.y), v.z).view(DrArray) if isinstance(v, Vec) else np.max(v)
+    dr.minimum = lambda a, b: np.minimum(a, np.float32(b) if np.isscalar(b) else b).view(DrArray)
+    dr.maximum = lambda a, b: np.maximum(a, np.float32(b) if np.isscalar(b) else b).view(DrArray)
+    dr.rcp = lambda x: (np.float32(1.0) / np.asarray(x, dtype=np.float32)).view(DrArray)
+    dr.detach = lambda x, *a: x
+    dr.copy = lambda x: x
+    dr.zeros = lambda t, n=1: _zero_si(_CURRENT["osv"]) if t is SurfaceInteraction3f else np.zeros(int(n), dtype=np.float32)
+    dr.hint = lambda v, **kw: bool(np.any(v)) if isinstance(v, np.ndarray) else v
+
+    class _Ctx:
+        def __init__(self, *a, **k): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    dr.resume_grad = dr.suspend_grad = _Ctx
+    return mi, dr
+
+
+_CURRENT = {"osv": None}
+
+
+def reference_render(our_scene, integrator_module, integrator_cls, props, spp, seed=0, monochromatic=False):
+    """Run the REFERENCE'S render() (integrators/common.py:122-213) + sample() for `our_scene` (a mitransient_b200
+    Scene) and return (steady (H,W,3), transient raw tensor, deposits (N,6) in the order the reference produced them)."""
+    import mitransient_b200 as mitr
+    global LANES
+    LANES = None
+    mi, dr = install_scene_services(monochromatic, mitr.ScalarTransform4f, mitr.ScalarColor3d)
+    thf = ref_module("mitransient.films.transient_hdr_film")
+    mod = ref_module(integrator_module)
+    sensor = our_scene.sensors()[0]
+    f = sensor.film()
+    film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
+                                              start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
+    log = []
+    inner = film.add_transient_data
+
+    def logged(pos, distance, wavelengths, spec, ray_weight, active, **kw):
+        a = np.broadcast_to(np.asarray(active, dtype=bool), (LANES,))
+        val = spec * ray_weight
+        rec = np.stack([np.asarray(pos.x), np.asarray(pos.y), np.asarray(distance), np.asarray(val.x), np.asarray(val.y),
+                        np.asarray(val.z)], axis=1).astype(np.float32)
+        nz = a & ((rec[:, 3] != 0) | (rec[:, 4] != 0) | (rec[:, 5] != 0))
+        log.append(rec[nz])
+        return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
+    film.add_transient_data = logged
+    _real_load = mi.load_dict
+    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    scene = ShimScene(our_scene, sensor)
+    _CURRENT["osv"] = scene.osv
+    shim_sensor = ShimSensor(film, spp)
+    shim_sensor._sampler.base_seed = sensor.sampler().base_seed
+    scene.sensors = lambda: [shim_sensor]
+    integ = getattr(mod, integrator_cls)(mi.Properties(**props))
+    steady, transient = integ.render(scene, shim_sensor, seed=seed, spp=spp)
+    LANES = None
+    return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)

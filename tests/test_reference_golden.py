@@ -146,3 +146,62 @@ def test_gpu_film_kernels_equal_reference(mitr, tag):
     assert np.abs(raw - ref).sum() <= 1e-6 * np.abs(ref).sum()
     dev = film.develop()[1].cpu().numpy()
     assert np.abs(dev - G[tag + "_developed"]).sum() <= 1e-6 * np.abs(ref).sum()
+
+
+# ------------------------------------------------------------------------------------------ the integrator loop
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from path_cases import PATH_CASES, path_case_scene, sort_rows  # noqa: E402
+
+GP = np.load(os.path.join(HERE, "golden", "reference_path_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(PATH_CASES))
+def test_oracle_deposits_equal_the_reference_integrator(mitr, oracle, name):
+    """The reference's render() (common.py:122-213) and TransientPath.sample() (transientpath.py:88-326) were EXECUTED
+    over the oracle's scene services; every deposit (pixel, optical path length, RGB value) the oracle produces on
+    its own must be one of theirs, bit for bit -- draw order, masks, MIS, roulette, depth / eta / OPL bookkeeping."""
+    scene, cfg, _ = path_case_scene(name)
+    r = oracle.render(scene, scene.integrator(), spp=cfg[3], seed=3, log_deposits=1 << 20)
+    assert np.array_equal(sort_rows(r["deposits"]), GP[name + "_deposits"])
+    # hdrfilm divides the sum by the weight (= spp); the oracle multiplies by 1/spp: one ulp apart when spp is not 2^k
+    np.testing.assert_allclose(r["steady"], GP[name + "_steady"], rtol=3e-7, atol=0)
+    ref = GP[name + "_raw"]                                   # same deposits, different summation order
+    assert np.abs(r["transient"] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mitransient"), reason="the reference tree is not available here")
+def test_reference_integrator_runs_live(mitr, oracle):
+    """Re-execute the reference integrator here (build container only) on a configuration that is NOT in the golden
+    file and compare with the oracle."""
+    import warnings
+    import refshim
+    d = mitr.cornell_box_config(7, 5, 40, 6, max_depth=7)
+    d["integrator"]["rr_depth"] = 3
+    d["large-box"]["bsdf"] = {"type": "conductor"}
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steady, raw, dep = refshim.reference_render(scene, "mitransient.integrators.transientpath", "TransientPath", props,
+                                                    spp=6, seed=11)
+    r = oracle.render(scene, scene.integrator(), spp=6, seed=11, log_deposits=1 << 20)
+    assert len(dep) > 100 and np.array_equal(sort_rows(dep), sort_rows(r["deposits"]))
+    np.testing.assert_allclose(steady.astype(np.float32), r["steady"], rtol=3e-7, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(PATH_CASES))
+def test_gpu_render_equals_the_reference_integrator(mitr, name):
+    """The CUDA path against the film / steady image the reference integrator produced (same deposits, other order)."""
+    scene, cfg, _ = path_case_scene(name)
+    integ = scene.integrator()
+    integ.collect_counters = True
+    steady, _ = integ.render(scene, spp=cfg[3], seed=3)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = GP[name + "_raw"]
+    assert integ.last_counters["deposits"] == len(GP[name + "_deposits"])
+    assert np.array_equal(raw != 0, ref != 0)
+    assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
+    np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)
