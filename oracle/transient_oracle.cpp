@@ -848,7 +848,7 @@ inline Ray nlos_sensor_ray(const Scene &sc, float sx, float sy) {
     V3 origin = v3(sc.sensor.origin[0], sc.sensor.origin[1], sc.sensor.origin[2]);
     V3 dir = target - origin;                                                                  // :155-157
     float dist = sqrtf(dot(dir, dir));
-    dir = dir * (1.0f / dist);
+    dir = v3(dir.x / dist, dir.y / dist, dir.z / dist);                                        // direction /= distance (Python-level: true division)
     return Ray{origin, dir, std::numeric_limits<float>::max()};
 }
 
@@ -945,7 +945,8 @@ V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const Nlos
     if (focus_laser && (rp.capture_type == TR_CAPTURE_CONFOCAL || rp.capture_type == TR_CAPTURE_EXHAUSTIVE)) {   // :448-458
         V3 rel = ctx.em_origin - vx.p;
         float dte = sqrtf(dot(rel, rel));
-        query = fma3(ctx.em_forward, dte, ctx.em_origin);
+        query = v3(ctx.em_origin.x + ctx.em_forward.x * dte, ctx.em_origin.y + ctx.em_forward.y * dte,
+                   ctx.em_origin.z + ctx.em_forward.z * dte);
     }
     rng.next_1d(); rng.next_1d();                                                             // sampler.next_2d(active_e)
     V3 dsp; float ds_dist;
@@ -967,7 +968,7 @@ V3 nlos_emitter_laser_targets_sample(const Scene &sc, const TrRenderParams &rp, 
     V3 d = target - vx.p;                                                                     // :526
     float dl = sqrtf(dot(d, d));
     if (!(dl > 0.0f)) return v3(0, 0, 0);     // confocal depth-0 vertex: target == si.p, NaN direction in the reference (:526-528, :545)
-    d = d * (1.0f / dl);
+    d = v3(d.x / dl, d.y / dl, d.z / dl);                                                     // :528  d /= distance_laser
     Ray ray_bsdf = spawn_ray_to(vx.p, vx.n, target);                                          // :529
     film.cnt->shadow_rays++;
     if (ray_test(sc, ray_bsdf)) return v3(0, 0, 0);                                           // :530
@@ -1053,7 +1054,7 @@ V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx
             ppdf *= pmf;                                                                      // :428
             V3 d = pp - si.p;
             float dist = sqrtf(dot(d, d));
-            d = d * (1.0f / dist);
+            d = v3(d.x / dist, d.y / dist, d.z / dist);                                       // :646  d /= dist
             float cos_ti = dot(si.n, d), cos_g = -dot(pn, d);                                 // :648-649
             bool act = (cos_ti > kEps) && (cos_g > kEps);
             wo = v3(dot(d, si.s), dot(d, si.tt), dot(d, si.n));                               // si.to_local(d)
@@ -1685,6 +1686,52 @@ void osv_bsdf_sample(void *h, uint64_t n, const int32_t *shape, const float *wi,
         BsdfSampleRec r; r.wo = r.weight = v3(0, 0, 0); r.pdf = 0.0f; r.eta = 1.0f; r.delta = false;
         if (active[i] && shape[i] >= 0) r = bsdf_sample(sc.bsdfs[sc.shapes[shape[i]].d.bsdf], ld3(wi, i), s1[i], s2[2 * i], s2[2 * i + 1]);
         st3(wo, i, r.wo); st3(weight, i, r.weight); pdf[i] = r.pdf; eta[i] = r.eta; delta[i] = r.delta;
+    }
+}
+
+// ---- services used by transient_nlos_path (transientnlospath.py) and nlos_capture_meter (nloscapturemeter.py)
+// emitter.sample_direction(it, sample, active) for the projector: ds.p, ds.d, ds.dist, ds.pdf (= 1 when active), weight
+void osv_projector_sample_direction(void *h, uint64_t n, const float *it_p, const uint8_t *active, float *ds_p, float *ds_d, float *ds_dist,
+                                    float *ds_pdf, float *weight) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    const TrEmitterDesc &em = sc.emitters[0];
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 p = v3(0, 0, 0), w = v3(0, 0, 0); float dist = 0.0f;
+        V3 itp = ld3(it_p, i);
+        if (active[i]) w = projector_sample_direction(em, itp, &p, &dist);
+        V3 d = p - itp; float l = sqrtf(dot(d, d));
+        st3(ds_p, i, p); st3(ds_d, i, active[i] ? d * (1.0f / l) : v3(0, 0, 0)); ds_dist[i] = dist; st3(weight, i, w);
+        ds_pdf[i] = active[i] ? 1.0f : 0.0f;                         // projector.cpp: ds.pdf = 1 (delta position)
+    }
+}
+// shape.sample_position(time, sample, active) for the shape index of every lane -> p, n, pdf
+void osv_shape_sample_position(void *h, uint64_t n, const int32_t *shape, const float *u, const uint8_t *active, float *p, float *nrm, float *pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 pp = v3(0, 0, 0), pn = v3(0, 0, 0); float ppdf = 0.0f;
+        if (active[i] && shape[i] >= 0) shape_sample_position(sc, sc.shapes[shape[i]], u[2 * i], u[2 * i + 1], &pp, &pn, &ppdf);
+        st3(p, i, pp); st3(nrm, i, pn); pdf[i] = ppdf;
+    }
+}
+void osv_dot(void *, uint64_t n, const float *a, const float *b, float *out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = dot(ld3(a, i), ld3(b, i));
+}
+uint32_t osv_n_shapes(void *h) { return (uint32_t) ((OsvScene *) h)->sc.shapes.size(); }
+float osv_shape_area(void *h, uint32_t shape) { return ((OsvScene *) h)->sc.shapes[shape].area; }
+int32_t osv_sensor_shape(void *h) { const Scene &sc = ((OsvScene *) h)->sc; return sc.sensor.type == TR_SENSOR_NLOS_CAPTURE_METER ? sc.sensor.shape : -1; }
+// DiscreteDistribution(pmf).sample_reuse_pmf(u) with the oracle's arithmetic (nlos_prepare + trace_nlos_path)
+void osv_discrete_sample_reuse_pmf(void *, uint64_t n, const float *pmf_in, uint32_t n_entries, const float *u, int32_t *index, float *u_new,
+                                   float *pmf_out) {
+    std::vector<float> cdf(n_entries); double acc = 0.0;
+    for (uint32_t k = 0; k < n_entries; ++k) { acc += (double) pmf_in[k]; cdf[k] = (float) acc; }
+    const float sum = (float) acc, norm = (float) (1.0 / acc);
+    for (uint64_t i = 0; i < n; ++i) {
+        float value = u[i] * sum;
+        uint32_t lo = 0, hi = n_entries - 1;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cdf[mid] < value) lo = mid + 1; else hi = mid; }
+        float cdf_prev = lo ? cdf[lo - 1] : 0.0f;
+        float pmf = pmf_in[lo] * norm;
+        index[i] = (int32_t) lo; pmf_out[i] = pmf; u_new[i] = (u[i] - cdf_prev * norm) / pmf;
     }
 }
 

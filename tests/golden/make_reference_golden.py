@@ -178,7 +178,7 @@ out["tonemap_in"], out["tonemap_out"] = x, vis.tonemap_transient(x, scaling=2.0)
 # The reference's render() (integrators/common.py:122-213) and TransientPath.sample() (transientpath.py:88-326),
 # UNMODIFIED, executed lane-wise over refshim's scene services (whose Mitsuba primitives are the oracle's osv_*
 # exports).  Stored: every non-zero deposit (x, y, opl, r, g, b), sorted; the raw film; the steady image.
-from path_cases import PATH_CASES, path_case_scene, sort_rows  # noqa: E402
+from path_cases import NLOS_CASES, PATH_CASES, nlos_case_scene, path_case_scene, sort_rows  # noqa: E402
 
 if __name__ == "__main__":
     path_out = {}
@@ -188,6 +188,14 @@ if __name__ == "__main__":
                                                     spp=cfg[3], seed=3)
         path_out[name + "_deposits"], path_out[name + "_raw"], path_out[name + "_steady"] = sort_rows(dep), raw, steady.astype(np.float32)
         print(name, cfg, props, "deposits:", len(dep))
+    # ---- I: transient_nlos_path: render() + TransientNLOSPath.prepare / sample / emitter_laser_sample /
+    # emitter_laser_targets_sample / emitter_nee_sample / hidden_geometry_sample (transientnlospath.py:251-927) and the
+    # NLOSCaptureMeter sensor (nloscapturemeter.py:136-202), all executed unmodified.
+    for name in NLOS_CASES:
+        scene, cfg, props = nlos_case_scene(name)
+        steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=cfg[3], seed=5)
+        path_out[name + "_deposits"], path_out[name + "_raw"] = sort_rows(dep), raw
+        print(name, cfg, props.get("capture_type"), "deposits:", len(dep))
     np.savez_compressed(os.path.join(HERE, "reference_path_golden.npz"), **path_out)
 
 np.savez_compressed(os.path.join(HERE, "reference_host_golden.npz"), **out)

@@ -31,3 +31,35 @@ def sort_rows(a):
     return a[np.lexsort(a.T[::-1])]
 
 
+
+
+# ---- transient_nlos_path + nlos_capture_meter: (film (w, h, bins, spp), nlos_z_scene keyword arguments, laser focus pixel,
+#      projector fov override, exhaustive_scan film)
+NLOS_CASES = {
+    "nlos_a": ((6, 6, 64, 8), {}, None, None, False),
+    "nlos_b": ((5, 5, 64, 8), {"nlos_hidden_geometry_sampling_do_rroulette": True}, None, None, False),
+    "nlos_c": ((5, 5, 64, 8), {"nlos_hidden_geometry_sampling": False, "account_first_and_last_bounces": True, "start_opl": 0.0,
+                               "window": 8.0}, None, None, False),
+    "nlos_d": ((5, 5, 64, 8), {"filter_depth": 3, "start_opl": 0.0, "window": 8.0}, None, None, False),
+    "nlos_e": ((5, 5, 64, 8), {"discard_direct_paths": True, "nlos_hidden_geometry_sampling_includes_relay_wall": True, "max_depth": 7,
+                               "rr_depth": 2, "start_opl": 0.0, "window": 8.0}, None, None, False),
+    "nlos_f": ((6, 6, 64, 16), {"capture_type": "single", "start_opl": 0.0, "window": 8.0}, (3, 2), None, False),
+    "nlos_g": ((6, 6, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, (3, 3), 60.0, False),
+    "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
+    "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
+}
+
+
+def nlos_case_scene(name):
+    cfg, kw, focus, fov, exhaustive = NLOS_CASES[name]
+    d = mitr.nlos_z_scene(*cfg, **kw)
+    if fov is not None:
+        d["emitter"]["fov"] = fov
+    if exhaustive:
+        f = d["relay_wall"]["nlos_sensor"]["transient_film"]
+        f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, cfg[0], cfg[1]
+    scene = mitr.load_dict(d)
+    if focus is not None:
+        wall = [v for v in d.values() if isinstance(v, dict) and v.get("type") == "rectangle"][0]
+        mitr.nlos.focus_emitter_at_relay_wall_pixel(focus, mitr.PluginSpec(wall), scene.emitters()[0]["spec"])
+    return scene, cfg, {k: v for k, v in d["integrator"].items() if k != "type"}

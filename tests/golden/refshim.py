@@ -400,7 +400,9 @@ def LBool(v=True): return _lanes(v, bool)
 
 class LVec(Vec):
     """Vec with lane-wide components and Dr.Jit masked assignment."""
-    caster = staticmethod(lambda c: _lanes(c, np.float32))
+    caster = staticmethod(lambda c: np.array(c, dtype=np.float32, copy=True).view(DrArray))
+
+    x = property(lambda s: s.c[0], lambda s, v: setattr(s, "c", (np.asarray(v, dtype=np.float32).view(DrArray),) + s.c[1:]))
 
     def __getitem__(self, k):
         if DrArray._is_mask(k):
@@ -421,8 +423,8 @@ class LVec(Vec):
         out.c = tuple(np.asarray(f(a, b)).view(DrArray) for a, b in zip(self.c, oc))
         return out
 
-    def arr(self):                                         # (n, dim) float32, contiguous: what the osv_* calls take
-        return np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(x, dtype=np.float32), (LANES,)) for x in self.c], axis=1))
+    def arr(self, n=None):                                 # (n, dim) float32, contiguous: what the osv_* calls take
+        return np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(x, dtype=np.float32), (n or LANES,)) for x in self.c], axis=1))
 
     @classmethod
     def from_arr(cls, a):
@@ -440,35 +442,68 @@ class Osv:
         self.lib = oracle.load()
         self.lib.osv_open.restype = C.c_void_p
         self.lib.osv_open.argtypes = [C.c_void_p]
+        self.lib.osv_shape_area.restype = C.c_float
+        self.lib.osv_n_shapes.restype = C.c_uint32
+        self.lib.osv_sensor_shape.restype = C.c_int32
         self.h = self.lib.osv_open(C.byref(desc))
         if not self.h:
             raise RuntimeError("osv_open failed: " + self.lib.oracle_last_error().decode())
         self._desc = desc
 
-    def call(self, name, *args):
+    def call(self, name, *args, n=None):
         fn = getattr(self.lib, name)
         fn.restype = None
-        conv = [C.c_void_p(self.h), C.c_uint64(LANES)]
+        conv = [C.c_void_p(self.h), C.c_uint64(LANES if n is None else n)]
         for a in args:
             conv.append(C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_int(int(a)))
         fn(*conv)
 
 
 def _f(n, k=None): return np.zeros((n,) if k is None else (n, k), dtype=np.float32)
-def _mask(m): return np.ascontiguousarray(np.broadcast_to(np.asarray(m, dtype=bool), (LANES,))).astype(np.uint8)
-def _flt(a): return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), (LANES,)))
+def _mask(m, n=None): return np.ascontiguousarray(np.broadcast_to(np.asarray(m, dtype=bool), (n or LANES,))).astype(np.uint8)
+def _flt(a, n=None): return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), (n or LANES,)))
+def _i32(a, n=None): return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.int32), (n or LANES,)))
+
+
+def width(*vals):
+    """Dr.Jit width of a set of values: 1 when everything is scalar (then results stay scalar and broadcast later)."""
+    w = 1
+    for v in vals:
+        for c in (v.c if isinstance(v, Vec) else (v,)):
+            a = np.asarray(c)
+            if a.ndim > 0:
+                w = max(w, a.shape[0])
+    return w
+
+
+def _out_vec(a, n):
+    v = LVec.from_arr(a)
+    if n == 1:
+        v.c = tuple(np.asarray(x[0]).view(DrArray) for x in v.c)
+    return v
+
+
+def _out(a, n):
+    return (np.asarray(a[0]) if n == 1 else a).view(DrArray)
 
 
 class Ray3f:
-    def __init__(self, o=None, d=None, maxt=None):
+    def __init__(self, o=None, d=None, maxt=None, wavelengths=None):
+        time = 0.0
         if isinstance(o, Ray3f):
             o, d, maxt = o.o, o.d, o.maxt
-        self.o, self.d, self.maxt = o, d, maxt
-        self.time, self.wavelengths = LFloat(0.0), None
+        elif maxt is not None and wavelengths is not None:        # RayDifferential3f(o, d, time, wavelengths)
+            time, maxt = maxt, None
+        self.o, self.d = LVec(o), LVec(d)
+        self.maxt = np.float32(np.finfo(np.float32).max) if maxt is None else maxt
+        self.time, self.wavelengths = (LFloat(0.0) if LANES else np.float32(0.0)), None
 
 
 class BSDFPtr:
-    Smooth, Delta = 0x1, 0x2                       # stand-ins for the BSDFFlags unions the integrators test
+    Smooth, Delta, Reflection = 0x1, 0x2, 0x4      # stand-ins for the BSDFFlags unions the integrators test
+
+    def eval(self, ctx, si, wo, active=True):
+        return self.eval_pdf(ctx, si, wo, active)[0]
 
     def __init__(self, osv, shape): self.osv, self.shape = osv, shape
 
@@ -511,6 +546,11 @@ class SurfaceInteraction3f:
         self.osv.call("osv_spawn_ray", self.p.arr(), self.n.arr(), d.arr(), o, maxt)
         return Ray3f(LVec.from_arr(o), d, maxt.view(DrArray))
 
+    def spawn_ray_to(self, target):
+        o, d, maxt = _f(LANES, 3), _f(LANES, 3), _f(LANES)
+        self.osv.call("osv_spawn_ray_to", self.p.arr(), self.n.arr(), target.arr(), o, d, maxt)
+        return Ray3f(LVec.from_arr(o), LVec.from_arr(d), maxt.view(DrArray))
+
     def to_world(self, v):
         out = _f(LANES, 3); self.osv.call("osv_to_world", self.s.arr(), self.tt.arr(), self.n.arr(), v.arr(), out); return LVec.from_arr(out)
 
@@ -545,13 +585,24 @@ class ShimScene:
         self.osv = Osv(our_scene.describe(sensor))
 
     def ray_intersect(self, ray, ray_flags=None, coherent=None, active=True):
-        n = LANES
+        n = width(ray.o, ray.d, ray.maxt)
         valid, t, p, nr, s, tt, shape, wi = np.zeros(n, np.uint8), _f(n), _f(n, 3), _f(n, 3), _f(n, 3), _f(n, 3), np.zeros(n, np.int32), _f(n, 3)
-        self.osv.call("osv_ray_intersect", ray.o.arr(), ray.d.arr(), _flt(ray.maxt), valid, t, p, nr, s, tt, shape, wi)
+        self.osv.call("osv_ray_intersect", ray.o.arr(n), ray.d.arr(n), _flt(ray.maxt, n), valid, t, p, nr, s, tt, shape, wi, n=n)
         si = SurfaceInteraction3f(); si.osv = self.osv
-        si.valid, si.t, si.shape = (valid != 0).view(DrArray), t.view(DrArray), shape
-        si.p, si.n, si.s, si.tt, si.wi = (LVec.from_arr(x) for x in (p, nr, s, tt, wi))
+        si.valid, si.t, si.shape = _out(valid != 0, n), _out(t, n), shape
+        si.p, si.n, si.s, si.tt, si.wi = (_out_vec(x, n) for x in (p, nr, s, tt, wi))
+        si.time = LFloat(0.0) if n != 1 else np.float32(0.0)
         return si
+
+    def ray_test(self, ray, active=True):
+        n = width(ray.o, ray.d, ray.maxt, active)
+        hit = np.zeros(n, np.uint8)
+        self.osv.call("osv_ray_test", ray.o.arr(n), ray.d.arr(n), _flt(ray.maxt, n), hit, n=n)
+        return _out((hit != 0) & np.broadcast_to(np.asarray(active, dtype=bool), (n,)), n)
+
+    def emitters(self): return [ProjectorShim(self)] if self.our_scene.emitters()[0].get("spec") is not None else []
+    def shapes(self): return [ShapeShim(self, i) for i in range(self.osv.lib.osv_n_shapes(C.c_void_p(self.osv.h)))]
+    def shapes_dr(self): return self
 
     def sample_emitter_direction(self, ref, sample, test_visibility=True, active=True):
         n = LANES
@@ -655,10 +706,15 @@ class ShimADIntegrator(ADIntegrator):
         idx = np.arange(LANES, dtype=np.int64) // spp
         py, px = idx // w, idx % w
         jitter = sampler.next_2d()
+        pos = LVec2.__new__(LVec2); pos.c = (px.astype(np.float32).view(DrArray), py.astype(np.float32).view(DrArray))
+        if hasattr(sensor, "sample_ray_differential"):        # a reference sensor class (nlos_capture_meter): run ITS code
+            scale = LVec2(np.float32(1.0) / np.float32(w), np.float32(1.0) / np.float32(h))       # rcp(film_size)
+            pos_adjusted = (pos + jitter) * scale
+            ray, weight = sensor.sample_ray_differential(LFloat(0.0), LFloat(0.0), pos_adjusted, LVec2(0.0), LBool(True))
+            return ray, LVec(weight), pos
         o, d, maxt = _f(LANES, 3), _f(LANES, 3), _f(LANES)
         scene.osv.call("osv_camera_rays", px.astype(np.uint32), py.astype(np.uint32), jitter.arr(), o, d, maxt)
         ray = Ray3f(LVec.from_arr(o), LVec.from_arr(d), maxt.view(DrArray))
-        pos = LVec2.__new__(LVec2); pos.c = (px.astype(np.float32).view(DrArray), py.astype(np.float32).view(DrArray))
         return ray, LVec(1.0), pos
 
     @staticmethod
@@ -757,5 +813,229 @@ def reference_render(our_scene, integrator_module, integrator_cls, props, spp, s
     scene.sensors = lambda: [shim_sensor]
     integ = getattr(mod, integrator_cls)(mi.Properties(**props))
     steady, transient = integ.render(scene, shim_sensor, seed=seed, spp=spp)
+    LANES = None
+    return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Part 3 -- what transient_nlos_path / nlos_capture_meter need on top: shapes, the projector, transforms,
+#  DiscreteDistribution, mi.traverse, meshgrid / linspace / gather, and dr.syntax's array-`if`.
+# ---------------------------------------------------------------------------------------------------------
+import ast
+import copy as _copy
+import inspect
+import textwrap
+
+
+class ShimTransform4f:
+    """mi.Transform4f as the reference uses it: translate(), translation(), `@ Vector3f`; float32 entries."""
+    def __init__(self, m=None): self.m = np.eye(4, dtype=np.float64) if m is None else np.asarray(m, dtype=np.float64)
+
+    def translate(self, v):
+        t = np.eye(4); t[:3, 3] = [float(np.asarray(c)) for c in (v.c if isinstance(v, Vec) else v)]
+        return ShimTransform4f(self.m @ t)
+
+    def translation(self):
+        return LVec(*[np.float32(self.m[k, 3]) for k in range(3)])
+
+    def __matmul__(self, v):                       # vectors only (directions): 3x3 block, float32, no contraction
+        m = self.m.astype(np.float32)
+        return LVec(*[(m[k, 0] * v.x + m[k, 1] * v.y) + m[k, 2] * v.z for k in range(3)])
+
+
+class ShapeShim:
+    def __init__(self, scene, index): self.scene, self.index = scene, index
+    def __eq__(self, o): return isinstance(o, ShapeShim) and o.index == self.index
+    __hash__ = None
+    def surface_area(self): return [float(self.scene.osv.lib.osv_shape_area(C.c_void_p(self.scene.osv.h), C.c_uint32(self.index)))]
+    def sample_position(self, time, sample, active=True): return ShapePtrLanes(self.scene, self.index).sample_position(time, sample, active)
+
+
+class ShapePtrLanes:
+    def __init__(self, scene, index): self.scene, self.index = scene, index
+
+    def sample_position(self, time, sample, active=True):
+        n = width(sample, self.index, active)
+        p, nr, pdf = _f(n, 3), _f(n, 3), _f(n)
+        self.scene.osv.call("osv_shape_sample_position", _i32(self.index, n), sample.arr(n), _mask(active, n), p, nr, pdf, n=n)
+        return types.SimpleNamespace(p=_out_vec(p, n), n=_out_vec(nr, n), pdf=_out(pdf, n))
+
+
+class ProjectorShim:
+    def __init__(self, scene):
+        self.scene = scene
+        from mitransient_b200.scene import _to_transform
+        self._tw = ShimTransform4f(_to_transform(scene.our_scene.emitters()[0]["spec"].get("to_world")).matrix)
+
+    def world_transform(self): return self._tw
+
+    def sample_direction(self, it, sample, active=True):
+        n = LANES
+        dp, dd, dist, pdf, w = _f(n, 3), _f(n, 3), _f(n), _f(n), _f(n, 3)
+        self.scene.osv.call("osv_projector_sample_direction", it.p.arr(), _mask(active), dp, dd, dist, pdf, w)
+        ds = DirectionSample3f()
+        ds.p, ds.d, ds.dist, ds.pdf, ds.delta, ds.emitter = LVec.from_arr(dp), LVec.from_arr(dd), dist.view(DrArray), pdf.view(DrArray), LBool(True), None
+        ds.n = LVec(0.0)
+        return ds, LVec.from_arr(w)
+
+
+class DiscreteDistribution:
+    def __init__(self, pmf): self.pmf = np.asarray(pmf, dtype=np.float32)
+
+    def sample_reuse_pmf(self, u, active=True):
+        n = width(u)
+        idx, un, pm = np.zeros(n, np.int32), _f(n), _f(n)
+        lib = _CURRENT["osv"].lib
+        lib.osv_discrete_sample_reuse_pmf.restype = None
+        lib.osv_discrete_sample_reuse_pmf(C.c_void_p(_CURRENT["osv"].h), C.c_uint64(n), C.c_void_p(self.pmf.ctypes.data), C.c_uint32(len(self.pmf)),
+                                          C.c_void_p(_flt(u, n).ctypes.data), C.c_void_p(idx.ctypes.data), C.c_void_p(un.ctypes.data),
+                                          C.c_void_p(pm.ctypes.data))
+        return idx, un.view(DrArray), pm.view(DrArray)
+
+
+class ShimSensorBase(Object):
+    """mi.Sensor: film(), sampler(), get_shape() come from the properties the driver passes in."""
+    def __init__(self, props):
+        self._film, self._sampler, self._shape = props.get("_film"), props.get("_sampler"), props.get("_shape")
+    def film(self): return self._film
+    def sampler(self): return self._sampler
+    def get_shape(self): return self._shape
+    def shape(self): return self._shape
+    def traverse(self, cb): pass
+
+
+def _rewrite_array_ifs(fn):
+    """dr.syntax for this stand-in: `if <array condition>: <assignments>` becomes lane-wise selects; everything else
+    (scalar conditions, loops driven by dr.hint) runs as ordinary Python."""
+    src = textwrap.dedent(inspect.getsource(fn))
+    tree = ast.parse(src)
+    fdef = tree.body[0]
+    fdef.decorator_list = []
+
+    class T(ast.NodeTransformer):
+        def visit_If(self, node):
+            self.generic_visit(node)
+            simple = not node.orelse and all(isinstance(b, (ast.Assign, ast.AugAssign)) and
+                                             isinstance(b.targets[0] if isinstance(b, ast.Assign) else b.target, ast.Name) for b in node.body)
+            if not simple:
+                return node
+            masked = []
+            for b in node.body:
+                tgt = b.targets[0] if isinstance(b, ast.Assign) else b.target
+                new = b.value if isinstance(b, ast.Assign) else ast.BinOp(left=ast.Name(id=tgt.id, ctx=ast.Load()), op=b.op, right=b.value)
+                sel = ast.Call(func=ast.Name(id="__shim_select", ctx=ast.Load()),
+                               args=[ast.Name(id="__shim_c", ctx=ast.Load()), new, ast.Name(id=tgt.id, ctx=ast.Load())], keywords=[])
+                masked.append(ast.Assign(targets=[ast.Name(id=tgt.id, ctx=ast.Store())], value=sel))
+            test = ast.Call(func=ast.Name(id="__shim_is_array", ctx=ast.Load()), args=[ast.Name(id="__shim_c", ctx=ast.Load())], keywords=[])
+            return [ast.Assign(targets=[ast.Name(id="__shim_c", ctx=ast.Store())], value=node.test),
+                    ast.If(test=test, body=masked, orelse=[ast.If(test=ast.Name(id="__shim_c", ctx=ast.Load()), body=node.body, orelse=[])])]
+    tree = ast.fix_missing_locations(T().visit(tree))
+    g = fn.__globals__
+    g["__shim_is_array"] = lambda c: isinstance(c, np.ndarray) and c.ndim > 0
+    g["__shim_select"] = lambda c, a, b: sys.modules["drjit"].select(c, a, b)
+    loc = {}
+    exec(compile(tree, inspect.getsourcefile(fn), "exec"), g, loc)
+    return loc[fdef.name]
+
+
+def install_nlos_services(monochromatic=False, transform_cls=None, color_fn=None):
+    mi, dr = install_scene_services(monochromatic, transform_cls, color_fn)
+    mi.Transform4f, mi.Sensor = ShimTransform4f, ShimSensorBase
+    mi.RayDifferential3f = Ray3f
+    mi.DiscreteDistribution, mi.ShapePtr, mi.EmitterPtr = DiscreteDistribution, ShapePtrLanes, EmitterPtr
+    mi.ScalarVector2f = Vec2F
+    mi.Interaction3f = mi.PositionSample3f = object
+    mi.BSDFSample3f = "BSDFSample3f"
+    mi.BSDFFlags.Reflection = BSDFPtr.Reflection
+    mi.Frame3f = types.SimpleNamespace(cos_theta=lambda v: v.z)
+    sys.modules["drjit.scalar"].Array3f = VecF
+    mi.traverse = lambda obj: {"film.size": Vec2I(int(obj.film().size().x), int(obj.film().size().y)),
+                               "film.laser_scan_width": getattr(obj.film(), "laser_scan_width", 0),
+                               "film.laser_scan_height": getattr(obj.film(), "laser_scan_height", 0)}
+    dr.syntax = lambda f=None, **kw: (_rewrite_array_ifs(f) if f is not None else (lambda g: _rewrite_array_ifs(g)))
+    dr.make_opaque = lambda *a: None
+    dr.linspace = lambda t, a, b, n, endpoint=True: (np.arange(int(n), dtype=np.float32) * np.float32((b - a) / (n if not endpoint else n - 1))
+                                                      + np.float32(a)).view(DrArray)
+    dr.meshgrid = lambda x, y: (np.tile(x, len(y)).view(DrArray), np.repeat(y, len(x)).view(DrArray))
+    osv_dot = lambda a, b: _dot(a, b)
+    dr.dot = osv_dot
+    dr.norm = lambda v: np.sqrt(_dot(v, v)).view(DrArray)
+    dr.normalize = lambda v: v * (np.float32(1.0) / np.sqrt(_dot(v, v)))
+    dr.square = dr.sqr = lambda x: (np.asarray(x, dtype=np.float32) * np.asarray(x, dtype=np.float32)).view(DrArray)
+    dr.abs = lambda x: np.abs(x).view(DrArray)
+    dr.copy = lambda x: _copy.copy(x)
+    base_zeros = dr.zeros
+    dr.zeros = lambda t, n=1: (types.SimpleNamespace(wo=LVec(0.0), pdf=LFloat(0.0), eta=LFloat(1.0), sampled_type=LUInt(0), sampled_component=0)
+                               if t == "BSDFSample3f" else base_zeros(t, n))
+    base_select = dr.select
+
+    def select(m, a, b):
+        if isinstance(a, types.SimpleNamespace) and isinstance(b, types.SimpleNamespace):
+            return types.SimpleNamespace(**{k: (select(m, getattr(a, k), getattr(b, k)) if k != "sampled_component" else 0)
+                                            for k in ("wo", "pdf", "eta", "sampled_type", "sampled_component")})
+        if isinstance(a, np.ndarray) and a.dtype.kind in "iu" and not isinstance(b, Vec):
+            return np.where(m, a, b).view(DrArray)
+        return base_select(m, a, b)
+    dr.select = select
+
+    def gather(t, src, idx, active=True):
+        idx = np.asarray(idx, dtype=np.int64)
+        if t is ShapePtrLanes:
+            return ShapePtrLanes(src, idx.astype(np.int32))
+        if isinstance(src, Vec):
+            out = LVec.__new__(LVec); out.c = tuple(np.asarray(c)[idx].view(DrArray) for c in src.c); return out
+        return np.asarray(src)[idx].view(DrArray)
+    dr.gather = gather
+    return mi, dr
+
+
+def _dot(a, b):
+    """dr.dot with the arithmetic contract's fused chain (the oracle's dot, through osv_dot)."""
+    n = width(a, b)
+    out = _f(n)
+    _CURRENT["osv"].call("osv_dot", a.arr(n), b.arr(n), out, n=n)
+    return _out(out, n)
+
+
+def reference_render_nlos(our_scene, props, spp, seed=0):
+    """Run the REFERENCE'S render() + TransientNLOSPath (prepare, sample, emitter_*_sample, hidden_geometry_sample)
+    and its NLOSCaptureMeter for `our_scene`; returns (steady, raw film, deposits)."""
+    import mitransient_b200 as mitr
+    global LANES
+    LANES = None
+    mi, dr = install_nlos_services(False, mitr.ScalarTransform4f, mitr.ScalarColor3d)
+    thf = ref_module("mitransient.films.transient_hdr_film")
+    mod = ref_module("mitransient.integrators.transientnlospath")
+    meter = ref_module("mitransient.sensors.nloscapturemeter")
+    sensor = our_scene.sensors()[0]
+    f = sensor.film()
+    film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
+                                              start_opl=f.start_opl, bin_width_opl=f.bin_width_opl,
+                                              exhaustive_scan=f.exhaustive_scan, laser_scan_width=f.laser_scan_width,
+                                              laser_scan_height=f.laser_scan_height))
+    log = []
+    inner = film.add_transient_data
+
+    def logged(pos, distance, wavelengths, spec, ray_weight, active, **kw):
+        a = np.broadcast_to(np.asarray(active, dtype=bool), (LANES,))
+        val = spec * ray_weight
+        cols = [np.broadcast_to(np.asarray(c, dtype=np.float32), (LANES,)) for c in (pos.x, pos.y, distance, val.x, val.y, val.z)]
+        rec = np.stack(cols, axis=1).astype(np.float32)
+        nz = a & ((rec[:, 3] != 0) | (rec[:, 4] != 0) | (rec[:, 5] != 0))
+        log.append(rec[nz])
+        return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
+    film.add_transient_data = logged
+    _real_load = mi.load_dict
+    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    scene = ShimScene(our_scene, sensor)
+    _CURRENT["osv"] = scene.osv
+    wall_index = int(scene.osv.lib.osv_sensor_shape(C.c_void_p(scene.osv.h)))
+    sampler = ShimSampler(spp); sampler.base_seed = sensor.sampler().base_seed
+    ref_sensor = meter.NLOSCaptureMeter(mi.Properties(sensor_origin=VecF(*[float(x) for x in sensor._world_transform.translation()]), _film=film,
+                                                      _sampler=sampler, _shape=ShapeShim(scene, wall_index)))
+    scene.sensors = lambda: [ref_sensor]
+    LANES = int(f.size()[0]) * int(f.size()[1])            # width of the prepare() phase: one lane per film pixel
+    integ = mod.TransientNLOSPath(mi.Properties(**props))
+    steady, transient = integ.render(scene, ref_sensor, seed=seed, spp=spp)
     LANES = None
     return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)

@@ -205,3 +205,52 @@ def test_gpu_render_equals_the_reference_integrator(mitr, name):
     assert np.array_equal(raw != 0, ref != 0)
     assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
     np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ transient_nlos_path
+from path_cases import NLOS_CASES, nlos_case_scene  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(NLOS_CASES))
+def test_oracle_nlos_deposits_equal_the_reference_integrator(mitr, oracle, name):
+    """TransientNLOSPath.prepare / sample / emitter_laser_sample / emitter_laser_targets_sample / emitter_nee_sample /
+    hidden_geometry_sample (transientnlospath.py:251-927) and NLOSCaptureMeter.sample_ray_differential
+    (nloscapturemeter.py:136-202) were EXECUTED over the oracle's scene services: confocal, single and exhaustive
+    captures, laser and plain emitter sampling, hidden-geometry sampling with and without roulette / relay wall,
+    filter_depth, discard_direct_paths, account_first_and_last_bounces.  Deposits bit for bit; the exhaustive films
+    (laser-indexed) element for element."""
+    scene, cfg, _ = nlos_case_scene(name)
+    r = oracle.render(scene, scene.integrator(), spp=cfg[3], seed=5, log_deposits=1 << 20)
+    assert len(GP[name + "_deposits"]) > 0
+    assert np.array_equal(sort_rows(r["deposits"]), GP[name + "_deposits"])
+    ref = GP[name + "_raw"]
+    assert r["transient"].shape == ref.shape and np.array_equal(r["transient"] != 0, ref != 0)
+    assert np.abs(r["transient"] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mitransient"), reason="the reference tree is not available here")
+def test_reference_nlos_integrator_runs_live(mitr, oracle):
+    import warnings
+    import refshim
+    d = mitr.nlos_z_scene(4, 5, 48, 6, start_opl=0.0, window=8.0, max_depth=5)
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=6, seed=9)
+    r = oracle.render(scene, scene.integrator(), spp=6, seed=9, log_deposits=1 << 20)
+    assert len(dep) > 50 and np.array_equal(sort_rows(dep), sort_rows(r["deposits"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(NLOS_CASES))
+def test_gpu_nlos_render_equals_the_reference_integrator(mitr, name):
+    scene, cfg, _ = nlos_case_scene(name)
+    integ = scene.integrator()
+    integ.collect_counters = True
+    integ.render(scene, spp=cfg[3], seed=5)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = GP[name + "_raw"]
+    assert integ.last_counters["deposits"] == len(GP[name + "_deposits"])
+    assert raw.shape == ref.shape and np.array_equal(raw != 0, ref != 0)
+    assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
