@@ -6,19 +6,20 @@
 //  only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 //  may load it.  Nothing under mitransient_b200/ links, imports or calls it.
 //
-//  PARITY STATUS: *partially pinned*.
-//   - PINNED against the reference's own code, executed: the film half of the path -- add_transient_data,
-//     TransientImageBlock.put_/accum (plain and exhaustive_scan index), develop_transient_, the phasor film
-//     (frequency selection, PhasorImageBlock.put, develop_phasors_) -- plus the benchmark scene dictionary, the
-//     integrators' parameter parsing and pass split.  tests/golden/make_reference_golden.py runs the UNMODIFIED
-//     Python of /root/reference/mitransient over a NumPy stand-in for drjit/mitsuba (tests/golden/refshim.py) and
-//     commits the outputs; tests/test_reference_golden.py requires this oracle to match them (the time-histogram
-//     films bit for bit).
-//   - UNPINNED: the ray-tracing half.  Its arithmetic lives in two third-party, un-vendored dependencies --
-//     mitsuba (pinned >=3.6.0,<3.9.0, mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the
-//     notebooks) -- which are not installable here (no wheel, no network), and the reference's only test is stale
-//     and shape-only (tests/integration/test_nlos.py:81-118).  For that half the oracle restates the published
-//     Mitsuba 3 algorithms and is validated by the analytic known-answer tests in tests/test_oracle_kat.py.
+//  PARITY STATUS: pinned against the reference's own code (executed), down to the Mitsuba primitives.
+//   - PINNED, film half: add_transient_data, TransientImageBlock.put_/accum (plain and exhaustive_scan index),
+//     develop_transient_, the phasor film, the benchmark scene dictionary, parameter parsing, pass split.
+//   - PINNED, integrator loops: TransientADIntegrator.render, TransientPath.sample, TransientNLOSPath.prepare /
+//     sample / emitter_*_sample / hidden_geometry_sample and NLOSCaptureMeter run UNMODIFIED over a NumPy stand-in
+//     for drjit/mitsuba (tests/golden/refshim.py) whose scene objects call this file's osv_* exports; every
+//     deposit of trace_transient_path / trace_nlos_path must equal one of theirs bit for bit
+//     (tests/golden/make_reference_golden.py, tests/test_reference_golden.py).
+//   - UNPINNED: the Mitsuba primitives themselves (ray casting, BSDF / emitter / sensor sampling, the sampler) and
+//     trace_volpath's loop.  Their arithmetic lives in two third-party, un-vendored dependencies -- mitsuba
+//     (pinned >=3.6.0,<3.9.0, mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the notebooks) --
+//     which are not installable here (no wheel, no network), and the reference's only test is stale and
+//     shape-only (tests/integration/test_nlos.py:81-118).  They restate the published Mitsuba 3 algorithms and
+//     are validated by the analytic known-answer tests in tests/test_oracle_kat.py.
 //
 //  What is restated (file:line relative to the mitransient tree):
 //    render driver        mitransient/integrators/common.py:122-213   -> oracle_render

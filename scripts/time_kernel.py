@@ -18,14 +18,25 @@ ap.add_argument("--bins", type=int, default=1024)
 ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol"])
 a = ap.parse_args()
-scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
+if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256 x 4096 bins, 1024 spp
+    a.width = a.height = 256 if a.width == 512 else a.width
+    a.bins = 4096 if a.bins == 1024 else a.bins
+    a.spp = 1024 if a.spp == 256 else a.spp
+    scene = mitr.load_dict(mitr.nlos_z_scene(a.width, a.height, a.bins, a.spp))
+elif a.scene == "vol":         # BASELINE config C4(i): volumetric Cornell box 256x384 x 512 bins
+    a.width, a.height, a.bins, a.spp = 256, 384, 512, 64
+    scene = mitr.load_dict(mitr.cornell_box_volumetric(a.width, a.height, a.bins, a.spp))
+else:
+    scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
 integ, sensor = scene.integrator(), scene.sensors()[0]
 dev = integ.device_scene(scene, sensor)
 lib = _lib.load()
 film = torch.zeros((a.height, a.width, a.bins, 4), dtype=torch.float32, device="cuda")
 steady = torch.zeros((a.height, a.width, 3), dtype=torch.float32, device="cuda")
 params = integ.make_params(a.spp, a.spp, 0)
+integ.fill_params_(params, scene, sensor)
 st = torch.cuda.current_stream()
 for _ in range(3):
     _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(), None, st.cuda_stream))
