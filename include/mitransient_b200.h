@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 9
+#define TR_ABI_VERSION 10
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -87,7 +87,10 @@ typedef struct TrBsdfDesc {
     float _pad[2];
 } TrBsdfDesc;
 
-enum { TR_EMITTER_AREA = 0, TR_EMITTER_PROJECTOR = 1 };
+/* TR_EMITTER_ANGULARAREA: mitransient's own `angulararea` emitter (mitransient/emitters/angulararea.py): an area light
+ * whose radiance falls off with the angle to the surface normal (1 inside beam_width, linear down to 0 at
+ * cutoff_angle); its sample_direction carries the reference's extra 1/dist^2 factor (:121-123).  transient_path only. */
+enum { TR_EMITTER_AREA = 0, TR_EMITTER_PROJECTOR = 1, TR_EMITTER_ANGULARAREA = 2 };
 
 typedef struct TrEmitterDesc {
     int32_t type;        /* TR_EMITTER_*                                                    */
@@ -98,7 +101,12 @@ typedef struct TrEmitterDesc {
     float world_to_local[12];    /* projector: inverse of to_world (row-major 3x4 affine)       */
     float camera_to_sample[16];  /* projector: Mitsuba's perspective_projection(1x1, fov_x, 1e-4,
                                     1e4): local space -> [0,1]^2 texture coordinates            */
-    float _pad[2];
+    float cutoff_angle;          /* angulararea: radians (angulararea.py:57-58)                  */
+    float beam_width;            /* angulararea: radians, <= cutoff_angle (:59-60)               */
+    float cos_cutoff_angle;      /* angulararea: the reference computes these three in double     */
+    float cos_beam_width;        /*   precision at construction (:61-67) and uses them as fp32    */
+    float inv_transition_width;  /*   constants: 1 / (cutoff - beam), +inf when they are equal    */
+    float _pad;
 } TrEmitterDesc;
 
 typedef struct TrMediumDesc { /* homogeneous medium + Henyey-Greenstein phase function      */
@@ -119,6 +127,9 @@ typedef struct TrSensorDesc {
     float origin[3];        /* nlos_capture_meter: sensor_origin
                                (mitransient/sensors/nloscapturemeter.py:100-102)            */
     int32_t medium;         /* index of the medium the sensor sits in, or -1                */
+    int32_t is_confocal;    /* nlos_capture_meter with original_film_width/height: a 1x1 film whose every ray goes to
+                               laser_target (nloscapturemeter.py:113-125, 142-144)          */
+    float laser_target[3];
 } TrSensorDesc;
 
 /* Film kinds.  TR_FILM_TRANSIENT_HDR: time histogram, film[y][x][t][c]

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 9
+TR_ABI_VERSION = 10
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -17,7 +17,7 @@ TR_PRIM_TRIANGLE, TR_PRIM_QUAD, TR_PRIM_BOX = 0, 1, 2
 TR_SHAPE_FLAG_SENSOR = 1
 TR_BSDF_DIFFUSE, TR_BSDF_NULL, TR_BSDF_CONDUCTOR, TR_BSDF_DIELECTRIC = 0, 1, 2, 3
 TR_BSDF_FLAG_TWOSIDED = 1
-TR_EMITTER_AREA, TR_EMITTER_PROJECTOR = 0, 1
+TR_EMITTER_AREA, TR_EMITTER_PROJECTOR, TR_EMITTER_ANGULARAREA = 0, 1, 2
 TR_SENSOR_PERSPECTIVE, TR_SENSOR_NLOS_CAPTURE_METER = 0, 1
 TR_INTEGRATOR_TRANSIENT_PATH, TR_INTEGRATOR_TRANSIENT_NLOS_PATH, TR_INTEGRATOR_TRANSIENT_PRBVOLPATH = 0, 1, 2
 
@@ -49,7 +49,8 @@ class TrBsdfDesc(C.Structure):
 class TrEmitterDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("shape", C.c_int32), ("radiance", C.c_float * 3), ("fov_x", C.c_float),
                 ("to_world", C.c_float * 12), ("world_to_local", C.c_float * 12), ("camera_to_sample", C.c_float * 16),
-                ("_pad", C.c_float * 2)]
+                ("cutoff_angle", C.c_float), ("beam_width", C.c_float), ("cos_cutoff_angle", C.c_float),
+                ("cos_beam_width", C.c_float), ("inv_transition_width", C.c_float), ("_pad", C.c_float)]
 
 
 class TrMediumDesc(C.Structure):
@@ -59,7 +60,7 @@ class TrMediumDesc(C.Structure):
 class TrSensorDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("shape", C.c_int32), ("to_world", C.c_float * 12),
                 ("sample_to_camera", C.c_float * 16), ("near_clip", C.c_float), ("far_clip", C.c_float),
-                ("origin", C.c_float * 3), ("medium", C.c_int32)]
+                ("origin", C.c_float * 3), ("medium", C.c_int32), ("is_confocal", C.c_int32), ("laser_target", C.c_float * 3)]
 
 
 class TrFilmDesc(C.Structure):

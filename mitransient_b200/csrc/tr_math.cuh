@@ -163,6 +163,32 @@ __device__ __forceinline__ void coordinate_system(V3 n, V3 *s, V3 *t) {
     *t = v3(b, fmaf(n.y, n.y * a, sign), -n.y);
 }
 
+// acos for the angulararea falloff: Cephes asinf / acosf polynomial, same operations as the oracle's acos_cephes
+__device__ __forceinline__ float asin_cephes(float x) {
+    float a = fabsf(x), z, w; bool big = a > 0.5f;
+    if (big) { z = 0.5f * (1.0f - a); w = sqrtf(z); } else { w = a; z = a * a; }
+    float p = fmaf(4.2163199048e-2f, z, 2.4181311049e-2f);
+    p = fmaf(p, z, 4.5470025998e-2f); p = fmaf(p, z, 7.4953002686e-2f); p = fmaf(p, z, 1.6666752422e-1f);
+    float r = fmaf(p * z, w, w);
+    if (big) r = 1.57079632679489661923f - (r + r);
+    return x < 0.0f ? -r : r;
+}
+__device__ __forceinline__ float acos_cephes(float x) {
+    if (x < -0.5f) return 3.14159265358979323846f - 2.0f * asin_cephes(sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * asin_cephes(sqrtf(0.5f * (1.0f - x)));
+    return 1.57079632679489661923f - asin_cephes(x);
+}
+// AngularAreaLight._fallof_curve (mitransient/emitters/angulararea.py:57-67, 73-81) for a direction in the emitter's frame
+// ang = (cutoff_angle, beam_width, cos_cutoff, cos_beam) of the DevEmitter, inv_transition = 1 / (cutoff - beam)
+__device__ __forceinline__ float angular_falloff(float4 ang, float inv_transition, V3 d) {
+    const float cutoff = ang.x, cos_cutoff = ang.z, cos_beam = ang.w;
+    V3 local_dir = normalize(d);
+    float cos_theta = local_dir.z;
+    float beam_res = cos_theta >= cos_beam ? 1.0f : (cutoff - acos_cephes(cos_theta)) * inv_transition;
+    return cos_theta > cos_cutoff ? beam_res : 0.0f;
+}
+__device__ __forceinline__ V3 frame_to_local(V3 n, V3 v) { V3 s, t; coordinate_system(n, &s, &t); return v3(dot(v, s), dot(v, t), dot(v, n)); }
+
 __device__ __forceinline__ V3 offset_p(V3 p, V3 n, V3 dir) {
     float mag = (1.0f + fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z))) * TR_RAY_EPSILON;
     mag = mulsign(mag, dot(n, dir));

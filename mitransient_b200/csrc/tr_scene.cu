@@ -330,7 +330,13 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
         emitters[i].type = e.type; emitters[i].shape = e.shape; emitters[i].fov_x = e.fov_x;
         for (int c = 0; c < 3; ++c) emitters[i].radiance[c] = e.radiance[c];
         memcpy(emitters[i].to_world, e.to_world, sizeof(e.to_world));
-        if (e.type == TR_EMITTER_AREA) {
+        if (e.type == TR_EMITTER_AREA || e.type == TR_EMITTER_ANGULARAREA) {
+            if (e.type == TR_EMITTER_ANGULARAREA) {
+                if (!(e.cutoff_angle >= e.beam_width) || !(e.beam_width >= 0.0f)) { err = "angulararea: need cutoff_angle >= beam_width >= 0"; return false; }
+                emitters[i].cutoff_angle = e.cutoff_angle; emitters[i].beam_width = e.beam_width;
+                emitters[i].cos_cutoff = e.cos_cutoff_angle; emitters[i].cos_beam = e.cos_beam_width; emitters[i].inv_transition = e.inv_transition_width;
+                out.has_delta_bsdfs = true; out.has_angular_emitters = true;
+            }
             if (e.shape < 0 || (uint32_t) e.shape >= ns) { err = "area emitter without a valid shape"; return false; }
             if (desc->shapes[e.shape].emitter != (int32_t) i) { err = "area emitter / shape cross reference mismatch"; return false; }
             n_area++;

@@ -85,7 +85,8 @@ static_assert(sizeof(DevBsdf) == 64, "DevBsdf must be 64 bytes");
 struct DevEmitter {            // 96 bytes
     int32_t type, shape; float radiance[3]; float fov_x;   // 24
     float to_world[12];                                    // 72
-    float _pad[6];
+    float cutoff_angle, beam_width, cos_cutoff, cos_beam;  // angulararea (angulararea.py:57-67), offsets 72..84
+    float inv_transition, _pad;
 };
 static_assert(sizeof(DevEmitter) == 96, "DevEmitter must be 96 bytes");
 
@@ -98,7 +99,8 @@ struct SceneImpl {
     TrSensorDesc sensor;
     TrFilmDesc film;
     uint32_t n_nodes = 0, n_prims = 0;
-    bool has_delta_bsdfs = false;        // conductor / dielectric present: the general-material kernel instantiation is used
+    bool has_delta_bsdfs = false;        // conductor / dielectric / angulararea present: the general-material kernel instantiation is used
+    bool has_angular_emitters = false;
     int device = -1;
     // cached owned-pixel list (tile sharding), rebuilt when (tile, rank, world) changes
     void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;

@@ -83,9 +83,6 @@ class TransientNLOSPath(TransientADIntegrator):
             if (film.laser_scan_width, film.laser_scan_height) != tuple(film.size()):           # :345-348
                 raise AssertionError("Sensor and laser scan resolution must be equal if "
                                      "force_equal_illumination_scanning is set to True")
-        if getattr(sensor, "is_confocal", False):
-            raise NotImplementedError("1x1 confocal sensors (original_film_width/height) are not implemented; use "
-                                      "capture_type='confocal' on the integrator")
         if self.hg_sampling:                                                                # :277-289
             areas = [0.0 if (s.is_sensor and not self.hg_sampling_includes_relay_wall) else s.surface_area()
                      for s in scene.shapes()]

@@ -20,5 +20,5 @@ class TransientPath(TransientADIntegrator):
                                       "transient_nlos_path + nlos_capture_meter")
         if not scene.emitters():
             return
-        if any(e["type"] != _abi.TR_EMITTER_AREA for e in scene.emitters()):
-            raise NotImplementedError("transient_path supports `area` emitters only")
+        if any(e["type"] not in (_abi.TR_EMITTER_AREA, _abi.TR_EMITTER_ANGULARAREA) for e in scene.emitters()):
+            raise NotImplementedError("transient_path supports `area` and `angulararea` emitters")

@@ -16,6 +16,7 @@ Supported plugin types
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Any, Dict, List, Optional
 
@@ -429,6 +430,8 @@ class Scene:
         for i, e in enumerate(self.emitters_):
             emitters[i].type, emitters[i].shape = e["type"], e["shape"]
             emitters[i].radiance[:] = [float(x) for x in _variant.colour(e["radiance"])]
+            for k in ("cutoff_angle", "beam_width", "cos_cutoff_angle", "cos_beam_width", "inv_transition_width"):
+                setattr(emitters[i], k, e.get(k, 0.0))
             spec = e.get("spec")
             if spec is not None:      # projector: read the CURRENT state (nlos.focus_* may have re-aimed it)
                 emitters[i].radiance[:] = [float(x) for x in
@@ -537,7 +540,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
     if t != "scene":
         if t in plugins.INTEGRATORS or t in plugins.FILMS or t in plugins.SENSORS:
             return plugins.instantiate(d)
-        if t in _SHAPE_TYPES or t in _BSDF_TYPES or t in ("projector", "area", "homogeneous", "perspective"):
+        if t in _SHAPE_TYPES or t in _BSDF_TYPES or t in ("projector", "area", "angulararea", "homogeneous", "perspective"):
             return PluginSpec(d)
         raise ValueError(f"load_dict(): unsupported plugin type {t!r}")
 
@@ -645,7 +648,7 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
             for ck, cv in val.items():      # every nested plugin of a shape must be one this build understands
                 ct = _type_of(cv)
                 if ct is not None and ck not in ("interior", "exterior") and ct not in _BSDF_TYPES + (
-                        "ref", "area", "homogeneous") + tuple(plugins.SENSORS):
+                        "ref", "area", "angulararea", "homogeneous") + tuple(plugins.SENSORS):
                     raise ValueError(f"shape {key!r}: unsupported nested plugin type {ct!r} (supported bsdfs: diffuse, "
                                      "conductor, dielectric, twosided, null; emitters: area; sensors: nlos_capture_meter)")
             _, bspec = _find_child(val, _BSDF_TYPES + ("ref",))
@@ -662,10 +665,19 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 shape.exterior_medium = add_medium(val["exterior"])
             scene.shapes_.append(shape)
             sidx = len(scene.shapes_) - 1
-            _, em = _find_child(val, ("area",))
+            _, em = _find_child(val, ("area", "angulararea"))
             if em is not None:
-                scene.emitters_.append({"type": _abi.TR_EMITTER_AREA, "shape": sidx,
-                                        "radiance": _rgb(em.get("radiance"), 1.0)})
+                entry = {"type": _abi.TR_EMITTER_AREA, "shape": sidx, "radiance": _rgb(em.get("radiance"), 1.0)}
+                if em.get("type") == "angulararea":      # mitransient/emitters/angulararea.py:54-69 (degrees -> radians)
+                    cutoff = float(em.get("cutoff_angle", 10))
+                    beam = float(em.get("beam_width", cutoff))
+                    if not cutoff >= beam:
+                        raise AssertionError("angulararea: cutoff_angle must be >= beam_width")
+                    c_rad, b_rad = cutoff * (math.pi / 180.0), beam * (math.pi / 180.0)       # dr.deg2rad on Python floats
+                    entry.update(type=_abi.TR_EMITTER_ANGULARAREA, cutoff_angle=c_rad, beam_width=b_rad,
+                                 cos_cutoff_angle=math.cos(c_rad), cos_beam_width=math.cos(b_rad),
+                                 inv_transition_width=(math.inf if c_rad - b_rad == 0.0 else 1.0 / (c_rad - b_rad)))
+                scene.emitters_.append(entry)
                 shape.emitter_index = len(scene.emitters_) - 1
             sk, se = _find_child(val, tuple(plugins.SENSORS))
             if se is not None:

@@ -72,6 +72,8 @@ class NLOSCaptureMeter(NLOSSensor):
         d.type, d.shape = _abi.TR_SENSOR_NLOS_CAPTURE_METER, self._shape_index
         d.origin[:] = [float(x) for x in self._world_transform.translation()]
         d.medium = -1
+        d.is_confocal = int(self.is_confocal)
+        d.laser_target[:] = [float(x) for x in np.asarray(self.laser_target, dtype=np.float64).reshape(3)]
         return d
 
     def traverse(self):       # nloscapturemeter.py:219-228

@@ -501,6 +501,38 @@ inline void shape_sample_position(const Scene &sc, const Shape &sh, float u0, fl
     }
 }
 
+// acos for the angulararea falloff (Cephes asinf/acosf polynomial; part of the arithmetic contract like sincos_cephes)
+inline float asin_cephes(float x) {
+    float a = fabsf(x), z, w; bool big = a > 0.5f;
+    if (big) { z = 0.5f * (1.0f - a); w = sqrtf(z); } else { w = a; z = a * a; }
+    float p = fmaf(4.2163199048e-2f, z, 2.4181311049e-2f);
+    p = fmaf(p, z, 4.5470025998e-2f); p = fmaf(p, z, 7.4953002686e-2f); p = fmaf(p, z, 1.6666752422e-1f);
+    float r = fmaf(p * z, w, w);
+    if (big) r = 1.57079632679489661923f - (r + r);
+    return x < 0.0f ? -r : r;
+}
+inline float acos_cephes(float x) {
+    if (x < -0.5f) return 3.14159265358979323846f - 2.0f * asin_cephes(sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * asin_cephes(sqrtf(0.5f * (1.0f - x)));
+    return 1.57079632679489661923f - asin_cephes(x);
+}
+// AngularAreaLight._fallof_curve (mitransient/emitters/angulararea.py:73-81) on a direction in the emitter's local frame
+struct AngularParams { float cutoff, cos_cutoff, cos_beam, inv_transition; };
+inline AngularParams angular_params(const TrEmitterDesc &em) {                  // :57-67 (computed by the host in double, like the reference)
+    AngularParams a; a.cutoff = em.cutoff_angle; a.inv_transition = em.inv_transition_width;
+    a.cos_cutoff = em.cos_cutoff_angle; a.cos_beam = em.cos_beam_width;
+    return a;
+}
+inline float angular_falloff(const TrEmitterDesc &em, V3 d) {
+    AngularParams a = angular_params(em);
+    V3 local_dir = normalize(d);                                               // :74
+    float cos_theta = local_dir.z;
+    float beam_res = cos_theta >= a.cos_beam ? 1.0f : (a.cutoff - acos_cephes(cos_theta)) * a.inv_transition;   // :76-79
+    return cos_theta > a.cos_cutoff ? beam_res : 0.0f;                         // :81
+}
+// Frame3f(n).to_local(v) with Mitsuba's coordinate_system(n)
+inline V3 frame_to_local(V3 n, V3 v) { V3 s, t; coordinate_system(n, &s, &t); return v3(dot(v, s), dot(v, t), dot(v, n)); }
+
 // Emitter(area)::sample_direction -> Shape::sample_direction (area pdf -> solid angle).
 // Returns the (unoccluded) weight radiance / pdf, or 0.
 inline V3 area_sample_direction(const Scene &sc, const TrEmitterDesc &em, V3 ref_p, float u0, float u1, DirectionSample *ds) {
@@ -516,8 +548,27 @@ inline V3 area_sample_direction(const Scene &sc, const TrEmitterDesc &em, V3 ref
     ds->delta = false;
     bool active = (dot(ds->d, ds->n) < 0.0f) && (ds->pdf != 0.0f);
     if (!active) return v3(0, 0, 0);
+    if (em.type == TR_EMITTER_ANGULARAREA) {                                   // AngularAreaLight.sample_direction  angulararea.py:106-127
+        V3 local_d = frame_to_local(ds->n, -ds->d);                            // :113-114
+        float inv_dist = 1.0f / ds->dist;                                      // :115
+        float falloff = angular_falloff(em, local_d);                          // :118
+        if (!(falloff > 0.0f)) return v3(0, 0, 0);                             // :119
+        float f = falloff * (inv_dist * inv_dist);                             // :122-123  radiance * (falloff * inv_dist^2) / ds.pdf
+        V3 spec = v3(em.radiance[0], em.radiance[1], em.radiance[2]) * f;
+        return v3(spec.x / ds->pdf, spec.y / ds->pdf, spec.z / ds->pdf);
+    }
     float inv = 1.0f / ds->pdf;
     return v3(em.radiance[0], em.radiance[1], em.radiance[2]) * inv;
+}
+// Emitter::eval(si) on the emitter's surface: `area` = radiance on the front side; `angulararea` (:93-101) adds the falloff
+inline V3 emitter_eval(const TrEmitterDesc &em, V3 wi) {
+    if (!(wi.z > 0.0f)) return v3(0, 0, 0);
+    V3 r = v3(em.radiance[0], em.radiance[1], em.radiance[2]);
+    if (em.type == TR_EMITTER_ANGULARAREA) {
+        float falloff = angular_falloff(em, wi);
+        return falloff > 0.0f ? r * falloff : v3(0, 0, 0);
+    }
+    return r;
 }
 
 // Scene::sample_emitter_direction without the visibility test [upstream scene.cpp]: uniform emitter choice with
@@ -541,6 +592,7 @@ inline V3 scene_sample_emitter_direction(const Scene &sc, V3 ref_p, float u0, fl
 inline float area_pdf_direction(const Scene &sc, const TrEmitterDesc &em, V3 d, V3 n_light, float dist) {
     float dp = dot(d, n_light);
     if (!(dp < 0.0f)) return 0.0f;
+    if (em.type == TR_EMITTER_ANGULARAREA && !(angular_falloff(em, frame_to_local(n_light, -d)) > 0.0f)) return 0.0f;   // :129-141
     const Shape &sh = sc.shapes[em.shape];
     float adp = fabsf(dp);
     float pdf = sh.inv_area * (adp != 0.0f ? (dist * dist) / adp : 0.0f);
@@ -745,9 +797,8 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
                     if (n_em > 1) em_pdf *= 1.0f / (float) n_em;  // Scene::pdf_emitter
                 }
                 float mis = mis_weight(prev_bsdf_pdf, em_pdf);    // :169-172
-                float cos_i = -dot(ray.d, si.n);                  // Frame3f::cos_theta(si.wi)
-                if (cos_i > 0.0f && !discard_direct_light)        // area.eval: front side only  :175-177
-                    Le = (beta * mis) * v3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));   // si.wi
+                if (!discard_direct_light) Le = (beta * mis) * emitter_eval(em, wi);        // emitter.eval(si)  :175-177
             }
         }
         film.add_transient(px, py, Le, distance, sample_scale, ray_weight);   // :180-181
@@ -846,6 +897,7 @@ inline Ray nlos_sensor_ray(const Scene &sc, float sx, float sy) {
     float Wf = (float) sc.film.width, Hf = (float) sc.film.height;
     float gx = (floorf(sx * Wf) + 0.5f) / Wf, gy = (floorf(sy * Hf) + 0.5f) / Hf;           // :149-150
     V3 target = xf_point(wall.d.to_world, fmaf(gx, 2.0f, -1.0f), fmaf(gy, 2.0f, -1.0f), 0.0f);   // :151-153
+    if (sc.sensor.is_confocal) target = v3(sc.sensor.laser_target[0], sc.sensor.laser_target[1], sc.sensor.laser_target[2]);   // :142-144
     V3 origin = v3(sc.sensor.origin[0], sc.sensor.origin[1], sc.sensor.origin[2]);
     V3 dir = target - origin;                                                                  // :155-157
     float dist = sqrtf(dot(dir, dir));
@@ -1657,10 +1709,8 @@ void osv_emitter_eval(void *h, uint64_t n, const int32_t *shape, const float *wi
     const Scene &sc = ((OsvScene *) h)->sc;
     for (uint64_t i = 0; i < n; ++i) {
         V3 r = v3(0, 0, 0);
-        if (active[i] && shape[i] >= 0 && sc.shapes[shape[i]].d.emitter >= 0 && wi[3 * i + 2] > 0.0f) {
-            const TrEmitterDesc &em = sc.emitters[sc.shapes[shape[i]].d.emitter];
-            r = v3(em.radiance[0], em.radiance[1], em.radiance[2]);
-        }
+        if (active[i] && shape[i] >= 0 && sc.shapes[shape[i]].d.emitter >= 0)
+            r = emitter_eval(sc.emitters[sc.shapes[shape[i]].d.emitter], ld3(wi, i));
         st3(rgb, i, r);
     }
 }
@@ -1713,6 +1763,26 @@ void osv_shape_sample_position(void *h, uint64_t n, const int32_t *shape, const 
         if (active[i] && shape[i] >= 0) shape_sample_position(sc, sc.shapes[shape[i]], u[2 * i], u[2 * i + 1], &pp, &pn, &ppdf);
         st3(p, i, pp); st3(nrm, i, pn); pdf[i] = ppdf;
     }
+}
+void osv_acos(void *, uint64_t n, const float *x, float *out) { for (uint64_t i = 0; i < n; ++i) out[i] = acos_cephes(x[i]); }
+void osv_frame_to_local(void *, uint64_t n, const float *nrm, const float *v, float *out) {
+    for (uint64_t i = 0; i < n; ++i) st3(out, i, frame_to_local(ld3(nrm, i), ld3(v, i)));
+}
+// Shape::sample_direction of the shape carrying emitter 0 (area pdf -> solid angle) and Shape::pdf_direction
+void osv_shape_sample_direction(void *h, uint64_t n, const float *ref_p, const float *u, const uint8_t *active, float *ds_p, float *ds_n,
+                                float *ds_d, float *ds_dist, float *ds_pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    TrEmitterDesc plain = sc.emitters[0]; plain.type = TR_EMITTER_AREA;
+    for (uint64_t i = 0; i < n; ++i) {
+        DirectionSample ds; ds.p = ds.n = ds.d = v3(0, 0, 0); ds.dist = ds.pdf = 0.0f;
+        if (active[i]) area_sample_direction(sc, plain, ld3(ref_p, i), u[2 * i], u[2 * i + 1], &ds);
+        st3(ds_p, i, ds.p); st3(ds_n, i, ds.n); st3(ds_d, i, ds.d); ds_dist[i] = ds.dist; ds_pdf[i] = ds.pdf;
+    }
+}
+void osv_shape_pdf_direction(void *h, uint64_t n, const float *ds_d, const float *ds_n, const float *ds_dist, const uint8_t *active, float *pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    TrEmitterDesc plain = sc.emitters[0]; plain.type = TR_EMITTER_AREA;
+    for (uint64_t i = 0; i < n; ++i) pdf[i] = active[i] ? area_pdf_direction(sc, plain, ld3(ds_d, i), ld3(ds_n, i), ds_dist[i]) : 0.0f;
 }
 void osv_dot(void *, uint64_t n, const float *a, const float *b, float *out) {
     for (uint64_t i = 0; i < n; ++i) out[i] = dot(ld3(a, i), ld3(b, i));

@@ -63,3 +63,19 @@ def nlos_case_scene(name):
         wall = [v for v in d.values() if isinstance(v, dict) and v.get("type") == "rectangle"][0]
         mitr.nlos.focus_emitter_at_relay_wall_pixel(focus, mitr.PluginSpec(wall), scene.emitters()[0]["spec"])
     return scene, cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
+
+
+# ---- mitransient's `angulararea` emitter under transient_path: (film, integrator overrides, cutoff_angle, beam_width in degrees)
+ANGULAR_CASES = {
+    "angular_a": ((8, 8, 64, 16), {"max_depth": 5}, 60.0, 35.0),
+    "angular_b": ((6, 6, 48, 16), {"max_depth": 8, "rr_depth": 2}, 80.0, 80.0),      # cutoff == beam: hard edge, inv_transition = inf
+}
+
+
+def angular_case_scene(name):
+    cfg, integ, cutoff, beam = ANGULAR_CASES[name]
+    d = mitr.cornell_box_config(*cfg, window=(3.5, 12.5))
+    d["integrator"].update(integ)
+    d["light"]["emitter"] = {"type": "angulararea", "radiance": {"type": "rgb", "value": [18.387, 10.9873, 2.75357]},
+                             "cutoff_angle": cutoff, "beam_width": beam}
+    return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}

@@ -765,7 +765,8 @@ def install_scene_services(monochromatic=False, transform_cls=None, color_fn=Non
     dr.rcp = lambda x: (np.float32(1.0) / np.asarray(x, dtype=np.float32)).view(DrArray)
     dr.detach = lambda x, *a: x
     dr.copy = lambda x: x
-    dr.zeros = lambda t, n=1: _zero_si(_CURRENT["osv"]) if t is SurfaceInteraction3f else np.zeros(int(n), dtype=np.float32)
+    dr.zeros = lambda t, n=1: (_zero_si(_CURRENT["osv"]) if isinstance(t, type) and issubclass(t, SurfaceInteraction3f)
+                               else np.zeros(int(n), dtype=np.float32))
     dr.hint = lambda v, **kw: bool(np.any(v)) if isinstance(v, np.ndarray) else v
 
     class _Ctx:
@@ -1038,4 +1039,147 @@ def reference_render_nlos(our_scene, props, spp, seed=0):
     integ = mod.TransientNLOSPath(mi.Properties(**props))
     steady, transient = integ.render(scene, ref_sensor, seed=seed, spp=spp)
     LANES = None
+    return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Part 4 -- mitransient's own `angulararea` emitter (emitters/angulararea.py) executed inside the scene services:
+#  Scene::sample_emitter_direction / pdf_emitter_direction [upstream: emitter choice, visibility test] around the
+#  REFERENCE class's sample_direction / pdf_direction / eval; the shape underneath is the oracle's.
+# ---------------------------------------------------------------------------------------------------------
+class ShimEmitterBase(Object):
+    def __init__(self, props): self._shape = props.get("_shape")
+    def get_shape(self): return self._shape
+    def traverse(self, cb): pass
+    def parameters_changed(self, keys=None): pass
+
+
+class _ConstTexture:
+    def __init__(self, rgb): self.rgb = [np.float32(x) for x in rgb]
+    def eval(self, si, active=True): return LVec(*self.rgb)
+
+
+class _EmitterShape:
+    """mi.Shape of the emitter: sample_direction / pdf_direction through the oracle."""
+    def __init__(self, scene): self.scene = scene
+
+    def sample_direction(self, ref, sample, active=True):
+        n = LANES
+        dp, dn, dd, dist, pdf = _f(n, 3), _f(n, 3), _f(n, 3), _f(n), _f(n)
+        self.scene.osv.call("osv_shape_sample_direction", ref.p.arr(), sample.arr(), _mask(active), dp, dn, dd, dist, pdf)
+        ds = DirectionSample3f()
+        ds.p, ds.n, ds.d, ds.dist, ds.pdf = LVec.from_arr(dp), LVec.from_arr(dn), LVec.from_arr(dd), dist.view(DrArray), pdf.view(DrArray)
+        ds.delta, ds.emitter = LBool(False), None
+        return ds
+
+    def pdf_direction(self, ref, ds, active=True):
+        pdf = _f(LANES)
+        self.scene.osv.call("osv_shape_pdf_direction", ds.d.arr(), ds.n.arr(), _flt(ds.dist), _mask(active), pdf)
+        return pdf.view(DrArray)
+
+
+class _Frame3f:
+    def __init__(self, n): self.n = n
+
+    def to_local(self, v):
+        out = _f(LANES, 3); _CURRENT["osv"].call("osv_frame_to_local", self.n.arr(), v.arr(), out); return LVec.from_arr(out)
+    cos_theta = staticmethod(lambda v: v.z)
+
+
+def install_angular_services():
+    """install_scene_services() + what emitters/angulararea.py needs; returns (mi, dr, AngularAreaLight)."""
+    import mitransient_b200 as mitr
+    mi, dr = install_scene_services(False, mitr.ScalarTransform4f, mitr.ScalarColor3d)
+    mi.Emitter = ShimEmitterBase
+    mi.Frame3f = _Frame3f
+    mi.EmitterPtr = lambda e: e
+    mi.SurfaceInteraction3f = _SiFromDs
+    mi.Interaction3f = mi.TraversalCallback = mi.PositionSample3f = object
+    dr.deg2rad = lambda x: x * (np.pi / 180.0)                   # Python floats stay Python floats (double), like Dr.Jit
+    dr.cos = lambda x: float(np.cos(x)) if isinstance(x, float) else np.cos(np.asarray(x, dtype=np.float32))
+
+    def acos(x):
+        out = _f(LANES); _CURRENT["osv"].call("osv_acos", _flt(x), out); return out.view(DrArray)
+    dr.acos = acos
+    dr.normalize = lambda v: v * (np.float32(1.0) / np.sqrt(_dot(v, v)))
+    dr.dot = _dot
+    dr.square = lambda x: (np.asarray(x, dtype=np.float32) * np.asarray(x, dtype=np.float32)).view(DrArray)
+    mod = ref_module("mitransient.emitters.angulararea")
+    return mi, dr, mod.AngularAreaLight
+
+
+class _SiFromDs(SurfaceInteraction3f):
+    """mi.SurfaceInteraction3f(ds, wavelengths): only handed to Texture.eval by the emitter."""
+    def __init__(self, ds=None, wavelengths=None): pass
+
+
+class AngularScene(ShimScene):
+    """A scene whose single emitter is the reference's AngularAreaLight."""
+    def attach(self, emitter):
+        self.ref_emitter = emitter
+
+    def sample_emitter_direction(self, ref, sample, test_visibility=True, active=True):
+        ds, spec = self.ref_emitter.sample_direction(ref, sample, LBool(active))          # Scene: one emitter, pick pdf 1
+        if test_visibility:
+            ray = ref.spawn_ray_to(ds.p)
+            nz = (np.asarray(spec.x) != 0) | (np.asarray(spec.y) != 0) | (np.asarray(spec.z) != 0)
+            occluded = self.ray_test(ray, nz)
+            spec = sys.modules["drjit"].select(occluded, 0.0, spec)
+        return ds, spec
+
+    def pdf_emitter_direction(self, ref, ds, active=True):
+        has = np.asarray(ds._shape) == self._emitter_shape
+        return self.ref_emitter.pdf_direction(ref, ds, LBool(np.asarray(active, dtype=bool) & has))
+
+
+class _RefEmitterPtr:
+    def __init__(self, scene, shape): self.scene, self.shape = scene, shape
+
+    def eval(self, si, active=True):
+        has = np.asarray(self.shape) == self.scene._emitter_shape
+        return self.scene.ref_emitter.eval(si, LBool(np.broadcast_to(np.asarray(active, dtype=bool), (LANES,)) & has))
+
+
+def reference_render_angular(our_scene, props, spp, seed=0):
+    """render() + TransientPath.sample() + AngularAreaLight.{sample_direction, pdf_direction, eval}, all reference code."""
+    global LANES
+    LANES = None
+    mi, dr, AngularAreaLight = install_angular_services()
+    thf = ref_module("mitransient.films.transient_hdr_film")
+    mod = ref_module("mitransient.integrators.transientpath")
+    sensor = our_scene.sensors()[0]
+    f = sensor.film()
+    film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
+                                              start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
+    log = []
+    inner = film.add_transient_data
+
+    def logged(pos, distance, wavelengths, spec, ray_weight, active, **kw):
+        a = np.broadcast_to(np.asarray(active, dtype=bool), (LANES,))
+        val = spec * ray_weight
+        cols = [np.broadcast_to(np.asarray(c, dtype=np.float32), (LANES,)) for c in (pos.x, pos.y, distance, val.x, val.y, val.z)]
+        rec = np.stack(cols, axis=1).astype(np.float32)
+        log.append(rec[a & ((rec[:, 3] != 0) | (rec[:, 4] != 0) | (rec[:, 5] != 0))])
+        return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
+    film.add_transient_data = logged
+    _real_load = mi.load_dict
+    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    scene = AngularScene(our_scene, sensor)
+    _CURRENT["osv"] = scene.osv
+    em = our_scene.emitters()[0]
+    scene._emitter_shape = em["shape"]
+    deg = 180.0 / np.pi
+    ref_em = AngularAreaLight(mi.Properties(radiance=_ConstTexture(em["radiance"]), cutoff_angle=em["cutoff_angle"] * deg,
+                                            beam_width=em["beam_width"] * deg, _shape=_EmitterShape(scene)))
+    scene.attach(ref_em)
+    SurfaceInteraction3f.emitter = lambda self, sc=None: _RefEmitterPtr(scene, self.shape)
+    try:
+        shim_sensor = ShimSensor(film, spp)
+        shim_sensor._sampler.base_seed = sensor.sampler().base_seed
+        scene.sensors = lambda: [shim_sensor]
+        integ = mod.TransientPath(mi.Properties(**props))
+        steady, transient = integ.render(scene, shim_sensor, seed=seed, spp=spp)
+    finally:
+        SurfaceInteraction3f.emitter = lambda self, sc=None: EmitterPtr(self.osv, self.shape)
+        LANES = None
     return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)

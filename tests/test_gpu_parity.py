@@ -233,3 +233,28 @@ def test_too_many_samples_is_rejected_like_the_reference_splits(mitr):
     rc = _lib.load().tr_render(dev.handle, C.byref(p), film.transient_storage.data_ptr(), film.steady_storage.data_ptr(),
                                None, _lib.current_stream_ptr())
     assert rc == mitr._abi.TR_ERR_INVALID_ARGUMENT and b"2^32" in _lib.load().tr_last_error()
+
+
+def test_multi_pass_accumulation(mitr, oracle):
+    """Two passes into the same film (what prepare() produces above 2^32 samples, common.py:56-85): pass 2 adds to
+    pass 1 (`accumulate`), both scaled by 1 / total_spp."""
+    import ctypes as C
+    from mitransient_b200 import _lib
+    from oracle import oracle as o
+    scene = mitr.load_dict(mitr.cornell_box_config(24, 16, 96, 8))
+    integ, sensor = scene.integrator(), scene.sensors()[0]
+    film = sensor.film()
+    film.prepare()
+    dev = integ.device_scene(scene, sensor)
+    desc = scene.describe(sensor)
+    ref_film = np.zeros((16, 24, 96, 4), np.float32); ref_steady = np.zeros((16, 24, 3), np.float32)
+    for i, (seed_i, spp_i) in enumerate(((123, 8), (77, 5))):
+        p = integ.make_params(spp_i, 13, seed_i, accumulate=(i > 0))
+        _lib.check(_lib.load().tr_render(dev.handle, C.byref(p), film.transient_storage.data_ptr(), film.steady_storage.data_ptr(),
+                                         None, _lib.current_stream_ptr()))
+        cnt = mitr._abi.TrCounters()
+        o._check(o.load().oracle_render(C.byref(desc), C.byref(p), ref_film.ctypes.data, ref_steady.ctypes.data, C.byref(cnt), 0, None, 0, None))
+    raw = film.develop(raw=True)[1].cpu().numpy()
+    err = film_l1(raw, ref_film)
+    assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL, err
+    np.testing.assert_allclose(film.steady_storage.cpu().numpy(), ref_steady, rtol=1e-4, atol=1e-6)

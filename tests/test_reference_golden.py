@@ -254,3 +254,33 @@ def test_gpu_nlos_render_equals_the_reference_integrator(mitr, name):
     assert integ.last_counters["deposits"] == len(GP[name + "_deposits"])
     assert raw.shape == ref.shape and np.array_equal(raw != 0, ref != 0)
     assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
+
+
+# ------------------------------------------------------------------------------------------ angulararea emitter
+from path_cases import ANGULAR_CASES, angular_case_scene  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(ANGULAR_CASES))
+def test_oracle_angulararea_equals_the_reference_emitter(mitr, oracle, name):
+    """AngularAreaLight.sample_direction / pdf_direction / eval / _fallof_curve (emitters/angulararea.py:73-141) were
+    EXECUTED inside the reference's transient_path loop; oracle deposits bit for bit."""
+    scene, cfg, _ = angular_case_scene(name)
+    r = oracle.render(scene, scene.integrator(), spp=cfg[3], seed=2, log_deposits=1 << 20)
+    assert len(GP[name + "_deposits"]) > 100
+    assert np.array_equal(sort_rows(r["deposits"]), GP[name + "_deposits"])
+    np.testing.assert_allclose(r["steady"], GP[name + "_steady"], rtol=3e-7, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(ANGULAR_CASES))
+def test_gpu_angulararea_equals_the_reference_emitter(mitr, name):
+    scene, cfg, _ = angular_case_scene(name)
+    integ = scene.integrator()
+    integ.collect_counters = True
+    steady, _ = integ.render(scene, spp=cfg[3], seed=2)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = GP[name + "_raw"]
+    assert integ.last_counters["deposits"] == len(GP[name + "_deposits"])
+    assert np.array_equal(raw != 0, ref != 0)
+    assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
+    np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)

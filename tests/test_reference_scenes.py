@@ -14,10 +14,9 @@ SUPPORTED = ["transient/cornell-box/cbox_diffuse.xml", "transient/cornell-box/cb
              "transient/cornell-box/cbox_volumetric.xml", "transient/cornell-box/cbox_diffuse_freq.xml",
              "diff-transient/cornell-box/cbox_volumetric.xml", "transient-nlos/nlos_Z.xml",
              "transient-nlos/nlos-z-simple.xml", "transient-nlos/nlos-z-room.xml",
-             "angulararea-emitter/scenes/area_1light.xml"]
+             "angulararea-emitter/scenes/area_1light.xml", "angulararea-emitter/scenes/angular_1light.xml"]
 # what the others need (documented in DESIGN.md, "Scope")
-UNSUPPORTED = {"angulararea-emitter/scenes/angular_1light.xml": "angulararea",
-               "polarization/cornell-box/cbox_polarized.xml": "roughconductor",
+UNSUPPORTED = {"polarization/cornell-box/cbox_polarized.xml": "roughconductor",
                "polarization/cornell-box/cbox_polarized_steady.xml": "stokes",
                "diff-transient/staircase/scene.xml": ""}
 
