@@ -47,12 +47,18 @@ NLOS_CASES = {
     "nlos_g": ((6, 6, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, (3, 3), 60.0, False),
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
+    # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point
+    "nlos_j": ((1, 1, 128, 256), {"capture_type": "single", "start_opl": 0.0, "window": 8.0, "original_film": (8, 8)}, (5, 3), None, False),
 }
 
 
 def nlos_case_scene(name):
     cfg, kw, focus, fov, exhaustive = NLOS_CASES[name]
+    kw = dict(kw)
+    original = kw.pop("original_film", None)
     d = mitr.nlos_z_scene(*cfg, **kw)
+    if original is not None:
+        d["relay_wall"]["nlos_sensor"]["original_film_width"], d["relay_wall"]["nlos_sensor"]["original_film_height"] = original
     if fov is not None:
         d["emitter"]["fov"] = fov
     if exhaustive:

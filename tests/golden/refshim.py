@@ -509,17 +509,17 @@ class BSDFPtr:
 
     def flags(self):
         sm, nl = np.zeros(LANES, np.uint8), np.zeros(LANES, np.uint8)
-        self.osv.call("osv_bsdf_smooth", self.shape, sm, nl)
+        self.osv.call("osv_bsdf_smooth", _i32(self.shape), sm, nl)
         return np.where(sm != 0, BSDFPtr.Smooth, BSDFPtr.Delta).astype(np.int64).view(DrArray)
 
     def eval_pdf(self, ctx, si, wo, active=True):
         val, pdf = _f(LANES, 3), _f(LANES)
-        self.osv.call("osv_bsdf_eval_pdf", self.shape, si.wi.arr(), wo.arr(), _mask(active), val, pdf)
+        self.osv.call("osv_bsdf_eval_pdf", _i32(self.shape), si.wi.arr(), wo.arr(), _mask(active), val, pdf)
         return LVec.from_arr(val), pdf.view(DrArray)
 
     def sample(self, ctx, si, sample1, sample2, active=True):
         wo, pdf, eta, delta, w = _f(LANES, 3), _f(LANES), _f(LANES), np.zeros(LANES, np.uint8), _f(LANES, 3)
-        self.osv.call("osv_bsdf_sample", self.shape, si.wi.arr(), _flt(sample1), sample2.arr(), _mask(active), wo, pdf, eta, delta, w)
+        self.osv.call("osv_bsdf_sample", _i32(self.shape), si.wi.arr(), _flt(sample1), sample2.arr(), _mask(active), wo, pdf, eta, delta, w)
         bs = types.SimpleNamespace(wo=LVec.from_arr(wo), pdf=pdf.view(DrArray), eta=eta.view(DrArray),
                                    sampled_type=np.where(delta != 0, BSDFPtr.Delta, BSDFPtr.Smooth).astype(np.int64).view(DrArray))
         return bs, LVec.from_arr(w)
@@ -530,7 +530,7 @@ class EmitterPtr:
 
     def eval(self, si, active=True):
         rgb = _f(LANES, 3)
-        self.osv.call("osv_emitter_eval", self.shape, si.wi.arr(), _mask(active), rgb)
+        self.osv.call("osv_emitter_eval", _i32(self.shape), si.wi.arr(), _mask(active), rgb)
         return LVec.from_arr(rgb)
 
 
@@ -616,7 +616,7 @@ class ShimScene:
 
     def pdf_emitter_direction(self, ref, ds, active=True):
         pdf = _f(LANES)
-        self.osv.call("osv_pdf_emitter_direction", ds._shape, ds.d.arr(), ds.n.arr(), _flt(ds.dist), _mask(active), pdf)
+        self.osv.call("osv_pdf_emitter_direction", _i32(ds._shape), ds.d.arr(), ds.n.arr(), _flt(ds.dist), _mask(active), pdf)
         return pdf.view(DrArray)
 
 
@@ -1032,8 +1032,13 @@ def reference_render_nlos(our_scene, props, spp, seed=0):
     _CURRENT["osv"] = scene.osv
     wall_index = int(scene.osv.lib.osv_sensor_shape(C.c_void_p(scene.osv.h)))
     sampler = ShimSampler(spp); sampler.base_seed = sensor.sampler().base_seed
+    extra = {}
+    if sensor.is_confocal:                                    # 1x1 film aimed at laser_target (nloscapturemeter.py:113-125)
+        extra = {"original_film_width": sensor.original_film_width, "original_film_height": sensor.original_film_height}
     ref_sensor = meter.NLOSCaptureMeter(mi.Properties(sensor_origin=VecF(*[float(x) for x in sensor._world_transform.translation()]), _film=film,
-                                                      _sampler=sampler, _shape=ShapeShim(scene, wall_index)))
+                                                      _sampler=sampler, _shape=ShapeShim(scene, wall_index), **extra))
+    if sensor.is_confocal:                                    # what mitransient.nlos.focus_emitter_at_relay_wall_* sets (nlos.py:28-34)
+        ref_sensor.laser_target = LVec(*[np.float32(x) for x in np.asarray(sensor.laser_target, dtype=np.float64)])
     scene.sensors = lambda: [ref_sensor]
     LANES = int(f.size()[0]) * int(f.size()[1])            # width of the prepare() phase: one lane per film pixel
     integ = mod.TransientNLOSPath(mi.Properties(**props))

@@ -143,9 +143,9 @@ def test_gpu_film_kernels_equal_reference(mitr, tag):
     raw = film.develop(raw=True)[1].cpu().numpy()
     ref = G[tag + "_raw"]
     assert np.array_equal(raw != 0, ref != 0)
-    assert np.abs(raw - ref).sum() <= 1e-6 * np.abs(ref).sum()
+    assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()       # film_c: 5000 deposits into ONE bin, atomics in any order
     dev = film.develop()[1].cpu().numpy()
-    assert np.abs(dev - G[tag + "_developed"]).sum() <= 1e-6 * np.abs(ref).sum()
+    assert np.abs(dev - G[tag + "_developed"]).sum() <= 1e-5 * np.abs(ref).sum()
 
 
 # ------------------------------------------------------------------------------------------ the integrator loop
