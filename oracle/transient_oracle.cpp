@@ -716,7 +716,9 @@ inline V3 bsdf_eval_pdf(const TrBsdfDesc &b, V3 wi, V3 wo, float *pdf) {
 inline BsdfSampleRec bsdf_sample(const TrBsdfDesc &b, V3 wi, float s1, float s2x, float s2y) {
     BsdfSampleRec r; r.wo = v3(0, 0, 0); r.weight = v3(0, 0, 0); r.pdf = 0.0f; r.eta = 1.0f; r.delta = false;
     const bool twosided = (b.flags & TR_BSDF_FLAG_TWOSIDED) != 0;
-    if (b.type == TR_BSDF_DIFFUSE) {
+    if (b.type == TR_BSDF_NULL) {                              // null.cpp: pass straight through, bs.wo = -si.wi
+        r.wo = -wi; r.weight = v3(1, 1, 1); r.pdf = 1.0f; r.delta = true;
+    } else if (b.type == TR_BSDF_DIFFUSE) {
         const bool flip = twosided && wi.z < 0.0f;
         const float cos_i_eff = flip ? -wi.z : wi.z;
         V3 wo = square_to_cosine_hemisphere(s2x, s2y);
@@ -1288,7 +1290,8 @@ V3 trace_volpath(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
             if (!act) break;
             dsum = dsum + h.t;
             act = sc.bsdfs[sc.shapes[h.shape].d.bsdf].type == TR_BSDF_NULL;
-            r = Ray{fma3(r.d, kRayEpsilon * 2.0f, h.p), r.d, std::numeric_limits<float>::max()};
+            const float e2 = kRayEpsilon * 2.0f;       // newOrigin = si.p + ray.d * RayEpsilon * 2  (:526, Python level: not fused)
+            r = Ray{v3(h.p.x + r.d.x * e2, h.p.y + r.d.y * e2, h.p.z + r.d.z * e2), r.d, std::numeric_limits<float>::max()};
         }
         distance = -dsum;
     }
@@ -1388,20 +1391,14 @@ V3 trace_volpath(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
         }
         // ---- BSDF sampling :364-408
         if (active_surface) {
-            float b1 = rng.next_1d(); (void) b1;
+            float b1 = rng.next_1d();
             float b2x = rng.next_1d(), b2y = rng.next_1d();
-            V3 wo_world; V3 bw = v3(0, 0, 0); float bs_pdf; bool is_null = bsdf->type == TR_BSDF_NULL;
-            if (is_null) {                                                         // Null BSDF: straight through
-                wo_world = ray.d; bw = v3(1, 1, 1); bs_pdf = 1.0f;
-            } else {
-                V3 wo = square_to_cosine_hemisphere(b2x, b2y);
-                bs_pdf = kInvPi * wo.z;
-                bool two_back = (bsdf->flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f;
-                float ci = two_back ? -cos_i : cos_i;
-                if (smooth && ci > 0.0f && bs_pdf > 0.0f) bw = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
-                if (two_back) wo.z = -wo.z;
-                wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));
-            }
+            const bool is_null = bsdf->type == TR_BSDF_NULL;
+            // bsdf.sample in the local frame (null.cpp: bs.wo = -si.wi, so the world direction is a frame round trip of ray.d)
+            V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));
+            BsdfSampleRec bs = bsdf_sample(*bsdf, wi, b1, b2x, b2y);
+            V3 bw = bs.weight; float bs_pdf = bs.pdf;
+            V3 wo_world = fma3(si.n, bs.wo.z, fma3(si.tt, bs.wo.y, si.s * bs.wo.x));   // si.to_world(bs.wo)
             active_surface = bs_pdf > 0.0f;                                        // :370
             if (active_surface) {
                 beta = beta * bw;                                                  // :386
@@ -1764,6 +1761,52 @@ void osv_shape_sample_position(void *h, uint64_t n, const int32_t *shape, const 
         st3(p, i, pp); st3(nrm, i, pn); pdf[i] = ppdf;
     }
 }
+// ---- services used by transient_prbvolpath (transient_prbvolpath.py): homogeneous media, HG phase function, medium transitions
+void osv_medium_sample_interaction(void *h, uint64_t n, const int32_t *medium, const float *o, const float *d, const float *maxt,
+                                   const float *u, const int32_t *channel, const uint8_t *active, uint8_t *valid, float *t, float *p,
+                                   float *sigma_t, float *sigma_s) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        valid[i] = 0; t[i] = kInf; st3(p, i, v3(0, 0, 0)); st3(sigma_t, i, v3(0, 0, 0)); st3(sigma_s, i, v3(0, 0, 0));
+        if (!active[i] || medium[i] < 0) continue;
+        MediumEvent me = medium_sample_interaction(sc, medium[i], Ray{ld3(o, i), ld3(d, i), maxt[i]}, u[i], (uint32_t) channel[i]);
+        valid[i] = me.valid; t[i] = me.t; st3(p, i, me.p); st3(sigma_t, i, me.sigma_t); st3(sigma_s, i, me.sigma_s);
+    }
+}
+void osv_medium_transmittance(void *, uint64_t n, const float *mei_t, const float *sigma_t, const float *si_t, const uint8_t *active, float *tr,
+                              float *pdf) {
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a = v3(0, 0, 0), b = v3(0, 0, 0);
+        if (active[i]) { MediumEvent me; me.t = mei_t[i]; me.mint = 0.0f; me.sigma_t = ld3(sigma_t, i); medium_transmittance_eval_pdf(me, si_t[i], &a, &b); }
+        st3(tr, i, a); st3(pdf, i, b);
+    }
+}
+void osv_phase_eval(void *h, uint64_t n, const int32_t *medium, const float *wi, const float *wo, const uint8_t *active, float *val) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) val[i] = (active[i] && medium[i] >= 0) ? hg_eval(sc.media[medium[i]].g, dot(ld3(wo, i), ld3(wi, i))) : 0.0f;
+}
+void osv_phase_sample(void *h, uint64_t n, const int32_t *medium, const float *wi, const float *s2, const uint8_t *active, float *wo, float *pdf) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 w = v3(0, 0, 0); pdf[i] = 0.0f;
+        if (active[i] && medium[i] >= 0) w = hg_sample(sc.media[medium[i]].g, ld3(wi, i), s2[2 * i], s2[2 * i + 1], &pdf[i]);
+        st3(wo, i, w);
+    }
+}
+void osv_target_medium(void *h, uint64_t n, const int32_t *shape, const float *nrm, const float *d, int32_t *out, uint8_t *transition) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) {
+        out[i] = -1; transition[i] = 0;
+        if (shape[i] < 0) continue;
+        Hit si; si.shape = (uint32_t) shape[i]; si.n = ld3(nrm, i);
+        out[i] = target_medium(sc, si, ld3(d, i)); transition[i] = is_medium_transition(sc, si);
+    }
+}
+void osv_shape_emitter(void *h, uint64_t n, const int32_t *shape, int32_t *emitter) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    for (uint64_t i = 0; i < n; ++i) emitter[i] = shape[i] >= 0 ? sc.shapes[shape[i]].d.emitter : -1;
+}
+int32_t osv_sensor_medium(void *h) { return ((OsvScene *) h)->sc.sensor.medium; }
 void osv_acos(void *, uint64_t n, const float *x, float *out) { for (uint64_t i = 0; i < n; ++i) out[i] = acos_cephes(x[i]); }
 void osv_frame_to_local(void *, uint64_t n, const float *nrm, const float *v, float *out) {
     for (uint64_t i = 0; i < n; ++i) st3(out, i, frame_to_local(ld3(nrm, i), ld3(v, i)));

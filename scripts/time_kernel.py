@@ -19,6 +19,7 @@ ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol"])
+ap.add_argument("--world", type=int, default=1, help="render only the tiles of rank 0 of `world` ranks (the per-GPU share of an N-GPU job)")
 a = ap.parse_args()
 if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256 x 4096 bins, 1024 spp
     a.width = a.height = 256 if a.width == 512 else a.width
@@ -35,7 +36,7 @@ dev = integ.device_scene(scene, sensor)
 lib = _lib.load()
 film = torch.zeros((a.height, a.width, a.bins, 4), dtype=torch.float32, device="cuda")
 steady = torch.zeros((a.height, a.width, 3), dtype=torch.float32, device="cuda")
-params = integ.make_params(a.spp, a.spp, 0)
+params = integ.make_params(a.spp, a.spp, 0, rank=0, world=a.world)
 integ.fill_params_(params, scene, sensor)
 st = torch.cuda.current_stream()
 for _ in range(3):
@@ -49,4 +50,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 print(f"{os.environ.get('MITRANSIENT_B200_LIB', 'default'):40s} {ms:8.3f} ms/step  "
-      f"{a.width * a.height * a.spp / ms / 1e3:9.1f} M-paths/s  film.sum={film.sum().item():.6e}")
+      f"{a.width * a.height * a.spp / a.world / ms / 1e3:9.1f} M-paths/s  film.sum={film.sum().item():.6e}")

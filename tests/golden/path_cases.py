@@ -85,3 +85,23 @@ def angular_case_scene(name):
     d["light"]["emitter"] = {"type": "angulararea", "radiance": {"type": "rgb", "value": [18.387, 10.9873, 2.75357]},
                              "cutoff_angle": cutoff, "beam_width": beam}
     return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
+
+
+# ---- transient_prbvolpath: (film, integrator overrides, volumetric scene?)
+VOL_CASES = {
+    "vol_a": ((6, 6, 48, 8), {"max_depth": 6}, True),
+    "vol_b": ((6, 6, 48, 8), {"max_depth": 12, "camera_unwarp": True, "rr_depth": 2}, True),
+    "vol_c": ((5, 7, 48, 16), {"max_depth": -1, "rr_depth": 1, "hide_emitters": True}, True),
+    "vol_d": ((6, 6, 48, 8), {"max_depth": 6}, False),          # no medium at all: the surface-only branch of the same loop
+}
+
+
+def vol_case_scene(name):
+    cfg, integ, volumetric = VOL_CASES[name]
+    if volumetric:
+        d = mitr.cornell_box_volumetric(*cfg, max_depth=8)
+    else:
+        d = mitr.cornell_box_config(*cfg, max_depth=8)
+        d["integrator"]["type"] = "transient_prbvolpath"
+    d["integrator"].update(integ)
+    return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}

@@ -1188,3 +1188,271 @@ def reference_render_angular(our_scene, props, spp, seed=0):
         SurfaceInteraction3f.emitter = lambda self, sc=None: EmitterPtr(self.osv, self.shape)
         LANES = None
     return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Part 5 -- transient_prbvolpath (integrators/transient_prbvolpath.py): media, phase functions, masked struct
+#  assignment (si[mask] = ..., ray[mask] = ..., medium[mask] = ...), lane-wise `while <array>`.
+# ---------------------------------------------------------------------------------------------------------
+class Struct:
+    """A Dr.Jit struct of lane arrays: s[mask] is a copy, s[mask] = other assigns lane-wise, field by field."""
+    _fields = ()
+
+    def __getitem__(self, k):
+        return _copy.copy(self)
+
+    def __setitem__(self, k, other):
+        k = np.asarray(k, dtype=bool)
+        for f in self._fields:
+            if not hasattr(other, f):
+                continue
+            a, b = getattr(self, f), getattr(other, f)
+            if isinstance(a, Vec) or isinstance(b, Vec):
+                av = a if isinstance(a, Vec) else LVec(a)
+                bv = b if isinstance(b, Vec) else LVec(b)
+                out = LVec.__new__(LVec)
+                out.c = tuple(np.where(k, np.asarray(y, dtype=np.float32), np.asarray(x, dtype=np.float32)).view(DrArray) for x, y in zip(av.c, bv.c))
+                setattr(self, f, out)
+            else:
+                setattr(self, f, np.where(k, np.asarray(b), np.asarray(a)).view(DrArray))
+
+
+class VSurfaceInteraction(SurfaceInteraction3f, Struct):
+    _fields = ("valid", "t", "p", "n", "s", "tt", "wi", "shape", "time")
+
+    def emitter(self, scene=None): return VEmitterPtr(self.osv, _i32(self.shape))
+
+    def _medium_info(self, d):
+        tgt, tr = np.zeros(LANES, np.int32), np.zeros(LANES, np.uint8)
+        self.osv.call("osv_target_medium", _i32(self.shape), self.n.arr(), d.arr(), tgt, tr)
+        return tgt, tr
+
+    def target_medium(self, d): return MediumPtr(self.osv, self._medium_info(d)[0])
+    def is_medium_transition(self): return (self._medium_info(LVec(0.0))[1] != 0).view(DrArray)
+
+    def spawn_ray_to(self, target): return VRay(SurfaceInteraction3f.spawn_ray_to(self, target))
+    def spawn_ray(self, d): return VRay(SurfaceInteraction3f.spawn_ray(self, d))
+
+
+class VInteraction(Struct):
+    """mi.Interaction3f: a position and a normal (zero for medium interactions: spawn_ray_to then applies no offset)."""
+    _fields = ("p", "n", "time")
+
+    def __init__(self, osv): self.osv, self.p, self.n, self.time = osv, LVec(0.0), LVec(0.0), LFloat(0.0)
+
+    def spawn_ray_to(self, target):
+        o, d, maxt = _f(LANES, 3), _f(LANES, 3), _f(LANES)
+        self.osv.call("osv_spawn_ray_to", self.p.arr(), self.n.arr(), target.arr(), o, d, maxt)
+        return VRay(Ray3f(LVec.from_arr(o), LVec.from_arr(d), maxt.view(DrArray)))
+
+
+class VRay(Ray3f, Struct):
+    _fields = ("o", "d", "maxt")
+
+    def __init__(self, o=None, d=None, time=None, wavelengths=None):
+        if isinstance(o, Ray3f):
+            self.o, self.d = LVec(o.o), LVec(o.d)
+            self.maxt = np.broadcast_to(np.asarray(o.maxt, dtype=np.float32), (LANES,)).copy().view(DrArray)
+        else:                                               # Ray3f(o, d, time, wavelengths): maxt = largest float
+            self.o, self.d = LVec(o), LVec(d)
+            self.maxt = LFloat(np.finfo(np.float32).max)
+        self.time, self.wavelengths = LFloat(0.0), None
+
+
+class VEmitterPtr(EmitterPtr):
+    def __ne__(self, other):
+        em = np.zeros(LANES, np.int32); self.osv.call("osv_shape_emitter", _i32(self.shape), em)
+        return (em >= 0).view(DrArray)
+    __hash__ = None
+
+
+class MediumInteraction(Struct):
+    _fields = ("t", "p", "n", "sigma_t", "sigma_s", "sigma_n", "combined_extinction", "wi", "time", "_valid", "_medium")
+
+    def is_valid(self): return (np.asarray(self.t) < np.inf).view(DrArray)        # MediumInteraction::is_valid(): t < inf
+    @property
+    def medium(self): return MediumPtr(self.osv, self._medium)
+
+    def spawn_ray(self, wo):
+        return VRay(Ray3f(self.p, wo, LFloat(np.finfo(np.float32).max)))
+
+
+class PhasePtr:
+    def __init__(self, osv, idx): self.osv, self.idx = osv, np.asarray(idx, dtype=np.int32)
+    def __getitem__(self, k): return PhasePtr(self.osv, self.idx.copy())
+    def __setitem__(self, k, other): self.idx = np.where(np.asarray(k, dtype=bool), other.idx, self.idx).astype(np.int32)
+
+    def eval_pdf(self, ctx, mei, wo, active=True):
+        val = _f(LANES)
+        self.osv.call("osv_phase_eval", _i32(self.idx), mei.wi.arr(), wo.arr(), _mask(active), val)
+        return val.view(DrArray), val.copy().view(DrArray)
+
+    def sample(self, ctx, mei, s1, s2, active=True):
+        wo, pdf = _f(LANES, 3), _f(LANES)
+        self.osv.call("osv_phase_sample", _i32(self.idx), mei.wi.arr(), s2.arr(), _mask(active), wo, pdf)
+        return LVec.from_arr(wo), LFloat(1.0), pdf.view(DrArray)                      # HG: sampled exactly, weight 1
+
+
+class MediumPtr:
+    def __init__(self, osv, idx): self.osv, self.idx = osv, np.broadcast_to(np.asarray(idx, dtype=np.int32), (LANES,)).copy()
+    def __ne__(self, other): return (self.idx >= 0).view(DrArray)
+    def __eq__(self, other): return (self.idx < 0).view(DrArray)
+    __hash__ = None
+    def __getitem__(self, k): return MediumPtr(self.osv, self.idx.copy())
+    def __setitem__(self, k, other): self.idx = np.where(np.asarray(k, dtype=bool), other.idx, self.idx).astype(np.int32)
+    def is_homogeneous(self): return LBool(True)
+    def use_emitter_sampling(self): return LBool(True)
+    def phase_function(self): return PhasePtr(self.osv, self.idx.copy())
+
+    def sample_interaction(self, ray, u, channel, active=True):
+        n = LANES
+        valid, t, p, st, ss = np.zeros(n, np.uint8), _f(n), _f(n, 3), _f(n, 3), _f(n, 3)
+        self.osv.call("osv_medium_sample_interaction", _i32(self.idx), ray.o.arr(), ray.d.arr(), _flt(ray.maxt), _flt(u),
+                      _i32(channel), _mask(active), valid, t, p, st, ss)
+        mei = MediumInteraction(); mei.osv = self.osv
+        mei.t, mei.p, mei.n = t.view(DrArray), LVec.from_arr(p), LVec(0.0)
+        mei.sigma_t, mei.sigma_s, mei.sigma_n, mei.combined_extinction = LVec.from_arr(st), LVec.from_arr(ss), LVec(0.0), LVec.from_arr(st)
+        mei.wi, mei.time, mei._valid, mei._medium = -ray.d, LFloat(0.0), valid != 0, self.idx.copy()
+        return mei
+
+    def transmittance_eval_pdf(self, mei, si, active=True):
+        tr, pdf = _f(LANES, 3), _f(LANES, 3)
+        self.osv.call("osv_medium_transmittance", _flt(mei.t), mei.sigma_t.arr(), _flt(si.t), _mask(active), tr, pdf)
+        return LVec.from_arr(tr), LVec.from_arr(pdf)
+
+
+class VScene(ShimScene):
+    def ray_intersect(self, ray, active=True, **kw):
+        si0 = ShimScene.ray_intersect(self, ray)
+        si = VSurfaceInteraction(); si.__dict__.update(si0.__dict__)
+        si.shape = np.asarray(si.shape, dtype=np.int32).view(DrArray)
+        if isinstance(active, np.ndarray):                        # scene.ray_intersect(ray, active): inactive lanes = no hit
+            a = np.asarray(active, dtype=bool)
+            si.valid = (np.asarray(si.valid) & a).view(DrArray)
+            si.t = np.where(a, si.t, np.float32(np.inf)).view(DrArray)
+            si.shape = np.where(a, si.shape, -1).astype(np.int32).view(DrArray)
+        return si
+
+    def shapes(self):
+        media = [(int(self.our_scene.shapes()[i].interior_medium), int(self.our_scene.shapes()[i].exterior_medium))
+                 for i in range(len(self.our_scene.shapes()))]
+        mk = lambda m: (types.SimpleNamespace(use_emitter_sampling=lambda: True, is_homogeneous=lambda: True) if m >= 0 else None)
+        return [types.SimpleNamespace(interior_medium=(lambda a=a: mk(a)), exterior_medium=(lambda b=b: mk(b))) for a, b in media]
+
+
+def _rewrite_syntax_vol(fn):
+    """dr.syntax for the volumetric integrator: array-`if`s (as above) and `while <array>:` -> `while any(array):`."""
+    src = textwrap.dedent(inspect.getsource(fn))
+    tree = ast.parse(src)
+    fdef = tree.body[0]
+    fdef.decorator_list = []
+
+    class W(ast.NodeTransformer):
+        def visit_While(self, node):
+            self.generic_visit(node)
+            node.test = ast.Call(func=ast.Name(id="__shim_any", ctx=ast.Load()), args=[node.test], keywords=[])
+            return node
+    tree = ast.fix_missing_locations(W().visit(tree))
+    g = fn.__globals__
+    g["__shim_any"] = lambda c: bool(np.any(c))
+    loc = {}
+    exec(compile(tree, inspect.getsourcefile(fn), "exec"), g, loc)
+    return loc[fdef.name]
+
+
+def reference_render_vol(our_scene, props, spp, seed=0):
+    """Run the REFERENCE'S render() + TransientPRBVolpathIntegrator.sample / sample_emitter / first_surface."""
+    import mitransient_b200 as mitr
+    global LANES
+    LANES = None
+    mi, dr = install_scene_services(False, mitr.ScalarTransform4f, mitr.ScalarColor3d)
+    mi.is_rgb = True
+    mi.MediumPtr, mi.PhaseFunctionPtr, mi.Interaction3f = "MediumPtr", "PhaseFunctionPtr", "Interaction3f"
+    mi.PhaseFunctionContext = lambda *a, **k: None
+    mi.SurfaceInteraction3f = VSurfaceInteraction
+    mi.Ray3f = mi.RayDifferential3f = VRay
+    mi.Mask = LBool
+    mi.math = types.SimpleNamespace(RayEpsilon=np.float32(8.940696716308594e-05))
+    mi.BSDFFlags.Null = 0x8
+    dr.size_v = lambda t: 3
+    dr.syntax = lambda f=None, **kw: (_rewrite_syntax_vol(f) if f is not None else (lambda g: _rewrite_syntax_vol(g)))
+    dr.square = lambda x: (np.asarray(x, dtype=np.float32) * np.asarray(x, dtype=np.float32)).view(DrArray)
+    osv_holder = {}
+    base_zeros = dr.zeros
+
+    def zeros(t, n=1):
+        if t == "MediumPtr": return MediumPtr(osv_holder["osv"], -1)
+        if t == "PhaseFunctionPtr": return PhasePtr(osv_holder["osv"], np.full(LANES, -1, np.int32))
+        if t == "Interaction3f": return VInteraction(osv_holder["osv"])
+        if isinstance(t, type) and issubclass(t, SurfaceInteraction3f):
+            si = VSurfaceInteraction(); si.__dict__.update(_zero_si(osv_holder["osv"]).__dict__)
+            si.shape = np.full(LANES, -1, np.int32).view(DrArray); si.time = LFloat(0.0)
+            si.p = si.n = si.s = si.tt = si.wi = LVec(LFloat(0.0), LFloat(0.0), LFloat(0.0))
+            return si
+        return base_zeros(t, n)
+    dr.zeros = zeros
+    base_select = dr.select
+
+    def select(m, a, b):
+        if isinstance(a, MediumPtr) and isinstance(b, MediumPtr):
+            return MediumPtr(a.osv, np.where(np.asarray(m, dtype=bool), a.idx, b.idx))
+        if isinstance(a, np.ndarray) and a.dtype.kind in "iu" and not isinstance(b, Vec):
+            return np.where(m, a, b).view(DrArray)
+        return base_select(m, a, b)
+    dr.select = select
+    dr.any = lambda v: np.logical_or.reduce([np.broadcast_to(np.asarray(x), (LANES,)) for x in v.c]).view(DrArray) if isinstance(v, Vec) else np.any(v)
+    Vec.__ne__ = lambda self, o: self._zip(o, lambda a, b: a != b)
+
+    # BSDFPtr additions: Null flag, eval_null_transmission
+    def flags(self):
+        sm, nl = np.zeros(LANES, np.uint8), np.zeros(LANES, np.uint8)
+        self.osv.call("osv_bsdf_smooth", _i32(self.shape), sm, nl)
+        return np.where(sm != 0, BSDFPtr.Smooth, np.where(nl != 0, 0x8 | BSDFPtr.Delta, BSDFPtr.Delta)).astype(np.int64).view(DrArray)
+
+    def sample(self, ctx, si, sample1, sample2, active=True):
+        wo, pdf, eta, delta, w = _f(LANES, 3), _f(LANES), _f(LANES), np.zeros(LANES, np.uint8), _f(LANES, 3)
+        self.osv.call("osv_bsdf_sample", _i32(self.shape), si.wi.arr(), _flt(sample1), sample2.arr(), _mask(active), wo, pdf, eta, delta, w)
+        fl = self.flags()
+        st = np.where(np.asarray(fl) & 0x8, 0x8 | BSDFPtr.Delta, np.where(delta != 0, BSDFPtr.Delta, BSDFPtr.Smooth)).astype(np.int64).view(DrArray)
+        return types.SimpleNamespace(wo=LVec.from_arr(wo), pdf=pdf.view(DrArray), eta=eta.view(DrArray), sampled_type=st), LVec.from_arr(w)
+
+    def eval_null_transmission(self, si, active=True):
+        sm, nl = np.zeros(LANES, np.uint8), np.zeros(LANES, np.uint8)
+        self.osv.call("osv_bsdf_smooth", _i32(self.shape), sm, nl)
+        v = np.where((nl != 0) & np.broadcast_to(np.asarray(active, dtype=bool), (LANES,)), np.float32(1), np.float32(0))
+        return LVec(v, v, v)
+    saved = (BSDFPtr.flags, BSDFPtr.sample)
+    BSDFPtr.flags, BSDFPtr.sample, BSDFPtr.eval_null_transmission = flags, sample, eval_null_transmission
+    try:
+        thf = ref_module("mitransient.films.transient_hdr_film")
+        mod = ref_module("mitransient.integrators.transient_prbvolpath")
+        sensor = our_scene.sensors()[0]
+        f = sensor.film()
+        film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
+                                                  start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
+        log = []
+        inner = film.add_transient_data
+
+        def logged(pos, distance, wavelengths, spec, ray_weight, active, **kw):
+            a = np.broadcast_to(np.asarray(active, dtype=bool), (LANES,))
+            val = spec * ray_weight
+            cols = [np.broadcast_to(np.asarray(c, dtype=np.float32), (LANES,)) for c in (pos.x, pos.y, distance, val.x, val.y, val.z)]
+            rec = np.stack(cols, axis=1).astype(np.float32)
+            log.append(rec[a & ((rec[:, 3] != 0) | (rec[:, 4] != 0) | (rec[:, 5] != 0))])
+            return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
+        film.add_transient_data = logged
+        _real_load = mi.load_dict
+        mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+        scene = VScene(our_scene, sensor)
+        _CURRENT["osv"] = osv_holder["osv"] = scene.osv
+        shim_sensor = ShimSensor(film, spp)
+        shim_sensor._sampler.base_seed = sensor.sampler().base_seed
+        scene.sensors = lambda: [shim_sensor]
+        integ = mod.TransientPRBVolpathIntegrator(mi.Properties(**props))
+        steady, transient = integ.render(scene, shim_sensor, seed=seed, spp=spp)
+    finally:
+        BSDFPtr.flags, BSDFPtr.sample = saved
+        del BSDFPtr.eval_null_transmission
+        del Vec.__ne__
+        LANES = None
+    return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)

@@ -284,3 +284,48 @@ def test_gpu_angulararea_equals_the_reference_emitter(mitr, name):
     assert np.array_equal(raw != 0, ref != 0)
     assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
     np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ transient_prbvolpath
+from path_cases import VOL_CASES, vol_case_scene  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(VOL_CASES))
+def test_oracle_volpath_deposits_equal_the_reference_integrator(mitr, oracle, name):
+    """TransientPRBVolpathIntegrator.sample / sample_emitter / first_surface (transient_prbvolpath.py:114-528) were
+    EXECUTED over the oracle's scene services (homogeneous media, HG phase functions, null boundaries, the
+    transmittance loop of next-event estimation, camera_unwarp, roulette at depth > rr_depth): deposits bit for bit."""
+    scene, cfg, _ = vol_case_scene(name)
+    r = oracle.render(scene, scene.integrator(), spp=cfg[3], seed=7, log_deposits=1 << 20)
+    assert len(GP[name + "_deposits"]) > 100
+    assert np.array_equal(sort_rows(r["deposits"]), GP[name + "_deposits"])
+    np.testing.assert_allclose(r["steady"], GP[name + "_steady"], rtol=3e-7, atol=0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mitransient"), reason="the reference tree is not available here")
+def test_reference_volpath_integrator_runs_live(mitr, oracle):
+    import warnings
+    import refshim
+    d = mitr.cornell_box_volumetric(5, 4, 40, 6, max_depth=7)
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        steady, raw, dep = refshim.reference_render_vol(scene, props, spp=6, seed=13)
+    r = oracle.render(scene, scene.integrator(), spp=6, seed=13, log_deposits=1 << 20)
+    assert len(dep) > 100 and np.array_equal(sort_rows(dep), sort_rows(r["deposits"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(VOL_CASES))
+def test_gpu_volpath_render_equals_the_reference_integrator(mitr, name):
+    scene, cfg, _ = vol_case_scene(name)
+    integ = scene.integrator()
+    integ.collect_counters = True
+    steady, _ = integ.render(scene, spp=cfg[3], seed=7)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = GP[name + "_raw"]
+    assert integ.last_counters["deposits"] == len(GP[name + "_deposits"])
+    assert np.array_equal(raw != 0, ref != 0)
+    assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
+    np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)
