@@ -10,12 +10,13 @@
 //   - PINNED, film half: add_transient_data, TransientImageBlock.put_/accum (plain and exhaustive_scan index),
 //     develop_transient_, the phasor film, the benchmark scene dictionary, parameter parsing, pass split.
 //   - PINNED, integrator loops: TransientADIntegrator.render, TransientPath.sample, TransientNLOSPath.prepare /
-//     sample / emitter_*_sample / hidden_geometry_sample and NLOSCaptureMeter run UNMODIFIED over a NumPy stand-in
-//     for drjit/mitsuba (tests/golden/refshim.py) whose scene objects call this file's osv_* exports; every
-//     deposit of trace_transient_path / trace_nlos_path must equal one of theirs bit for bit
+//     sample / emitter_*_sample / hidden_geometry_sample, NLOSCaptureMeter, TransientPRBVolpathIntegrator.sample /
+//     sample_emitter / first_surface and AngularAreaLight run UNMODIFIED over a NumPy stand-in for drjit/mitsuba
+//     (tests/golden/refshim.py) whose scene objects call this file's osv_* exports; every deposit of
+//     trace_transient_path / trace_nlos_path / trace_volpath must equal one of theirs bit for bit
 //     (tests/golden/make_reference_golden.py, tests/test_reference_golden.py).
-//   - UNPINNED: the Mitsuba primitives themselves (ray casting, BSDF / emitter / sensor sampling, the sampler) and
-//     trace_volpath's loop.  Their arithmetic lives in two third-party, un-vendored dependencies -- mitsuba
+//   - UNPINNED: the Mitsuba primitives themselves (ray casting, BSDF / emitter / medium / sensor sampling, the
+//     sampler).  Their arithmetic lives in two third-party, un-vendored dependencies -- mitsuba
 //     (pinned >=3.6.0,<3.9.0, mitransient/version.py:5-7, setup.py:21) and drjit (1.1.0 in the notebooks) --
 //     which are not installable here (no wheel, no network), and the reference's only test is stale and
 //     shape-only (tests/integration/test_nlos.py:81-118).  They restate the published Mitsuba 3 algorithms and
