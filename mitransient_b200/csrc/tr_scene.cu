@@ -321,6 +321,7 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             bsdfs[i].k[c] = desc->bsdfs[i].k[c]; bsdfs[i].tr[c] = desc->bsdfs[i].specular_transmittance[c];
         }
         if (bsdfs[i].type >= TR_BSDF_CONDUCTOR) out.has_delta_bsdfs = true;
+        if (bsdfs[i].type == TR_BSDF_NULL) out.has_null_bsdfs = true;
     }
     std::vector<DevEmitter> emitters(std::max(1u, desc->n_emitters));
     memset(emitters.data(), 0, emitters.size() * sizeof(DevEmitter));

@@ -101,6 +101,7 @@ struct SceneImpl {
     uint32_t n_nodes = 0, n_prims = 0;
     bool has_delta_bsdfs = false;        // conductor / dielectric / angulararea present: the general-material kernel instantiation is used
     bool has_angular_emitters = false;
+    bool has_null_bsdfs = false;         // transient_path walks through null boundaries as delta lobes (general-material kernels)
     int device = -1;
     // cached owned-pixel list (tile sharding), rebuilt when (tile, rank, world) changes
     void *d_pixels = nullptr; uint32_t n_pixels = 0; uint32_t px_tile = 0, px_rank = 0, px_world = 0;

@@ -847,8 +847,9 @@ V3 trace_transient_path(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, R
         float s2x = rng.next_1d(), s2y = rng.next_1d();            // sampler.next_2d()
         V3 bsdf_weight = v3(0, 0, 0); float bs_pdf = 0.0f; V3 wo_world = v3(0, 0, 0);
         float bs_eta = 1.0f; bool bs_delta = false;
-        if (active_next && bsdf->type != TR_BSDF_NULL) {
-            // si.wi = si.to_local(-ray.d); the plugins sample in the local frame (diffuse.cpp / conductor.cpp / dielectric.cpp)
+        if (active_next) {
+            // si.wi = si.to_local(-ray.d); the plugins sample in the local frame (diffuse / conductor / dielectric / null .cpp);
+            // a null boundary is a delta lobe that passes straight through and still counts as a vertex (:318)
             V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));
             BsdfSampleRec bs = bsdf_sample(*bsdf, wi, s1, s2x, s2y);
             bsdf_weight = bs.weight; bs_pdf = bs.pdf; bs_eta = bs.eta; bs_delta = bs.delta;

@@ -15,11 +15,17 @@ PATH_CASES = {
                {"back": {"type": "twosided", "bsdf": {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]},
                                                        "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}},
                 "small-box": {"type": "dielectric", "int_ior": 1.33, "ext_ior": 1.0}}),
+    "path_g": ((6, 6, 48, 8), {"max_depth": 8}, "volumetric"),
 }
 
 
 def path_case_scene(name):
     cfg, integ, bsdfs = PATH_CASES[name]
+    if bsdfs == "volumetric":       # cbox_volumetric under transient_path: null boundaries are walked through as delta lobes
+        d = mitr.cornell_box_volumetric(*cfg, max_depth=8)
+        d["integrator"]["type"] = "transient_path"
+        d["integrator"].update(integ)
+        return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
     d = mitr.cornell_box_config(*cfg, window=(3.5, 12.5))
     d["integrator"].update(integ)
     for shape, b in bsdfs.items():
