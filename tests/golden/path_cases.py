@@ -54,12 +54,37 @@ NLOS_CASES = {
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
     # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point
+    "nlos_k": ((8, 6, 128, 64), {"perspective": "single"}, None, None, False),
+    "nlos_l": ((8, 6, 128, 64), {"perspective": "confocal"}, None, None, False),
     "nlos_j": ((1, 1, 128, 256), {"capture_type": "single", "start_opl": 0.0, "window": 8.0, "original_film": (8, 8)}, (5, 3), None, False),
 }
 
 
+def _perspective_nlos_scene(cfg, capture):
+    """transient_nlos_path looking at the relay wall through an ordinary perspective camera (the setup of the reference's
+    examples/transient-nlos/nlos-z-simple.xml)."""
+    T = mitr.ScalarTransform4f
+    v, f = mitr.letter_z_mesh()
+    cam = T().look_at(origin=[-1.2, 0.0, 1.6], target=[0.0, 0.0, 0.0], up=[0, 1, 0])
+    return {"type": "scene",
+            "integrator": {"type": "transient_nlos_path", "nlos_laser_sampling": True, "nlos_hidden_geometry_sampling": True,
+                           "capture_type": capture, "account_first_and_last_bounces": capture == "single", "max_depth": 5},
+            "sensor": {"type": "perspective", "fov": 40.0, "near_clip": 0.1, "far_clip": 100.0, "to_world": cam,
+                       "sampler": {"type": "independent", "sample_count": cfg[3]},
+                       "film": {"type": "transient_hdr_film", "width": cfg[0], "height": cfg[1], "temporal_bins": cfg[2],
+                                "start_opl": 0.0, "bin_width_opl": 12.0 / cfg[2], "rfilter": {"type": "box"}}},
+            "emitter": {"type": "projector", "irradiance": 100.0, "fov": 0.2, "to_world": cam},
+            "relay_wall": {"type": "rectangle", "to_world": T().scale([2.0, 2.0, 1.0]),
+                           "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.8}}},
+            "hidden": {"type": "trimesh", "vertices": v, "faces": f, "to_world": T().translate([0.0, 0.0, 1.0]),
+                       "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 1.0}}}}
+
+
 def nlos_case_scene(name):
     cfg, kw, focus, fov, exhaustive = NLOS_CASES[name]
+    if "perspective" in kw:
+        d = _perspective_nlos_scene(cfg, kw["perspective"])
+        return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
     kw = dict(kw)
     original = kw.pop("original_film", None)
     d = mitr.nlos_z_scene(*cfg, **kw)

@@ -1010,6 +1010,7 @@ def reference_render_nlos(our_scene, props, spp, seed=0):
     meter = ref_module("mitransient.sensors.nloscapturemeter")
     sensor = our_scene.sensors()[0]
     f = sensor.film()
+    scene = None
     film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
                                               start_opl=f.start_opl, bin_width_opl=f.bin_width_opl,
                                               exhaustive_scan=f.exhaustive_scan, laser_scan_width=f.laser_scan_width,
@@ -1032,6 +1033,28 @@ def reference_render_nlos(our_scene, props, spp, seed=0):
     _CURRENT["osv"] = scene.osv
     wall_index = int(scene.osv.lib.osv_sensor_shape(C.c_void_p(scene.osv.h)))
     sampler = ShimSampler(spp); sampler.base_seed = sensor.sampler().base_seed
+    if not hasattr(sensor, "is_confocal"):                    # a perspective camera drives transient_nlos_path (nlos-z-simple.xml)
+        class _PerspectiveSensor(ShimSensor):
+            """mi.Sensor `perspective` [upstream]: sample_ray at a film position = the oracle's camera ray (pixel corner)."""
+            def get_shape(self): return None
+
+            def sample_ray(self, time, sample1, sample2, sample3, active=True):
+                w, h = int(self._film.size().x), int(self._film.size().y)
+                n = width(sample2)
+                px = np.rint(np.asarray(sample2.x, dtype=np.float64) * w).astype(np.uint32)
+                py = np.rint(np.asarray(sample2.y, dtype=np.float64) * h).astype(np.uint32)
+                o, d, maxt = _f(n, 3), _f(n, 3), _f(n)
+                scene.osv.call("osv_camera_rays", np.ascontiguousarray(np.broadcast_to(px, (n,))), np.ascontiguousarray(np.broadcast_to(py, (n,))),
+                               _f(n, 2), o, d, maxt, n=n)
+                return Ray3f(LVec.from_arr(o), LVec.from_arr(d), maxt.view(DrArray)), LVec(1.0)
+        ref_sensor = _PerspectiveSensor(film, spp)
+        ref_sensor._sampler.base_seed = sensor.sampler().base_seed
+        scene.sensors = lambda: [ref_sensor]
+        LANES = int(f.size()[0]) * int(f.size()[1])
+        integ = mod.TransientNLOSPath(mi.Properties(**props))
+        steady, transient = integ.render(scene, ref_sensor, seed=seed, spp=spp)
+        LANES = None
+        return np.asarray(steady), film.develop_transient_(raw=True).numpy(), np.concatenate(log, axis=0) if log else np.zeros((0, 6), np.float32)
     extra = {}
     if sensor.is_confocal:                                    # 1x1 film aimed at laser_target (nloscapturemeter.py:113-125)
         extra = {"original_film_width": sensor.original_film_width, "original_film_height": sensor.original_film_height}
