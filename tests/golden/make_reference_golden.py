@@ -178,8 +178,8 @@ out["tonemap_in"], out["tonemap_out"] = x, vis.tonemap_transient(x, scaling=2.0)
 # The reference's render() (integrators/common.py:122-213) and TransientPath.sample() (transientpath.py:88-326),
 # UNMODIFIED, executed lane-wise over refshim's scene services (whose Mitsuba primitives are the oracle's osv_*
 # exports).  Stored: every non-zero deposit (x, y, opl, r, g, b), sorted; the raw film; the steady image.
-from path_cases import (ANGULAR_CASES, NLOS_CASES, PATH_CASES, VOL_CASES, angular_case_scene, nlos_case_scene,  # noqa: E402
-                        path_case_scene, sort_rows, vol_case_scene)
+from path_cases import (ANGULAR_CASES, NLOS_CASES, PATH_CASES, PHASOR_CASES, VOL_CASES, angular_case_scene,  # noqa: E402
+                        nlos_case_scene, path_case_scene, phasor_case_scene, sort_rows, vol_case_scene)
 
 if __name__ == "__main__":
     path_out = {}
@@ -211,6 +211,15 @@ if __name__ == "__main__":
         steady, raw, dep = refshim.reference_render_vol(scene, props, spp=cfg[3], seed=7)
         path_out[name + "_deposits"], path_out[name + "_raw"], path_out[name + "_steady"] = sort_rows(dep), raw, steady.astype(np.float32)
         print(name, cfg, props, "deposits:", len(dep))
+    # ---- L: the reference's PhasorHDRFilm filled by the reference's transient_path loop (monochromatic variant)
+    mitr.set_variant("llvm_ad_mono")
+    for name in PHASOR_CASES:
+        scene, cfg, props = phasor_case_scene(name)
+        steady, raw, dep = refshim.reference_render(scene, "mitransient.integrators.transientpath", "TransientPath", props, spp=cfg[3],
+                                                    seed=3, monochromatic=True)
+        path_out[name + "_raw"], path_out[name + "_steady"] = raw, steady.astype(np.float32)
+        print(name, cfg, "phasor film", raw.shape, "deposits:", len(dep))
+    mitr.set_variant("cuda_rgb")
     np.savez_compressed(os.path.join(HERE, "reference_path_golden.npz"), **path_out)
 
 np.savez_compressed(os.path.join(HERE, "reference_host_golden.npz"), **out)

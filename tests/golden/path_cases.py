@@ -136,3 +136,18 @@ def vol_case_scene(name):
         d["integrator"]["type"] = "transient_prbvolpath"
     d["integrator"].update(integ)
     return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
+
+
+# ---- phasor_hdr_film filled by the reference's transient_path loop (monochromatic variant)
+PHASOR_CASES = {"phasor_path_a": ((6, 5, 256, 8), {"max_depth": 8}, 0.5, 0.5),
+                "phasor_path_b": ((4, 4, 1024, 16), {"max_depth": 5, "camera_unwarp": True}, 0.2, 0.1)}
+
+
+def phasor_case_scene(name):
+    """Call with the monochromatic variant active (mitr.set_variant('..._mono'))."""
+    cfg, integ, wl_mean, wl_sigma = PHASOR_CASES[name]
+    d = mitr.cornell_box_config(*cfg)
+    d["integrator"].update(integ)
+    d["sensor"]["film"] = {"type": "phasor_hdr_film", "width": cfg[0], "height": cfg[1], "temporal_bins": cfg[2], "start_opl": 3.5,
+                           "bin_width_opl": 6.0 / cfg[2], "wl_mean": wl_mean, "wl_sigma": wl_sigma}
+    return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}

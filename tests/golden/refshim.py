@@ -791,8 +791,16 @@ def reference_render(our_scene, integrator_module, integrator_cls, props, spp, s
     mod = ref_module(integrator_module)
     sensor = our_scene.sensors()[0]
     f = sensor.film()
-    film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
-                                              start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
+    if hasattr(f, "frequencies"):                     # the reference's PhasorHDRFilm collects the deposits (monochromatic variant)
+        dr.cos = lambda x: np.cos(np.asarray(x, dtype=np.float32))
+        dr.sin = lambda x: np.sin(np.asarray(x, dtype=np.float32))
+        phf = ref_module("mitransient.films.phasor_hdr_film")
+        film = phf.PhasorHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins, start_opl=f.start_opl,
+                                               bin_width_opl=f.bin_width_opl, wl_mean=f.wl_mean, wl_sigma=f.wl_sigma))
+        film.develop_transient_ = lambda raw=True: film.develop_phasors_(raw=raw)
+    else:
+        film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
+                                                  start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
     log = []
     inner = film.add_transient_data
 

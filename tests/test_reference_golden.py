@@ -329,3 +329,37 @@ def test_gpu_volpath_render_equals_the_reference_integrator(mitr, name):
     assert np.array_equal(raw != 0, ref != 0)
     assert np.abs(raw - ref).sum() <= 1e-5 * np.abs(ref).sum()
     np.testing.assert_allclose(steady.cpu().numpy(), GP[name + "_steady"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ phasor film through the loop
+from path_cases import PHASOR_CASES, phasor_case_scene  # noqa: E402
+
+
+@pytest.fixture
+def mono(mitr):
+    mitr.set_variant("llvm_ad_mono")
+    yield
+    mitr.set_variant("cuda_rgb")
+
+
+@pytest.mark.parametrize("name", sorted(PHASOR_CASES))
+def test_oracle_phasor_render_equals_the_reference(mitr, oracle, mono, name):
+    """The reference's PhasorHDRFilm + PhasorImageBlock collecting the deposits of the reference's transient_path loop
+    (monochromatic variant): the oracle's phasor film within the cos / sin accuracy (NumPy there, Cephes here)."""
+    scene, cfg, _ = phasor_case_scene(name)
+    r = oracle.render(scene, scene.integrator(), spp=cfg[3], seed=3)
+    ref = GP[name + "_raw"]
+    assert r["transient"].shape == ref.shape
+    assert np.abs(r["transient"] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    np.testing.assert_allclose(r["steady"][..., 0], GP[name + "_steady"][..., 0], rtol=3e-7, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(PHASOR_CASES))
+def test_gpu_phasor_render_equals_the_reference(mitr, mono, name):
+    scene, cfg, _ = phasor_case_scene(name)
+    integ = scene.integrator()
+    integ.render(scene, spp=cfg[3], seed=3)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = GP[name + "_raw"]
+    assert np.abs(raw - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
