@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 10
+#define TR_ABI_VERSION 11
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -216,7 +216,14 @@ typedef struct TrRenderParams {
     /* transient_nlos_path */
     int32_t capture_type;   /* TR_CAPTURE_*                                                 */
     int32_t filter_depth;   /* -1 = off                                                     */
-    uint32_t _reserved[7];  /* (the `single` laser target and the per-pixel sensor targets,
+    /* Exhaustive captures (transientnlospath.py:340-379): with force_equal_illumination_scanning the illuminated
+       points are the sensor's scanned points; otherwise they come from a laser_scan_width x laser_scan_height grid
+       of rays shot through a copy of the projector with the field of view illumination_scan_fov --
+       laser_scan_sample_to_camera is that copy's sample -> camera matrix (inverse of Mitsuba's
+       perspective_projection(1x1, fov, 1e-4, 1e4)), row-major 4x4.                                        */
+    int32_t force_equal_grids;
+    float laser_scan_sample_to_camera[16];
+    uint32_t _reserved[6];  /* (the `single` laser target and the per-pixel sensor targets,
                                transientnlospath.py:295-339, are traced on the device)      */
 } TrRenderParams;
 

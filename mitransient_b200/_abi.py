@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 10
+TR_ABI_VERSION = 11
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -86,7 +86,8 @@ class TrRenderParams(C.Structure):
                 ("flags", C.c_uint32), ("spp", C.c_uint32), ("total_spp", C.c_uint32), ("seed", C.c_uint32),
                 ("tile_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
                 ("film_channels", C.c_int32), ("accumulate", C.c_int32),
-                ("capture_type", C.c_int32), ("filter_depth", C.c_int32), ("_reserved", C.c_uint32 * 7)]
+                ("capture_type", C.c_int32), ("filter_depth", C.c_int32), ("force_equal_grids", C.c_int32),
+                ("laser_scan_sample_to_camera", C.c_float * 16), ("_reserved", C.c_uint32 * 6)]
 
 
 class TrCounters(C.Structure):

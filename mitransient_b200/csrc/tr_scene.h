@@ -112,6 +112,7 @@ struct SceneImpl {
     std::vector<float> frequencies; void *d_freqs = nullptr;   // phasor film: host / device copy of TrFilmDesc.frequencies
     void *d_nlos = nullptr;              // float4 targets[H*W + 1] | float hg_table[2 * n_shapes]
     uint32_t nlos_key = 0xffffffffu; float hg_sum = 0.f, hg_norm = 0.f;
+    size_t nlos_capacity = 0; uint32_t nlos_grid = 0; float nlos_s2c[16] = {0};   // laser grid of an Exhaustive capture with its own fov
 };
 
 bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err);

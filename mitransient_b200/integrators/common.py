@@ -94,7 +94,7 @@ class TransientADIntegrator:
         p.spp, p.total_spp, p.seed = spp_i, total_spp, seed_i
         p.tile_size, p.rank, p.world = tile_size, rank, world
         p.film_channels, p.accumulate = film_channels, int(accumulate)
-        p.capture_type, p.filter_depth = 0, -1
+        p.capture_type, p.filter_depth, p.force_equal_grids = 0, -1, 1
         return p
 
     def device_scene(self, scene: Scene, sensor) -> _lib.DeviceScene:

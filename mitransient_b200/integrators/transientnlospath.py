@@ -2,8 +2,10 @@
 
 Plugin parameters, defaults and rejections follow transientnlospath.py:201-249; ``prepare`` (:251-383: hidden
 geometry area distribution, per-pixel sensor targets, laser targets) and ``sample`` (:673-927) run on the device
-(csrc/tr_render.cu, NLOS branch).  Exhaustive captures are implemented for equal sensor / laser grids
-(``force_equal_illumination_scanning=True``, the default) on an ``exhaustive_scan`` film; AD is out of scope.
+(csrc/tr_render.cu, NLOS branch).  Exhaustive captures need an ``exhaustive_scan`` film: the illuminated points are
+the sensor's scanned points (``force_equal_illumination_scanning=True``, the default) or a ``laser_scan_width x
+laser_scan_height`` grid shot through a copy of the projector with the field of view ``illumination_scan_fov``; AD is
+out of scope.
 """
 from __future__ import annotations
 
@@ -74,13 +76,11 @@ class TransientNLOSPath(TransientADIntegrator):
             raise NotImplementedError("transient_nlos_path expects a `projector` emitter (the laser)")
         film = sensor.film()
         if self.capture_type == CaptureType.Exhaustive:
-            if not self.force_equal_grids:
-                raise NotImplementedError("Exhaustive captures are implemented for force_equal_illumination_scanning=True "
-                                          "(the illumination_scan_fov laser grid, transientnlospath.py:349-379, is not)")
             if not getattr(film, "exhaustive_scan", False):
                 raise ValueError("Exhaustive captures need a transient_hdr_film with exhaustive_scan=True "
-                                 "(laser_scan_width / laser_scan_height = the film size)")
-            if (film.laser_scan_width, film.laser_scan_height) != tuple(film.size()):           # :345-348
+                                 "(laser_scan_width / laser_scan_height = the laser grid)")
+            if self.force_equal_grids and self.laser_sampling and \
+                    (film.laser_scan_width, film.laser_scan_height) != tuple(film.size()):      # :345-348
                 raise AssertionError("Sensor and laser scan resolution must be equal if "
                                      "force_equal_illumination_scanning is set to True")
         if self.hg_sampling:                                                                # :277-289
@@ -112,3 +112,10 @@ class TransientNLOSPath(TransientADIntegrator):
     def fill_params_(self, params, scene, sensor):
         params.capture_type = _CAPTURE_TO_ABI[self.capture_type]
         params.filter_depth = self.filter_depth
+        params.force_equal_grids = int(self.force_equal_grids)
+        # the widened copy of the projector that scans the illuminated points (transientnlospath.py:349-356):
+        # inverse of Mitsuba's perspective_projection(1x1 texture, fov, 1e-4, 1e4)
+        from ..transforms import parse_fov, perspective_projection
+        fov_x = float(parse_fov(self.illumination_scan_fov, "x", 1.0))
+        s2c = perspective_projection((1, 1), (1, 1), (0, 0), fov_x, 1e-4, 1e4).inverse()
+        params.laser_scan_sample_to_camera[:] = s2c.matrix.astype("float32").reshape(-1).tolist()

@@ -890,6 +890,7 @@ constexpr float kEps = 5.9604644775390625e-08f;   // dr.epsilon(Float) = 2^-24
 struct NlosCtx {
     const TrEmitterDesc *em; V3 em_origin, em_forward;
     std::vector<V3> sensor_targets; V3 laser_target_single; bool laser_single_valid;
+    std::vector<V3> laser_targets;                              // Exhaustive capture: the illuminated points (:345-379)
     std::vector<float> hg_pmf, hg_cdf; float hg_sum, hg_norm;   // DiscreteDistribution over shapes (:277-292)
     uint32_t sensor_shape;
     uint32_t laser_res_x = 0, laser_res_y = 0;                  // Exhaustive capture: illumination grid (:340-348)
@@ -920,10 +921,18 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
         err = "unknown capture type"; return false;
     }
     if (rp.capture_type == TR_CAPTURE_EXHAUSTIVE) {
-        // force_equal_illumination_scanning = True (:345-348): the laser grid is the sensor grid
-        ctx.laser_res_x = sc.film.width; ctx.laser_res_y = sc.film.height;
-        if (sc.film.laser_scan_width && (sc.film.laser_scan_width != sc.film.width || sc.film.laser_scan_height != sc.film.height)) {
-            err = "Sensor and laser scan resolution must be equal if force_equal_illumination_scanning is set to True"; return false;
+        // laser_resolution = (film.laser_scan_width, film.laser_scan_height) (:341-343); the sampling loop runs over the
+        // sensor grid when force_equal_illumination_scanning is set (:599-601), over the laser grid otherwise (:602-604)
+        const bool have = sc.film.laser_scan_width && sc.film.laser_scan_height;
+        if (rp.force_equal_grids) {
+            ctx.laser_res_x = sc.film.width; ctx.laser_res_y = sc.film.height;
+            if ((rp.flags & TR_FLAG_NLOS_LASER_SAMPLING) && have &&
+                (sc.film.laser_scan_width != sc.film.width || sc.film.laser_scan_height != sc.film.height)) {
+                err = "Sensor and laser scan resolution must be equal if force_equal_illumination_scanning is set to True"; return false;
+            }
+        } else {
+            if (!have) { err = "Exhaustive capture with its own laser grid needs film.laser_scan_width / laser_scan_height"; return false; }
+            ctx.laser_res_x = sc.film.laser_scan_width; ctx.laser_res_y = sc.film.laser_scan_height;
         }
     }
     ctx.em = &sc.emitters[0];
@@ -955,6 +964,30 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
     // Single capture: where the laser axis meets the scene :328-336
     Hit hl = ray_intersect(sc, Ray{ctx.em_origin, ctx.em_forward, std::numeric_limits<float>::max()});
     ctx.laser_target_single = hl.p; ctx.laser_single_valid = hl.valid;
+    if (rp.capture_type == TR_CAPTURE_EXHAUSTIVE) {
+        if (rp.force_equal_grids) ctx.laser_targets = ctx.sensor_targets;                      // :345-348
+        else {
+            // :349-379: a copy of the projector with fov = illumination_scan_fov shoots one ray per laser grid point
+            // (meshgrid of linspace(0, 1, res, endpoint=False), x fastest); projector.sample_ray [upstream]: the direction
+            // sample picks the point of the 1x1 irradiance texture the ray goes through
+            const uint32_t lw = ctx.laser_res_x, lh = ctx.laser_res_y;
+            ctx.laser_targets.resize((size_t) lw * lh);
+            float sx_step = 1.0f / (float) lw, sy_step = 1.0f / (float) lh;
+            const float *m = rp.laser_scan_sample_to_camera;
+            bool any = false;
+            for (uint32_t y = 0; y < lh; ++y) for (uint32_t x = 0; x < lw; ++x) {
+                float u = fmaf((float) x, sx_step, 0.0f), v = fmaf((float) y, sy_step, 0.0f);
+                float cx = fmaf(m[0], u, fmaf(m[1], v, m[3])), cy = fmaf(m[4], u, fmaf(m[5], v, m[7]));
+                float cz = fmaf(m[8], u, fmaf(m[9], v, m[11])), cw = fmaf(m[12], u, fmaf(m[13], v, m[15]));
+                float iw = 1.0f / cw;
+                V3 dl = normalize(v3(cx * iw, cy * iw, cz * iw));
+                V3 dw = xf_vector(ctx.em->to_world, dl);
+                Hit h = ray_intersect(sc, Ray{ctx.em_origin, dw, std::numeric_limits<float>::max()});
+                ctx.laser_targets[(size_t) y * lw + x] = h.p; any = any || h.valid;
+            }
+            if (!any) { err = "The emitter did not intersect any geometry in the scene."; return false; }
+        }
+    }
     if (rp.capture_type == TR_CAPTURE_SINGLE && (rp.flags & TR_FLAG_NLOS_LASER_SAMPLING) && !hl.valid) { err = "The emitter is not pointing at the scene!"; return false; }
     return true;
 }
@@ -1055,7 +1088,7 @@ V3 nlos_emitter_laser_sample(const Scene &sc, const TrRenderParams &rp, const Nl
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t laser_x = (uint32_t) ((float) i / (float) ctx.laser_res_y);              // :618  UInt(i / Float(res_y))
             uint32_t laser_y = i % ctx.laser_res_y;                                           // :619
-            sum = sum + nlos_emitter_laser_targets_sample(sc, rp, ctx, rng, vx, ctx.sensor_targets[i], beta, distance, eta,
+            sum = sum + nlos_emitter_laser_targets_sample(sc, rp, ctx, rng, vx, ctx.laser_targets[i], beta, distance, eta,
                                                           depth + 1, px, py, sample_scale, film, laser_x, laser_y);
         }
         return sum * (1.0f / (float) n);                                                      // :627
@@ -1831,6 +1864,19 @@ void osv_shape_pdf_direction(void *h, uint64_t n, const float *ds_d, const float
 }
 void osv_dot(void *, uint64_t n, const float *a, const float *b, float *out) {
     for (uint64_t i = 0; i < n; ++i) out[i] = dot(ld3(a, i), ld3(b, i));
+}
+// Projector::sample_ray [upstream] of a copy of the scene's projector whose sample -> camera matrix is s2c: one ray per (u, v)
+void osv_projector_sample_ray(void *h, uint64_t n, const float *s2c, const float *uv, float *o, float *d) {
+    const Scene &sc = ((OsvScene *) h)->sc;
+    const TrEmitterDesc &em = sc.emitters[0];
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *m = s2c; float u = uv[2 * i], v = uv[2 * i + 1];
+        float cx = fmaf(m[0], u, fmaf(m[1], v, m[3])), cy = fmaf(m[4], u, fmaf(m[5], v, m[7]));
+        float cz = fmaf(m[8], u, fmaf(m[9], v, m[11])), cw = fmaf(m[12], u, fmaf(m[13], v, m[15]));
+        float iw = 1.0f / cw;
+        V3 dl = normalize(v3(cx * iw, cy * iw, cz * iw));
+        st3(o, i, v3(em.to_world[3], em.to_world[7], em.to_world[11])); st3(d, i, xf_vector(em.to_world, dl));
+    }
 }
 uint32_t osv_n_shapes(void *h) { return (uint32_t) ((OsvScene *) h)->sc.shapes.size(); }
 float osv_shape_area(void *h, uint32_t shape) { return ((OsvScene *) h)->sc.shapes[shape].area; }

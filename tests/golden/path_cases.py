@@ -54,6 +54,9 @@ NLOS_CASES = {
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
     # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point
+    # Exhaustive capture with its own (non-square) laser grid, scanned through a 30-degree copy of the projector
+    "nlos_m": ((4, 4, 32, 4), {"capture_type": "exhaustive", "force_equal_illumination_scanning": False, "illumination_scan_fov": 30.0,
+                               "laser_grid": (3, 2), "start_opl": 0.0, "window": 8.0}, (2, 2), None, True),
     "nlos_k": ((8, 6, 128, 64), {"perspective": "single"}, None, None, False),
     "nlos_l": ((8, 6, 128, 64), {"perspective": "confocal"}, None, None, False),
     "nlos_j": ((1, 1, 128, 256), {"capture_type": "single", "start_opl": 0.0, "window": 8.0, "original_film": (8, 8)}, (5, 3), None, False),
@@ -87,6 +90,7 @@ def nlos_case_scene(name):
         return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
     kw = dict(kw)
     original = kw.pop("original_film", None)
+    laser_grid = kw.pop("laser_grid", None)
     d = mitr.nlos_z_scene(*cfg, **kw)
     if original is not None:
         d["relay_wall"]["nlos_sensor"]["original_film_width"], d["relay_wall"]["nlos_sensor"]["original_film_height"] = original
@@ -95,6 +99,8 @@ def nlos_case_scene(name):
     if exhaustive:
         f = d["relay_wall"]["nlos_sensor"]["transient_film"]
         f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, cfg[0], cfg[1]
+        if laser_grid is not None:
+            f["laser_scan_width"], f["laser_scan_height"] = laser_grid
     scene = mitr.load_dict(d)
     if focus is not None:
         wall = [v for v in d.values() if isinstance(v, dict) and v.get("type") == "rectangle"][0]

@@ -840,6 +840,10 @@ class ShimTransform4f:
     """mi.Transform4f as the reference uses it: translate(), translation(), `@ Vector3f`; float32 entries."""
     def __init__(self, m=None): self.m = np.eye(4, dtype=np.float64) if m is None else np.asarray(m, dtype=np.float64)
 
+    @property
+    def matrix(self):                              # world_transform().matrix.to_numpy()[..., 0]  (transientnlospath.py:355)
+        return types.SimpleNamespace(to_numpy=lambda: self.m[..., None])
+
     def translate(self, v):
         t = np.eye(4); t[:3, 3] = [float(np.asarray(c)) for c in (v.c if isinstance(v, Vec) else v)]
         return ShimTransform4f(self.m @ t)
@@ -958,6 +962,22 @@ def install_nlos_services(monochromatic=False, transform_cls=None, color_fn=None
     mi.BSDFFlags.Reflection = BSDFPtr.Reflection
     mi.Frame3f = types.SimpleNamespace(cos_theta=lambda v: v.z)
     sys.modules["drjit.scalar"].Array3f = VecF
+    class _ScanProjector:
+        """mi.load_dict({'type': 'projector', 'fov': ..., 'to_world': ...}) of TransientNLOSPath.prepare (:352-356): only its
+        sample_ray is used (:366-367); the rays are the oracle's (same widened sample -> camera matrix as the host computes)."""
+        def __init__(self, d):
+            from mitransient_b200.transforms import parse_fov, perspective_projection
+            fov_x = float(parse_fov(float(d["fov"]), "x", 1.0))
+            self.s2c = np.ascontiguousarray(perspective_projection((1, 1), (1, 1), (0, 0), fov_x, 1e-4, 1e4).inverse().matrix.astype(np.float32))
+
+        def sample_ray(self, time, sample1, sample2, sample3, active=True):
+            n = width(sample3)
+            o, dd = _f(n, 3), _f(n, 3)
+            _CURRENT["osv"].call("osv_projector_sample_ray", self.s2c, sample3.arr(n), o, dd, n=n)
+            return Ray3f(LVec.from_arr(o), LVec.from_arr(dd)), LVec(1.0)
+    prev_load = mi.load_dict
+    mi.load_dict = lambda d: _ScanProjector(d) if d.get("type") == "projector" else prev_load(d)
+    mi.ScalarTransform4f = transform_cls
     mi.traverse = lambda obj: {"film.size": Vec2I(int(obj.film().size().x), int(obj.film().size().y)),
                                "film.laser_scan_width": getattr(obj.film(), "laser_scan_width", 0),
                                "film.laser_scan_height": getattr(obj.film(), "laser_scan_height", 0)}

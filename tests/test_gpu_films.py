@@ -61,10 +61,6 @@ def test_exhaustive_rejections(mitr):
     scene = mitr.load_dict(d)
     with pytest.raises(ValueError, match="exhaustive_scan"):
         scene.integrator().render(scene, spp=1)
-    d = exhaustive_scene(mitr, 4, 16, 1, force_equal_illumination_scanning=False)
-    scene = mitr.load_dict(d)
-    with pytest.raises(NotImplementedError):
-        scene.integrator().render(scene, spp=1)
     d = exhaustive_scene(mitr, 4, 16, 1)
     d["relay_wall"]["nlos_sensor"]["transient_film"]["laser_scan_width"] = 2
     scene = mitr.load_dict(d)
