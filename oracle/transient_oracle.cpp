@@ -1025,18 +1025,30 @@ inline V3 projector_sample_direction(const TrEmitterDesc &em, V3 itp, V3 *ds_p, 
 struct NlosVertex { V3 p, n; float cos_i; const TrBsdfDesc *bsdf; };
 
 // emitter_nee_sample   transientnlospath.py:433-509
+// `distance` is taken BY REFERENCE: the reference adds ds.dist to its argument in place (:497-498), and with plain emitter
+// sampling that argument IS the loop's distance (Dr.Jit arrays are mutable objects) -- so with nlos_laser_sampling off and
+// account_first_and_last_bounces on, every emitter connection also lengthens the rest of the path (SURVEY appendix B.11;
+// reproduced because the executed reference does it).  The laser-sampling path passes a temporary (:562).
 V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
-                           V3 beta, float distance, float eta, uint32_t depth, bool active_e, bool focus_laser,
+                           V3 beta, float &distance, float eta, uint32_t depth, bool active_e, bool focus_laser,
                            float px, float py, float sample_scale, Film &film, uint32_t laser_x = 0, uint32_t laser_y = 0) {
     if (!active_e) return v3(0, 0, 0);
     film.cnt->shadow_rays++;
-    if (ray_test(sc, spawn_ray_to(vx.p, vx.n, ctx.em_origin))) return v3(0, 0, 0);             // :442
     V3 query = vx.p;
     if (focus_laser && (rp.capture_type == TR_CAPTURE_CONFOCAL || rp.capture_type == TR_CAPTURE_EXHAUSTIVE)) {   // :448-458
         V3 rel = ctx.em_origin - vx.p;
         float dte = sqrtf(dot(rel, rel));
         query = v3(ctx.em_origin.x + ctx.em_forward.x * dte, ctx.em_origin.y + ctx.em_forward.y * dte,
                    ctx.em_origin.z + ctx.em_forward.z * dte);
+    }
+    if (ray_test(sc, spawn_ray_to(vx.p, vx.n, ctx.em_origin))) {                              // :442
+        // occluded: no deposit and no sampler draw, but the projector's sample_direction fills ds.dist without looking at
+        // its mask (mitsuba projector.cpp, a direct call on the one emitter object), and :497-498 is unmasked too
+        if (rp.flags & TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES) {
+            V3 dd = ctx.em_origin - query;
+            distance += sqrtf(dot(dd, dd)) * eta;
+        }
+        return v3(0, 0, 0);
     }
     rng.next_1d(); rng.next_1d();                                                             // sampler.next_2d(active_e)
     V3 dsp; float ds_dist;
@@ -1072,7 +1084,8 @@ V3 nlos_emitter_laser_targets_sample(const Scene &sc, const TrRenderParams &rp, 
     float pdf_ls = (dl * dl) / cos_wl;                                                        // :546-550
     bsdf_spec = v3(bsdf_spec.x / pdf_ls, bsdf_spec.y / pdf_ls, bsdf_spec.z / pdf_ls);         // :551
     NlosVertex vb{sb.p, sb.n, -dot(ray_bsdf.d, sb.n), &sc.bsdfs[sc.shapes[sb.shape].d.bsdf]}; // :553
-    return nlos_emitter_nee_sample(sc, rp, ctx, rng, vb, beta * bsdf_spec, distance + dl * eta, eta, depth + 1, true, true,
+    float distance_at_spot = distance + dl * eta;                                             // a temporary: not aliased
+    return nlos_emitter_nee_sample(sc, rp, ctx, rng, vb, beta * bsdf_spec, distance_at_spot, eta, depth + 1, true, true,
                                    px, py, sample_scale, film, laser_x, laser_y);             // :560-564
 }
 
@@ -1781,10 +1794,12 @@ void osv_projector_sample_direction(void *h, uint64_t n, const float *it_p, cons
     for (uint64_t i = 0; i < n; ++i) {
         V3 p = v3(0, 0, 0), w = v3(0, 0, 0); float dist = 0.0f;
         V3 itp = ld3(it_p, i);
-        if (active[i]) w = projector_sample_direction(em, itp, &p, &dist);
+        // projector.cpp fills the DirectionSample without looking at `active`; only the returned spectrum is masked
+        w = projector_sample_direction(em, itp, &p, &dist);
+        if (!active[i]) w = v3(0, 0, 0);
         V3 d = p - itp; float l = sqrtf(dot(d, d));
-        st3(ds_p, i, p); st3(ds_d, i, active[i] ? d * (1.0f / l) : v3(0, 0, 0)); ds_dist[i] = dist; st3(weight, i, w);
-        ds_pdf[i] = active[i] ? 1.0f : 0.0f;                         // projector.cpp: ds.pdf = 1 (delta position)
+        st3(ds_p, i, p); st3(ds_d, i, d * (1.0f / l)); ds_dist[i] = dist; st3(weight, i, w);
+        ds_pdf[i] = 1.0f;                                            // projector.cpp: ds.pdf = 1 (delta position)
     }
 }
 // shape.sample_position(time, sample, active) for the shape index of every lane -> p, n, pdf

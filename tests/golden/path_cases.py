@@ -51,6 +51,16 @@ NLOS_CASES = {
                                "rr_depth": 2, "start_opl": 0.0, "window": 8.0}, None, None, False),
     "nlos_f": ((6, 6, 64, 16), {"capture_type": "single", "start_opl": 0.0, "window": 8.0}, (3, 2), None, False),
     "nlos_g": ((6, 6, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, (3, 3), 60.0, False),
+    # plain emitter sampling + account_first_and_last_bounces: the reference's in-place `distance += ds.dist` inside
+    # emitter_nee_sample leaks into the loop's own distance -- deposits carry the accumulated lengths
+    "nlos_n": ((5, 5, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "nlos_hidden_geometry_sampling": False,
+                                "account_first_and_last_bounces": True, "start_opl": 0.0, "window": 16.0, "max_depth": 6},
+               (2, 2), 120.0, False),
+    # ... and with an occluder between part of the scene and the laser: occluded connections deposit nothing but still add
+    # ds.dist (the projector fills its DirectionSample regardless of the mask, :497-498 is unmasked)
+    "nlos_o": ((5, 5, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "nlos_hidden_geometry_sampling": False,
+                                "account_first_and_last_bounces": True, "start_opl": 0.0, "window": 16.0, "max_depth": 6,
+                                "occluder": True}, (2, 2), 120.0, False),
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
     # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point
@@ -91,7 +101,11 @@ def nlos_case_scene(name):
     kw = dict(kw)
     original = kw.pop("original_film", None)
     laser_grid = kw.pop("laser_grid", None)
+    occluder = kw.pop("occluder", False)
     d = mitr.nlos_z_scene(*cfg, **kw)
+    if occluder:
+        d["occluder"] = {"type": "rectangle", "to_world": mitr.ScalarTransform4f().translate([-0.25, 0.1, 0.5]).scale([0.3, 0.3, 1.0]),
+                         "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.7}}}
     if original is not None:
         d["relay_wall"]["nlos_sensor"]["original_film_width"], d["relay_wall"]["nlos_sensor"]["original_film_height"] = original
     if fov is not None:
