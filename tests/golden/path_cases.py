@@ -61,6 +61,11 @@ NLOS_CASES = {
     "nlos_o": ((5, 5, 64, 64), {"capture_type": "single", "nlos_laser_sampling": False, "nlos_hidden_geometry_sampling": False,
                                 "account_first_and_last_bounces": True, "start_opl": 0.0, "window": 16.0, "max_depth": 6,
                                 "occluder": True}, (2, 2), 120.0, False),
+    # exhaustive capture with laser sampling and an occluder: some laser targets are invisible from some vertices.  The
+    # `active_e &= ...` inside emitter_laser_targets_sample mutates the mask it was handed, but that mask is not state of the
+    # recorded (symbolic) laser loop, so every laser target starts from the caller's mask (refshim._SymbolicLoopState)
+    "nlos_p": ((3, 3, 48, 4), {"capture_type": "exhaustive", "nlos_hidden_geometry_sampling": False, "start_opl": 0.0, "window": 16.0,
+                               "max_depth": 6, "rr_depth": 2, "occluder": True}, None, None, True),
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
     # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point

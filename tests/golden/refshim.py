@@ -917,6 +917,54 @@ class ShimSensorBase(Object):
     def traverse(self, cb): pass
 
 
+class _SymbolicLoopState(ast.NodeTransformer):
+    """Dr.Jit records the body of a `while` over arrays ONCE (symbolic mode, the default): only the loop's state
+    variables -- the names the body assigns -- are carried from one iteration to the next.  An array that lives outside
+    the loop, is not assigned in it, but is MUTATED in place by something the body calls (`active_e &= ...` inside
+    emitter_laser_targets_sample, called from the exhaustive-capture loop of emitter_laser_sample,
+    transientnlospath.py:612-628) enters every recorded iteration with its pre-loop value.  This stand-in runs loops
+    iteration by iteration, so it restores such arrays at the top of every iteration to keep that meaning."""
+    counter = 0
+
+    def visit_While(self, node):
+        self.generic_visit(node)
+        def root(t):
+            while isinstance(t, (ast.Attribute, ast.Subscript, ast.Starred)):
+                t = t.value
+            return [t.id] if isinstance(t, ast.Name) else ([r for e in t.elts for r in root(e)] if isinstance(t, (ast.Tuple, ast.List)) else [])
+        stored = {n.id for b in node.body for n in ast.walk(b) if isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del))}
+        for b in node.body:                                   # `x.f = ...`, `x[mask] = ...`, `x[mask] += ...` modify x as well
+            for n in ast.walk(b):
+                for t in (n.targets if isinstance(n, ast.Assign) else [n.target] if isinstance(n, (ast.AugAssign, ast.AnnAssign)) else []):
+                    stored.update(root(t))
+        loaded = {n.id for b in node.body for n in ast.walk(b) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+        names = sorted(loaded - stored)
+        _SymbolicLoopState.counter += 1
+        snap = "__shim_snap%d" % _SymbolicLoopState.counter
+        take = ast.Assign(targets=[ast.Name(id=snap, ctx=ast.Store())],
+                          value=ast.Call(func=ast.Name(id="__shim_snapshot", ctx=ast.Load()),
+                                         args=[ast.Call(func=ast.Name(id="locals", ctx=ast.Load()), args=[], keywords=[]),
+                                               ast.Constant(value=tuple(names))], keywords=[]))
+        put = ast.Expr(value=ast.Call(func=ast.Name(id="__shim_restore", ctx=ast.Load()), args=[ast.Name(id=snap, ctx=ast.Load())], keywords=[]))
+        node.body = [put] + node.body
+        return [take, node]
+
+
+def _shim_snapshot(frame_locals, names):
+    saved = []
+    for n in names:
+        v = frame_locals.get(n)
+        for a in (v.c if isinstance(v, Vec) else (v,)):
+            if isinstance(a, np.ndarray) and a.ndim > 0 and a.flags.writeable:
+                saved.append((a, a.copy()))
+    return saved
+
+
+def _shim_restore(saved):
+    for a, c in saved:
+        a[...] = c
+
+
 def _rewrite_array_ifs(fn):
     """dr.syntax for this stand-in: `if <array condition>: <assignments>` becomes lane-wise selects; everything else
     (scalar conditions, loops driven by dr.hint) runs as ordinary Python."""
@@ -942,8 +990,9 @@ def _rewrite_array_ifs(fn):
             test = ast.Call(func=ast.Name(id="__shim_is_array", ctx=ast.Load()), args=[ast.Name(id="__shim_c", ctx=ast.Load())], keywords=[])
             return [ast.Assign(targets=[ast.Name(id="__shim_c", ctx=ast.Store())], value=node.test),
                     ast.If(test=test, body=masked, orelse=[ast.If(test=ast.Name(id="__shim_c", ctx=ast.Load()), body=node.body, orelse=[])])]
-    tree = ast.fix_missing_locations(T().visit(tree))
+    tree = ast.fix_missing_locations(_SymbolicLoopState().visit(T().visit(tree)))
     g = fn.__globals__
+    g["__shim_snapshot"], g["__shim_restore"] = _shim_snapshot, _shim_restore
     g["__shim_is_array"] = lambda c: isinstance(c, np.ndarray) and c.ndim > 0
     g["__shim_select"] = lambda c, a, b: sys.modules["drjit"].select(c, a, b)
     loc = {}
@@ -1403,8 +1452,9 @@ def _rewrite_syntax_vol(fn):
             self.generic_visit(node)
             node.test = ast.Call(func=ast.Name(id="__shim_any", ctx=ast.Load()), args=[node.test], keywords=[])
             return node
-    tree = ast.fix_missing_locations(W().visit(tree))
+    tree = ast.fix_missing_locations(_SymbolicLoopState().visit(W().visit(tree)))
     g = fn.__globals__
+    g["__shim_snapshot"], g["__shim_restore"] = _shim_snapshot, _shim_restore
     g["__shim_any"] = lambda c: bool(np.any(c))
     loc = {}
     exec(compile(tree, inspect.getsourcefile(fn), "exec"), g, loc)
