@@ -1,0 +1,141 @@
+"""Random sweeps of integrator options, BSDFs, media and occluders: the oracle's deposits against the REFERENCE'S OWN
+render() + sample(), executed over refshim (build container only: needs /root/reference).  Test infrastructure.
+
+    python tests/golden/fuzz_reference.py nlos|path|vol  N  FIRST_SEED
+"""
+import os
+import random
+import sys
+import traceback
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, HERE)
+import numpy as np  # noqa: E402
+
+import refshim  # noqa: E402
+import mitransient_b200 as mitr  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+T = mitr.ScalarTransform4f
+
+
+def sortrows(a): return a[np.lexsort(a.T[::-1])]
+
+def cmp(tag, cfgdesc, dep, r):
+    a, b = sortrows(dep), sortrows(r["deposits"])
+    eq = a.shape == b.shape and np.array_equal(a, b)
+    print(("OK  " if eq else "FAIL"), tag, len(a), len(b), cfgdesc, flush=True)
+    return eq
+
+def fuzz_nlos(rng, i):
+    kw = {}
+    cap = rng.choice(["confocal", "single", "exhaustive"])
+    kw["capture_type"] = cap
+    kw["nlos_laser_sampling"] = rng.random() < 0.6
+    kw["nlos_hidden_geometry_sampling"] = rng.random() < 0.6
+    if kw["nlos_hidden_geometry_sampling"]:
+        kw["nlos_hidden_geometry_sampling_do_rroulette"] = rng.random() < 0.5
+        kw["nlos_hidden_geometry_sampling_includes_relay_wall"] = rng.random() < 0.5
+    kw["account_first_and_last_bounces"] = rng.random() < 0.5
+    kw["discard_direct_paths"] = rng.random() < 0.3
+    if rng.random() < 0.3: kw["filter_depth"] = rng.choice([2, 3, 4])
+    kw["max_depth"] = rng.choice([3, 4, 6, 8, -1]) if "filter_depth" not in kw else rng.choice([5, 6, 8])
+    kw["rr_depth"] = rng.choice([1, 2, 5])
+    w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
+    spp = rng.choice([4, 8, 16])
+    if cap == "exhaustive": spp = 4
+    d = mitr.nlos_z_scene(w, h, 48, spp, start_opl=0.0, window=16.0, **kw)
+    if not kw["nlos_laser_sampling"]:
+        d["emitter"]["fov"] = rng.choice([60.0, 120.0])
+    if rng.random() < 0.4:
+        d["occluder"] = {"type": "rectangle", "to_world": T().translate([-0.25, 0.1, 0.5]).scale([0.3, 0.3, 1.0]),
+                         "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.7}}}
+    if cap == "exhaustive":
+        f = d["relay_wall"]["nlos_sensor"]["transient_film"]
+        f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, w, h
+    scene = mitr.load_dict(d)
+    if cap == "single":
+        mitr.nlos.focus_emitter_at_relay_wall_pixel((rng.randrange(w), rng.randrange(h)), mitr.PluginSpec(d["relay_wall"]), scene.emitters()[0]["spec"])
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    ok = cmp("nlos", (kw, w, h, spp, seed, "occ" in "".join(d.keys())), dep, r)
+    if cap == "exhaustive" and ok:
+        ok = np.array_equal(raw != 0, r["transient"] != 0) and np.abs(raw - r["transient"]).max() <= 1e-6 * max(1, np.abs(raw).max())
+        if not ok: print("FAIL exhaustive film", kw)
+    return ok
+
+GOLD = {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]}, "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}
+BSDFS = [None, {"type": "conductor", "material": "none"}, {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0},
+         {"type": "twosided", "bsdf": GOLD}, {"type": "null"}, GOLD, {"type": "dielectric", "int_ior": "water", "ext_ior": "air"},
+         {"type": "dielectric", "int_ior": 1.0, "ext_ior": 1.5},
+         {"type": "conductor", "eta": 0.2, "k": 3.9, "specular_reflectance": {"type": "rgb", "value": [0.9, 0.5, 0.3]}},
+         {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.2, 0.9, 0.4]}},
+         {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.3}}]
+
+def fuzz_path(rng, i):
+    integ = {"max_depth": rng.choice([2, 3, 5, 8, 12, -1]), "rr_depth": rng.choice([1, 2, 3, 5]),
+             "camera_unwarp": rng.random() < 0.4, "discard_direct_light": rng.random() < 0.3}
+    w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
+    spp = rng.choice([4, 8])
+    d = mitr.cornell_box_config(w, h, 32, spp, max_depth=8)
+    d["integrator"].update(integ)
+    bs = {}
+    for shape in ("small-box", "large-box", "back", "floor"):
+        b = rng.choice(BSDFS if shape.endswith("box") else [None, None] + BSDFS[:4] + BSDFS[5:])
+        if b is not None: d[shape]["bsdf"] = b; bs[shape] = b["type"] + str(b.get("material", b.get("int_ior", "")))
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render(scene, "mitransient.integrators.transientpath", "TransientPath", props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    ok = cmp("path", (integ, bs, w, h, spp, seed), dep, r)
+    if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
+    return ok
+
+def fuzz_vol(rng, i):
+    integ = {"max_depth": rng.choice([2, 3, 6, 12, -1]), "rr_depth": rng.choice([1, 2, 5]),
+             "camera_unwarp": rng.random() < 0.4, "hide_emitters": rng.random() < 0.3}
+    w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
+    spp = rng.choice([4, 8])
+    media = rng.random() < 0.8
+    d = mitr.cornell_box_volumetric(w, h, 32, spp, max_depth=8) if media else mitr.cornell_box_config(w, h, 32, spp, max_depth=8)
+    if not media: d["integrator"] = {"type": "transient_prbvolpath", "temporal_filter": "box"}
+    d["integrator"].update(integ)
+    if media:
+        for shape in ("small-box", "large-box"):
+            d[shape]["interior"]["sigma_t"] = rng.choice([0.5, 2.0, 5.0, 14.0])
+            d[shape]["interior"]["phase"]["g"] = rng.choice([-0.5, 0.0, 0.1, 0.7])
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render_vol(scene, props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    ok = cmp("vol", (integ, media, w, h, spp, seed), dep, r)
+    if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
+    return ok
+
+FUZZERS = {"nlos": fuzz_nlos, "path": fuzz_path, "vol": fuzz_vol}
+
+
+def run_one(which, seed):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return FUZZERS[which](random.Random(seed), seed)
+
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore")
+    which, n, s0 = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    fn = FUZZERS[which]
+    bad = 0
+    for i in range(n):
+        rng = random.Random(s0 + i)
+        try:
+            if not fn(rng, i): bad += 1; print("   ^ seed", s0 + i)
+        except Exception as e:
+            print("EXC seed", s0 + i, type(e).__name__, str(e)[:300]); traceback.print_exc(limit=3)
+    print("bad:", bad, "of", n)

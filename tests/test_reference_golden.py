@@ -363,3 +363,14 @@ def test_gpu_phasor_render_equals_the_reference(mitr, mono, name):
     raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
     ref = GP[name + "_raw"]
     assert np.abs(raw - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------ random option sweeps (live)
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mitransient"), reason="the reference tree is not available here")
+@pytest.mark.parametrize("which,seed", [("path", 1300), ("path", 1307), ("path", 1311), ("nlos", 105), ("nlos", 1203), ("nlos", 1210),
+                                        ("nlos", 1226), ("vol", 1400), ("vol", 1403), ("vol", 1409)])
+def test_oracle_equals_the_executed_reference_on_random_configurations(mitr, oracle, which, seed):
+    """A slice of tests/golden/fuzz_reference.py (200 configurations were swept when it was written): random integrator
+    options, BSDFs, media parameters and occluders; the oracle's deposits must equal the executed reference's."""
+    import fuzz_reference
+    assert fuzz_reference.run_one(which, seed)
