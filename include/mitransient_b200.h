@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 11
+#define TR_ABI_VERSION 12
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -144,13 +144,19 @@ typedef struct TrSensorDesc {
 enum { TR_FILM_TRANSIENT_HDR = 0, TR_FILM_PHASOR_HDR = 1 };
 
 typedef struct TrFilmDesc {  /* mitransient/films/transient_hdr_film.py:114-121             */
-    uint32_t width, height;
+    uint32_t width, height;        /* the rendered window = film.crop_size() (the whole film unless a crop window is
+                                      set): the block the reference allocates (transient_hdr_film.py:192-197)          */
     uint32_t temporal_bins;
     float start_opl;
     float bin_width_opl;
     uint32_t laser_scan_width, laser_scan_height; /* exhaustive_scan film (transient_hdr_film.py:119-121); 0, 0 = off */
     uint32_t type;                 /* TR_FILM_*                                             */
     uint32_t n_frequencies;        /* phasor film: F                                        */
+    uint32_t crop_offset_x, crop_offset_y; /* film.crop_offset(): where the window sits in the full film.  Enters only the
+                                      film-sample arithmetic of ADIntegrator.sample_rays [upstream]: pos = pixel + offset,
+                                      sample = fma(pos + jitter, 1/crop_size, -offset/crop_size); sample_to_camera is built
+                                      for the window.  The block subtracts the offset again
+                                      (transient_image_block.py:131), so film[y][x] is window-relative.                 */
     uint32_t _pad;
     const float *frequencies;      /* phasor film: host, [F] (phasor_hdr_film.py:125-137)   */
 } TrFilmDesc;

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 11
+TR_ABI_VERSION = 12
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -67,7 +67,8 @@ class TrFilmDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("temporal_bins", C.c_uint32),
                 ("start_opl", C.c_float), ("bin_width_opl", C.c_float),
                 ("laser_scan_width", C.c_uint32), ("laser_scan_height", C.c_uint32),
-                ("type", C.c_uint32), ("n_frequencies", C.c_uint32), ("_pad", C.c_uint32),
+                ("type", C.c_uint32), ("n_frequencies", C.c_uint32),
+                ("crop_offset_x", C.c_uint32), ("crop_offset_y", C.c_uint32), ("_pad", C.c_uint32),
                 ("frequencies", C.POINTER(C.c_float))]
 
 

@@ -13,7 +13,7 @@ namespace tr {
 // registers first (match.any + shuffle reduction) so that one vector RED per distinct bin reaches L2.
 __global__ void __launch_bounds__(256) film_scatter_add_kernel(float *__restrict__ film, const TrDeposit *__restrict__ dep,
                                                                unsigned long long n, uint32_t W, uint32_t H, uint32_t T,
-                                                               float start_opl, float bin_width, int C) {
+                                                               float start_opl, float bin_width, int C, float crop_x, float crop_y) {
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     const float Tf = (float) T;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) film_scatter_add_kernel(float *__restrict
             float pos = (d.opl - start_opl) / bin_width;              // transient_hdr_film.py:263
             ok = (pos >= 0.0f) && (pos < Tf) && !(r == 0.0f && g == 0.0f && b == 0.0f);   // :265
             if (ok) {
-                float fx = floorf(d.x), fy = floorf(d.y);             // transient_image_block.py:131
+                float fx = floorf(d.x) - crop_x, fy = floorf(d.y) - crop_y;   // floor(pos) - offset  transient_image_block.py:131
                 ok = fx >= 0.0f && fy >= 0.0f && fx < (float) W && fy < (float) H;       // :146
                 if (ok) {
                     uint32_t x = (uint32_t) fx, y = (uint32_t) fy, z = (uint32_t) floorf(pos);
@@ -109,7 +109,7 @@ int tr_film_scatter_add(float *film, const TrFilmDesc *fd, int32_t channels, con
     int grid = (int) std::min<unsigned long long>(blocks, (unsigned long long) n_sm * 8);
     tr::film_scatter_add_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(film, deposits, n, fd->width, fd->height,
                                                                         fd->temporal_bins, fd->start_opl, fd->bin_width_opl,
-                                                                        channels);
+                                                                        channels, (float) fd->crop_offset_x, (float) fd->crop_offset_y);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }

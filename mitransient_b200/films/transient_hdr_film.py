@@ -37,6 +37,7 @@ class TransientHDRFilm:
         props.get("pixel_format"), props.get("component_format"), props.get("file_format")
         self.channels = list("RGBW")           # no FilmFlags.Alpha on a Python mi.Film subclass
         self.transient_storage = None          # torch.float32 CUDA tensor (H, W, T, C), like TransientImageBlock.tensor
+        self._window_storage = None
         self.steady_storage = None             # torch.float32 CUDA tensor (H, W, 3), the developed steady image
 
     # ---- mi.Film accessors
@@ -63,7 +64,9 @@ class TransientHDRFilm:
 
     def describe(self) -> _abi.TrFilmDesc:
         d = _abi.TrFilmDesc()
-        d.width, d.height, d.temporal_bins = self._width, self._height, self.temporal_bins
+        # the block covers the crop window (transient_hdr_film.py:192-197); the whole film unless one is set
+        d.width, d.height, d.temporal_bins = self._crop_size[0], self._crop_size[1], self.temporal_bins
+        d.crop_offset_x, d.crop_offset_y = self._crop_offset
         d.start_opl, d.bin_width_opl = self.start_opl, self.bin_width_opl
         d.type = _abi.TR_FILM_TRANSIENT_HDR
         if self.exhaustive_scan:               # transient_image_block.py:59-66
@@ -88,9 +91,12 @@ class TransientHDRFilm:
                              "(only the box reconstruction filter)")
         if self.exhaustive_scan and (self.laser_scan_width <= 0 or self.laser_scan_height <= 0):
             raise ValueError("exhaustive_scan needs laser_scan_width and laser_scan_height > 0")
-        if self._crop_offset != (0, 0) or self._crop_size != (self._width, self._height):
-            raise NotImplementedError("crop windows are not supported by the transient block "
-                                      "(the reference sizes it from size(), transient_hdr_film.py:194-195)")
+        cropped = self._crop_offset != (0, 0) or self._crop_size != (self._width, self._height)
+        if cropped and self.exhaustive_scan:   # "this type of scanning does not support cropping" (transient_hdr_film.py:87)
+            raise ValueError("exhaustive_scan films do not support crop windows")
+        if (min(self._crop_offset) < 0 or min(self._crop_size) <= 0 or self._crop_offset[0] + self._crop_size[0] > self._width
+                or self._crop_offset[1] + self._crop_size[1] > self._height):
+            raise ValueError("Film: the crop window must lie inside the film")
 
     # ---- lifecycle (transient_hdr_film.py:129-148, 173-202)
     def prepare(self, aovs: Sequence[str] = ()):
@@ -100,18 +106,42 @@ class TransientHDRFilm:
         if len(aovs):
             raise NotImplementedError("AOVs are not supported")
         _lib.check(_lib.load().tr_device_check())
-        w, h = self.size()
+        w, h = self.crop_size()
         if self.exhaustive_scan:               # (H, W, Lh, Lw, T, C)   transient_image_block.py:63-66
             shape = (h, w, self.laser_scan_height, self.laser_scan_width, self.temporal_bins, len(self.channels))
         else:
             shape = (h, w, self.temporal_bins, len(self.channels))
-        self.transient_storage = torch.zeros(shape, dtype=torch.float32, device="cuda")
+        self._window_storage = None
+        if self.is_cropped():
+            # The reference sizes the transient block from size(), not crop_size(), while giving it the crop OFFSET
+            # (transient_hdr_film.py:192-195): the tensor keeps the full film's shape and the rendered window sits in
+            # its top-left corner.  The kernel renders the window into a dense tensor of its own; finish_render()
+            # pastes it into that corner.  (The steady hdrfilm is sized by the crop window, :131-144.)
+            fw, fh = self.size()
+            self._window_storage = torch.zeros(shape, dtype=torch.float32, device="cuda")
+            self.transient_storage = torch.zeros((fh, fw) + shape[2:], dtype=torch.float32, device="cuda")
+        else:
+            self.transient_storage = torch.zeros(shape, dtype=torch.float32, device="cuda")
         self.steady_storage = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
         return len(self.channels)
+
+    def is_cropped(self) -> bool:
+        return self._crop_offset != (0, 0) or self._crop_size != (self._width, self._height)
+
+    def render_target(self):
+        """The dense (crop_h, crop_w, T, C) tensor the integrator's kernel writes."""
+        return self._window_storage if self._window_storage is not None else self.transient_storage
+
+    def finish_render(self):
+        if self._window_storage is not None:
+            w, h = self.crop_size()
+            self.transient_storage[:h, :w] = self._window_storage
 
     def clear(self):
         if self.transient_storage is not None:
             self.transient_storage.zero_()
+        if getattr(self, "_window_storage", None) is not None:
+            self._window_storage.zero_()
         if self.steady_storage is not None:
             self.steady_storage.zero_()
 
@@ -131,6 +161,7 @@ class TransientHDRFilm:
         dep = torch.cat([pos.reshape(n, 2), distance.reshape(n, 1), spec.reshape(n, 3)], dim=1)
         dep = dep.to(device="cuda", dtype=torch.float32).contiguous()
         fd = self.describe()
+        fd.width, fd.height = self.size()      # the block is film-sized even under a crop window (see prepare())
         _lib.check(_lib.load().tr_film_scatter_add(self.transient_storage.data_ptr(), C.byref(fd),
                                                    len(self.channels), dep.data_ptr(), n,
                                                    _lib.current_stream_ptr()))

@@ -130,7 +130,7 @@ class TransientADIntegrator:
                                       film_channels=film.raw_channels(),
                                       accumulate=(i > 0) or film.needs_zeroed_accumulate())
             self.fill_params_(params, scene, sensor)
-            _lib.check(lib.tr_render(dev.handle, C.byref(params), film.transient_storage.data_ptr(),
+            _lib.check(lib.tr_render(dev.handle, C.byref(params), film.render_target().data_ptr(),
                                      film.steady_storage.data_ptr(),
                                      counters.data_ptr() if counters is not None else None,
                                      _lib.current_stream_ptr()))
@@ -140,6 +140,7 @@ class TransientADIntegrator:
             c = counters.cpu().tolist()
             self.last_counters = dict(zip(("paths", "vertices", "deposits", "deposits_in_range", "bin_checksum",
                                            "shadow_rays"), c[:6]))
+        film.finish_render()
         steady, transient = film.develop()
         if evaluate:
             torch.cuda.current_stream().synchronize()
@@ -161,13 +162,13 @@ class TransientADIntegrator:
         self.check_transient_(scene, sensor)
         self.check_scene_(scene, sensor)
         film.check_supported()
-        if film.raw_channels() != 4 or film.needs_zeroed_accumulate():
-            raise NotImplementedError("render_to_host supports plain transient_hdr_film films")
+        if film.raw_channels() != 4 or film.needs_zeroed_accumulate() or film.is_cropped():
+            raise NotImplementedError("render_to_host supports plain transient_hdr_film films without a crop window")
         s = sensor.sampler().clone()
         if spp != 0:
             s.set_sample_count(spp)
         spp = s.sample_count()
-        w, h = film.size()
+        w, h = film.crop_size()
         ch = 4 if raw else 3
         if world > 1:
             from ..distributed import owned_pixels

@@ -465,7 +465,7 @@ class Scene:
     def description_key(self, sensor):
         f = sensor.film()
         em = tuple(_to_transform(e["spec"].get("to_world")).matrix.tobytes() for e in self.emitters_ if e.get("spec"))
-        return (id(sensor), f.size(), f.temporal_bins, float(f.start_opl), float(f.bin_width_opl),
+        return (id(sensor), f.size(), f.crop_size(), f.crop_offset(), f.temporal_bins, float(f.start_opl), float(f.bin_width_opl),
                 sensor.state_key(), em, _variant.is_monochromatic(), f.state_key())
 
     def __repr__(self):

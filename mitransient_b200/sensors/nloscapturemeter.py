@@ -36,6 +36,9 @@ class NLOSCaptureMeter(NLOSSensor):
         self._film = fspec if not isinstance(fspec, dict) else plugins.instantiate(fspec)
         _, sspec = _find_child(props, ("independent",))
         self._sampler = IndependentSampler(Properties(sspec or {}))
+        if hasattr(self._film, "crop_size") and (tuple(self._film.crop_size()) != tuple(self._film.size()) or tuple(self._film.crop_offset()) != (0, 0)):
+            # the reference's sensor divides crop-relative film samples by the FULL film size (nloscapturemeter.py:133-150)
+            raise NotImplementedError("nlos_capture_meter: films with a crop window are not supported")
         self.original_film_width = props.get("original_film_width", None)
         self.original_film_height = props.get("original_film_height", None)
         if self.original_film_width is None or self.original_film_height is None:

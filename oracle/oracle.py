@@ -85,7 +85,7 @@ def render(scene, integrator, sensor=0, seed=0, spp=0, raw=True, n_threads=0, ra
         s.set_sample_count(spp)
     spp = s.sample_count()
     desc = scene.describe(sensor)
-    w, h = film.size()
+    w, h = film.crop_size()
     if desc.film.type == _abi.TR_FILM_PHASOR_HDR:      # (H, W, 2F + 1), always raw
         C_ = film.raw_channels()
         shape = (h, w, C_)
@@ -106,6 +106,13 @@ def render(scene, integrator, sensor=0, seed=0, spp=0, raw=True, n_threads=0, ra
     _check(lib.oracle_render(C.byref(desc), C.byref(params), out.ctypes.data, steady.ctypes.data, C.byref(cnt),
                              int(n_threads), log.ctypes.data if log_deposits else None, int(log_deposits),
                              C.byref(n_logged)))
+    if getattr(film, "is_cropped", lambda: False)():
+        # the reference's transient block keeps the full film's shape with the window in its top-left corner
+        # (transient_hdr_film.py:192-195)
+        fw, fh = film.size()
+        full = np.zeros((fh, fw) + out.shape[2:], dtype=np.float32)
+        full[:h, :w] = out
+        out = full
     return {"steady": steady, "transient": out, "counters": cnt.as_dict(),
             "deposits": log[: n_logged.value] if log_deposits else None}
 

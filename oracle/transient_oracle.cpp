@@ -611,11 +611,13 @@ struct Film {
         V3 value = (spec * sample_scale) * ray_weight;
         if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) return;  // x + 0 == x: skipping is exact
         cnt->deposits++;
-        if (log) log->push_back(TrDeposit{px, py, distance, value.x, value.y, value.z});
+        if (log)    // positions are logged as the reference's add_transient_data receives them: film coordinates (window + offset)
+            log->push_back(TrDeposit{px + (float) fd.crop_offset_x, py + (float) fd.crop_offset_y, distance, value.x, value.y, value.z});
         if (fd.type == TR_FILM_PHASOR_HDR) { add_phasor(px, py, value, distance); return; }
         float pos_distance = (distance - fd.start_opl) / fd.bin_width_opl;
         bool mask = (pos_distance >= 0.0f) && (pos_distance < (float) fd.temporal_bins);
         if (!mask) return;
+        if (!(px >= 0.0f && py >= 0.0f)) return;                                             // :146  0 <= p
         uint32_t x = (uint32_t) floorf(px), y = (uint32_t) floorf(py), z = (uint32_t) floorf(pos_distance);
         if (!(x < fd.width && y < fd.height && z < fd.temporal_bins)) return;
         uint64_t pix = (uint64_t) y * fd.width + x;
@@ -632,6 +634,7 @@ struct Film {
     inline void add_phasor(float px, float py, V3 value, float distance) {
         float opl = distance - fd.start_opl;                                                 // :255
         if (!std::isfinite(opl)) return;                                                     // phasor_image_block.py:50
+        if (!(px >= 0.0f && py >= 0.0f)) return;
         uint32_t x = (uint32_t) floorf(px), y = (uint32_t) floorf(py);
         if (!(x < fd.width && y < fd.height)) return;
         uint64_t pix = (uint64_t) y * fd.width + x;
@@ -652,8 +655,10 @@ struct Film {
 inline Ray sample_camera_ray(const Scene &sc, uint32_t px, uint32_t py, float jx, float jy) {
     // ADIntegrator.sample_rays + perspective.sample_ray [upstream]
     const TrSensorDesc &se = sc.sensor;
-    float fx = (float) px + jx, fy = (float) py + jy;
-    float sx = fx * (1.0f / (float) sc.film.width), sy = fy * (1.0f / (float) sc.film.height);
+    // pos = pixel + crop_offset; pos_adjusted = fma(pos + jitter, rcp(crop_size), -crop_offset * rcp(crop_size))
+    float scx = 1.0f / (float) sc.film.width, scy = 1.0f / (float) sc.film.height;
+    float fx = (float) (px + sc.film.crop_offset_x) + jx, fy = (float) (py + sc.film.crop_offset_y) + jy;
+    float sx = fmaf(fx, scx, -(float) sc.film.crop_offset_x * scx), sy = fmaf(fy, scy, -(float) sc.film.crop_offset_y * scy);
     const float *m = se.sample_to_camera;
     float cx = fmaf(m[0], sx, fmaf(m[1], sy, m[3]));
     float cy = fmaf(m[4], sx, fmaf(m[5], sy, m[7]));
@@ -1587,8 +1592,10 @@ int oracle_film_scatter_add(float *film, const TrFilmDesc *fd, int channels, con
     if (!film || !fd || !dep) { g_err = "null argument"; return TR_ERR_INVALID_ARGUMENT; }
     TrCounters cnt{};
     Film f{*fd, film, channels, &cnt, nullptr};
+    // recorded positions are film coordinates: the block subtracts its offset, floor(pos) - offset (:131)
+    const float ox = (float) fd->crop_offset_x, oy = (float) fd->crop_offset_y;
     for (uint64_t i = 0; i < n; ++i)
-        f.add_transient(dep[i].x, dep[i].y, v3(dep[i].r, dep[i].g, dep[i].b), dep[i].opl, 1.0f, 1.0f);
+        f.add_transient(floorf(dep[i].x) - ox, floorf(dep[i].y) - oy, v3(dep[i].r, dep[i].g, dep[i].b), dep[i].opl, 1.0f, 1.0f);
     return TR_OK;
 }
 

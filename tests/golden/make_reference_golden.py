@@ -74,6 +74,20 @@ out["film_exh_deposits"], out["film_exh_laser"] = dep, np.stack([lx, ly], axis=1
 out["film_exh_raw"] = raw.numpy()
 meta["film_exh"] = props
 
+# a crop window: the transient block keeps the FULL film's size but takes the crop offset (transient_hdr_film.py:192-195),
+# so deposits land at (pos - offset) inside a film-sized tensor and positions left of / above the window are dropped
+props = dict(width=9, height=7, temporal_bins=16, start_opl=0.5, bin_width_opl=0.4, crop_width=4, crop_height=3,
+             crop_offset_x=3, crop_offset_y=2)
+film = thf.TransientHDRFilm(mi.Properties(**props))
+film.prepare([])
+dep = deposits(np.random.default_rng(77), 5000, 9, 7, 0.0, 8.0, 0.5, 0.4, 16)
+film.add_transient_data(mi.Vector2f(dep[:, 0], dep[:, 1]), mi.Float(dep[:, 2]), None, mi.Spectrum(dep[:, 3], dep[:, 4], dep[:, 5]),
+                        mi.Float(1.0), mi.Bool(np.ones(len(dep), dtype=bool)))
+out["film_d_deposits"], out["film_d_raw"] = dep, film.develop_transient_(raw=True).numpy()
+out["film_d_developed"] = film.develop_transient_(raw=False).numpy()
+assert out["film_d_raw"].shape == (7, 9, 16, 4) and np.all(out["film_d_raw"][:, 6:] == 0) and np.all(out["film_d_raw"][5:] == 0)
+meta["film_d"] = props
+
 # ------------------------------------------------------------------ C: phasor_hdr_film (monochromatic variant)
 mi, dr = refshim.install(True, mitr.ScalarTransform4f, mitr.ScalarColor3d)
 phf = refshim.ref_module("mitransient.films.phasor_hdr_film")

@@ -16,6 +16,9 @@ PATH_CASES = {
                                                        "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}},
                 "small-box": {"type": "dielectric", "int_ior": 1.33, "ext_ior": 1.0}}),
     "path_g": ((6, 6, 48, 8), {"max_depth": 8}, "volumetric"),
+    # a crop window (crop_width, crop_height, crop_offset_x, crop_offset_y) of a 12 x 10 film: sample_rays shifts the pixels,
+    # the block subtracts the offset again and keeps the film's size (transient_hdr_film.py:192-195)
+    "path_h": ((12, 10, 32, 8), {"max_depth": 6, "crop": (5, 4, 6, 3)}, {}),
 }
 
 
@@ -27,6 +30,10 @@ def path_case_scene(name):
         d["integrator"].update(integ)
         return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
     d = mitr.cornell_box_config(*cfg, window=(3.5, 12.5))
+    integ = dict(integ)
+    crop = integ.pop("crop", None)
+    if crop is not None:
+        d["sensor"]["film"].update(crop_width=crop[0], crop_height=crop[1], crop_offset_x=crop[2], crop_offset_y=crop[3])
     d["integrator"].update(integ)
     for shape, b in bsdfs.items():
         d[shape]["bsdf"] = b

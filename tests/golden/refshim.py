@@ -663,14 +663,14 @@ class ShimSampler:
 
 
 class ShimSteadyBlock:
-    def __init__(self, film): self.film = film; self.data = np.zeros((film.h, film.w, 4), dtype=np.float32)
+    def __init__(self, film): self.film = film; self.offset = film.offset; self.data = np.zeros((film.h, film.w, 4), dtype=np.float32)
     def coalesce(self): return False
     def set_coalesce(self, v): pass
 
 
 class ShimSteadyFilm:
     """hdrfilm + ImageBlock (box): put accumulates [R, G, B, weight] at floor(pos); develop = colour / weight."""
-    def __init__(self, w, h): self.w, self.h, self.acc = w, h, np.zeros((h, w, 4), dtype=np.float32)
+    def __init__(self, w, h, offset=(0, 0)): self.w, self.h, self.offset, self.acc = w, h, offset, np.zeros((h, w, 4), dtype=np.float32)
     def prepare(self, aovs): self.acc[...] = 0; return 3
     def clear(self): self.acc[...] = 0
     def base_channels_count(self): return 3
@@ -680,6 +680,13 @@ class ShimSteadyFilm:
     def develop(self, raw=False):
         w = self.acc[..., 3:4]
         return self.acc[..., :3] / np.where(w == 0, 1, w)
+
+
+def _steady_film_from_dict(d):
+    """mi.load_dict({'type': 'hdrfilm', ...}) as TransientHDRFilm.prepare issues it (transient_hdr_film.py:131-144): sized by
+    the crop window."""
+    return ShimSteadyFilm(int(d.get("crop_width", d["width"])), int(d.get("crop_height", d["height"])),
+                          (int(d.get("crop_offset_x", 0)), int(d.get("crop_offset_y", 0))))
 
 
 class ShimSensor:
@@ -700,13 +707,15 @@ class ShimADIntegrator(ADIntegrator):
 
     def sample_rays(self, scene, sensor, sampler, reparam=None):
         global LANES
-        w, h = int(sensor.film().size().x), int(sensor.film().size().y)
+        film = sensor.film()                                   # film_size = film.crop_size(); pos += film.crop_offset()
+        w, h = int(film.crop_size().x), int(film.crop_size().y)
+        ox, oy = int(film.crop_offset().x), int(film.crop_offset().y)
         spp = sampler.sample_count()
         LANES = w * h * spp
         idx = np.arange(LANES, dtype=np.int64) // spp
         py, px = idx // w, idx % w
         jitter = sampler.next_2d()
-        pos = LVec2.__new__(LVec2); pos.c = (px.astype(np.float32).view(DrArray), py.astype(np.float32).view(DrArray))
+        pos = LVec2.__new__(LVec2); pos.c = ((px + ox).astype(np.float32).view(DrArray), (py + oy).astype(np.float32).view(DrArray))
         if hasattr(sensor, "sample_ray_differential"):        # a reference sensor class (nlos_capture_meter): run ITS code
             scale = LVec2(np.float32(1.0) / np.float32(w), np.float32(1.0) / np.float32(h))       # rcp(film_size)
             pos_adjusted = (pos + jitter) * scale
@@ -719,7 +728,7 @@ class ShimADIntegrator(ADIntegrator):
 
     @staticmethod
     def _splat_to_block(block, film, pos, value, weight, alpha, aovs, wavelengths):
-        x, y = np.asarray(pos.x).astype(np.int64), np.asarray(pos.y).astype(np.int64)
+        x, y = np.asarray(pos.x).astype(np.int64) - block.offset[0], np.asarray(pos.y).astype(np.int64) - block.offset[1]
         for k, v in enumerate((value.x, value.y, value.z, np.full(LANES, weight, dtype=np.float32))):
             np.add.at(block.data[..., k], (y, x), np.asarray(v, dtype=np.float32))
 
@@ -800,7 +809,9 @@ def reference_render(our_scene, integrator_module, integrator_cls, props, spp, s
         film.develop_transient_ = lambda raw=True: film.develop_phasors_(raw=raw)
     else:
         film = thf.TransientHDRFilm(mi.Properties(width=f.size()[0], height=f.size()[1], temporal_bins=f.temporal_bins,
-                                                  start_opl=f.start_opl, bin_width_opl=f.bin_width_opl))
+                                                  start_opl=f.start_opl, bin_width_opl=f.bin_width_opl,
+                                                  crop_width=f.crop_size()[0], crop_height=f.crop_size()[1],
+                                                  crop_offset_x=f.crop_offset()[0], crop_offset_y=f.crop_offset()[1]))
     log = []
     inner = film.add_transient_data
 
@@ -814,7 +825,7 @@ def reference_render(our_scene, integrator_module, integrator_cls, props, spp, s
         return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
     film.add_transient_data = logged
     _real_load = mi.load_dict
-    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    mi.load_dict = lambda d: _steady_film_from_dict(d) if d.get("type") == "hdrfilm" else _real_load(d)
     scene = ShimScene(our_scene, sensor)
     _CURRENT["osv"] = scene.osv
     shim_sensor = ShimSensor(film, spp)
@@ -1105,7 +1116,7 @@ def reference_render_nlos(our_scene, props, spp, seed=0):
         return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
     film.add_transient_data = logged
     _real_load = mi.load_dict
-    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    mi.load_dict = lambda d: _steady_film_from_dict(d) if d.get("type") == "hdrfilm" else _real_load(d)
     scene = ShimScene(our_scene, sensor)
     _CURRENT["osv"] = scene.osv
     wall_index = int(scene.osv.lib.osv_sensor_shape(C.c_void_p(scene.osv.h)))
@@ -1268,7 +1279,7 @@ def reference_render_angular(our_scene, props, spp, seed=0):
         return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
     film.add_transient_data = logged
     _real_load = mi.load_dict
-    mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+    mi.load_dict = lambda d: _steady_film_from_dict(d) if d.get("type") == "hdrfilm" else _real_load(d)
     scene = AngularScene(our_scene, sensor)
     _CURRENT["osv"] = scene.osv
     em = our_scene.emitters()[0]
@@ -1543,7 +1554,7 @@ def reference_render_vol(our_scene, props, spp, seed=0):
             return inner(pos, distance, wavelengths, spec, ray_weight, active, **kw)
         film.add_transient_data = logged
         _real_load = mi.load_dict
-        mi.load_dict = lambda d: ShimSteadyFilm(d["width"], d["height"]) if d.get("type") == "hdrfilm" else _real_load(d)
+        mi.load_dict = lambda d: _steady_film_from_dict(d) if d.get("type") == "hdrfilm" else _real_load(d)
         scene = VScene(our_scene, sensor)
         _CURRENT["osv"] = osv_holder["osv"] = scene.osv
         shim_sensor = ShimSensor(film, spp)

@@ -276,3 +276,25 @@ def test_ply_loader_ascii_and_binary(mitr, tmp_path):
     scene = mitr.load_dict({"type": "scene", "m": {"type": "ply", "filename": str(path), "bsdf": {"type": "diffuse"}}})
     shape = scene.shapes()[0]
     assert len(shape.prims) == 2 and sorted(shape.prim_types.tolist()) == [0, 1]     # the quad was merged, the triangle kept
+
+
+def test_crop_window_film_descriptor(mitr):
+    """A crop window renders crop_size() pixels (film.describe: width / height = the window, plus its offset); the
+    exhaustive layout and the NLOS sensor reject it like the reference's documentation says / code implies."""
+    props = {"type": "transient_hdr_film", "width": 12, "height": 10, "temporal_bins": 8, "crop_width": 5, "crop_height": 4,
+             "crop_offset_x": 6, "crop_offset_y": 3}
+    film = mitr.load_dict(props)
+    d = film.describe()
+    assert (d.width, d.height, d.crop_offset_x, d.crop_offset_y) == (5, 4, 6, 3)
+    assert film.size() == (12, 10) and film.crop_size() == (5, 4) and film.is_cropped()
+    film.check_supported()
+    plain = mitr.load_dict({"type": "transient_hdr_film", "width": 12, "height": 10, "temporal_bins": 8})
+    assert not plain.is_cropped() and (plain.describe().crop_offset_x, plain.describe().crop_offset_y) == (0, 0)
+    with pytest.raises(ValueError, match="crop window must lie inside"):
+        mitr.load_dict({**props, "crop_offset_x": 9}).check_supported()
+    with pytest.raises(ValueError, match="exhaustive_scan"):
+        mitr.load_dict({**props, "exhaustive_scan": True, "laser_scan_width": 2, "laser_scan_height": 2}).check_supported()
+    d = mitr.nlos_z_scene(8, 8, 16, 4)
+    d["relay_wall"]["nlos_sensor"]["transient_film"].update(crop_width=4, crop_height=4)
+    with pytest.raises(NotImplementedError, match="crop window"):
+        mitr.load_dict(d)

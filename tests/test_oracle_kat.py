@@ -391,3 +391,21 @@ def test_glass_slab_optical_path_length(oracle, mitr):
     assert direct == pytest.approx(2.0 * 0.96 ** 2, rel=0.02)
     assert bounce == pytest.approx(2.0 * 0.96 ** 2 * 0.04 ** 2, rel=0.25)
     assert film[:b0 - 1].sum() == 0.0                                                # nothing arrives earlier
+
+
+def test_crop_window_camera_rays_are_the_full_films_rays(oracle, mitr):
+    """Film crop windows (ADIntegrator.sample_rays [upstream]: pos = pixel + crop_offset, sample = fma(pos + jitter,
+    1 / crop_size, -crop_offset / crop_size); perspective sensor: sample_to_camera built for the window): pixel (x, y) of
+    the window looks along the same ray as pixel (x + ox, y + oy) of the whole film."""
+    full = mitr.load_dict(mitr.cornell_box_config(12, 10, 32, 8))
+    d = mitr.cornell_box_config(12, 10, 32, 8)
+    d["sensor"]["film"].update(crop_width=5, crop_height=4, crop_offset_x=6, crop_offset_y=3)
+    win = mitr.load_dict(d)
+    for (x, y, jx, jy) in [(0, 0, 0.1, 0.9), (4, 3, 0.5, 0.5), (2, 1, 0.99, 0.01), (0, 3, 0.0, 0.0)]:
+        o1, d1, m1 = oracle.camera_ray(win, win.sensors()[0], x, y, jx, jy)
+        o2, d2, m2 = oracle.camera_ray(full, full.sensors()[0], x + 6, y + 3, jx, jy)
+        assert np.abs(d1 - d2).max() < 2e-7 and np.abs(o1 - o2).max() < 2e-7 and abs(m1 - m2) < 1e-3
+    # and the rendered window has the window's shape while the reference-shaped tensor keeps the film's
+    r = oracle.render(win, win.integrator(), spp=4, seed=1)
+    assert r["steady"].shape == (4, 5, 3) and r["transient"].shape == (10, 12, 32, 4)
+    assert np.all(r["transient"][4:] == 0) and np.all(r["transient"][:, 5:] == 0) and r["transient"].sum() > 0

@@ -21,16 +21,18 @@ def _film_desc(mitr, props, frequencies=None):
     fd.start_opl, fd.bin_width_opl = props["start_opl"], props["bin_width_opl"]
     if props.get("exhaustive_scan"):
         fd.laser_scan_width, fd.laser_scan_height = props["laser_scan_width"], props["laser_scan_height"]
+    fd.crop_offset_x, fd.crop_offset_y = props.get("crop_offset_x", 0), props.get("crop_offset_y", 0)   # block: film-sized + offset
     if frequencies is not None:
         fd.type, fd.n_frequencies = mitr._abi.TR_FILM_PHASOR_HDR, len(frequencies)
         fd.frequencies = frequencies.ctypes.data_as(C.POINTER(C.c_float))
     return fd
 
 
-@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c"])
+@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c", "film_d"])
 def test_oracle_film_equals_reference_film_bit_for_bit(mitr, oracle, tag):
     """add_transient_data + TransientImageBlock.put_ + accum + develop_transient_ (transient_hdr_film.py:250-276,
-    220-248; transient_image_block.py:83-151): window edges, inf / nan distances, zero deposits, W channel."""
+    220-248; transient_image_block.py:83-151): window edges, inf / nan distances, zero deposits, W channel; film_d has
+    a crop window (film-sized block addressed at pos - crop_offset, :131 and transient_hdr_film.py:192-195)."""
     props = META[tag]
     film = np.zeros(G[tag + "_raw"].shape, dtype=np.float32)
     oracle.film_scatter_add(film, _film_desc(mitr, props), G[tag + "_deposits"])
@@ -130,7 +132,7 @@ def test_tonemap_equals_reference(mitr):
 
 # ------------------------------------------------------------------------------------------ GPU kernels
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c"])
+@pytest.mark.parametrize("tag", ["film_a", "film_b", "film_c", "film_d"])
 def test_gpu_film_kernels_equal_reference(mitr, tag):
     """tr_film_scatter_add + tr_film_develop through the host mirror's add_transient_data / develop against the
     reference film (only the order of the fp32 additions differs)."""
