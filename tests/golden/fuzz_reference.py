@@ -1,7 +1,7 @@
 """Random sweeps of integrator options, BSDFs, media and occluders: the oracle's deposits against the REFERENCE'S OWN
 render() + sample(), executed over refshim (build container only: needs /root/reference).  Test infrastructure.
 
-    python tests/golden/fuzz_reference.py nlos|path|vol  N  FIRST_SEED
+    python tests/golden/fuzz_reference.py nlos|nlos_scene|path|vol  N  FIRST_SEED
 """
 import os
 import random
@@ -68,6 +68,47 @@ def fuzz_nlos(rng, i):
         if not ok: print("FAIL exhaustive film", kw)
     return ok
 
+def fuzz_nlos_scene(rng, i):
+    """Scene variety under transient_nlos_path: several hidden shapes of different kinds and areas (the hidden-geometry
+    area distribution), a scaled / shifted relay wall, two-sided and coloured BSDFs, sensor and laser at different places."""
+    kw = {"capture_type": rng.choice(["confocal", "single"]), "nlos_laser_sampling": rng.random() < 0.7,
+          "nlos_hidden_geometry_sampling": rng.random() < 0.8, "account_first_and_last_bounces": rng.random() < 0.5,
+          "max_depth": rng.choice([4, 6, -1]), "rr_depth": rng.choice([2, 5])}
+    if kw["nlos_hidden_geometry_sampling"]:
+        kw["nlos_hidden_geometry_sampling_do_rroulette"] = rng.random() < 0.5
+        kw["nlos_hidden_geometry_sampling_includes_relay_wall"] = rng.random() < 0.3
+    w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
+    spp = rng.choice([8, 16])
+    d = mitr.nlos_z_scene(w, h, 48, spp, start_opl=0.0, window=24.0, **kw)
+    if not kw["nlos_laser_sampling"]:
+        d["emitter"]["fov"] = rng.choice([60.0, 120.0])
+    colour = lambda: {"type": "rgb", "value": [round(rng.uniform(0.2, 1.0), 3) for _ in range(3)]}
+    diffuse = lambda: ({"type": "diffuse", "reflectance": colour()} if rng.random() < 0.5
+                       else {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": round(rng.uniform(0.3, 1.0), 3)}})
+    d["geometry"]["bsdf"] = diffuse()
+    if rng.random() < 0.5:
+        d["relay_wall"]["bsdf"] = {"type": "diffuse", "reflectance": colour()}
+    if rng.random() < 0.5:       # a bigger relay wall, shifted sideways
+        d["relay_wall"]["to_world"] = T().translate([rng.choice([0.0, 0.2]), 0.0, 0.0]).scale([rng.choice([1.0, 1.5]), rng.choice([1.0, 0.75]), 1.0])
+    n_extra = rng.choice([0, 1, 2])
+    for k in range(n_extra):
+        kind = rng.choice(["rectangle", "cube"])
+        pos = [rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(0.7, 1.4)]
+        sc = rng.uniform(0.1, 0.35)
+        tw = T().translate(pos).rotate([0, 1, 0], 180.0 if kind == "rectangle" else rng.uniform(0, 90)).scale([sc, sc * rng.uniform(0.5, 1.5), sc])
+        d["hidden%d" % k] = {"type": kind, "to_world": tw, "bsdf": diffuse()}
+    if rng.random() < 0.4:       # sensor somewhere else than the laser
+        d["relay_wall"]["nlos_sensor"]["sensor_origin"] = [rng.uniform(-0.8, 0.8), rng.uniform(-0.3, 0.3), rng.uniform(0.2, 0.6)]
+    scene = mitr.load_dict(d)
+    if kw["capture_type"] == "single":
+        mitr.nlos.focus_emitter_at_relay_wall_pixel((rng.randrange(w), rng.randrange(h)), mitr.PluginSpec(d["relay_wall"]), scene.emitters()[0]["spec"])
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    return cmp("nlos_scene", (kw, w, h, spp, seed, n_extra), dep, r)
+
+
 GOLD = {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]}, "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}
 BSDFS = [None, {"type": "conductor", "material": "none"}, {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0},
          {"type": "twosided", "bsdf": GOLD}, {"type": "null"}, GOLD, {"type": "dielectric", "int_ior": "water", "ext_ior": "air"},
@@ -87,6 +128,14 @@ def fuzz_path(rng, i):
     for shape in ("small-box", "large-box", "back", "floor"):
         b = rng.choice(BSDFS if shape.endswith("box") else [None, None] + BSDFS[:4] + BSDFS[5:])
         if b is not None: d[shape]["bsdf"] = b; bs[shape] = b["type"] + str(b.get("material", b.get("int_ior", "")))
+    extra = rng.random() < 0.35          # a second (and third) area light: uniform emitter selection with sample reuse
+    if extra:
+        d["small-box"]["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": [2.0, 5.0, 1.0]}}
+        if rng.random() < 0.5:
+            d["lamp2"] = {"type": "rectangle", "to_world": T().translate([0.5, -0.2, 0.3]).rotate([0, 1, 0], -90.0).scale([0.2, 0.2, 1.0]),
+                          "bsdf": {"type": "diffuse", "reflectance": 0.5},
+                          "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [9.0, 3.0, 4.0]}}}
+        bs["emitters"] = 2 + ("lamp2" in d)
     scene = mitr.load_dict(d)
     props = {k: v for k, v in d["integrator"].items() if k != "type"}
     seed = rng.randrange(1000)
@@ -118,7 +167,7 @@ def fuzz_vol(rng, i):
     if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
     return ok
 
-FUZZERS = {"nlos": fuzz_nlos, "path": fuzz_path, "vol": fuzz_vol}
+FUZZERS = {"nlos": fuzz_nlos, "nlos_scene": fuzz_nlos_scene, "path": fuzz_path, "vol": fuzz_vol}
 
 
 def run_one(which, seed):
