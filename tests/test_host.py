@@ -298,3 +298,103 @@ def test_crop_window_film_descriptor(mitr):
     d["relay_wall"]["nlos_sensor"]["transient_film"].update(crop_width=4, crop_height=4)
     with pytest.raises(NotImplementedError, match="crop window"):
         mitr.load_dict(d)
+
+
+def _fake_mitsuba(mitr):
+    """The few Mitsuba objects mitsuba_adapter touches, as plain Python (Mitsuba itself cannot be installed here)."""
+    import types
+    T = mitr.ScalarTransform4f
+
+    class Obj:
+        def __init__(self, kind, params, ident=""): self._kind, self._params, self._id = kind, params, ident
+        def __str__(self): return self._kind + "[\n]"
+        def id(self): return self._id
+
+    class Shape(Obj):
+        def __init__(self, kind, params, ident, bsdf, emitter=None, mesh=False):
+            super().__init__(kind, params, ident); self._bsdf, self._emitter, self._mesh = bsdf, emitter, mesh
+        def is_mesh(self): return self._mesh
+        def bsdf(self): return self._bsdf
+        def emitter(self): return self._emitter
+
+    class Emitter(Obj):
+        def __init__(self, kind, params, shape=None): super().__init__(kind, params); self._shape = shape
+        def get_shape(self): return self._shape
+
+    class Film:
+        temporal_bins, start_opl, bin_width_opl, exhaustive_scan = 32, 3.5, 0.25, False
+        def size(self): return (8, 6)
+        def crop_size(self): return (8, 6)
+        def crop_offset(self): return (0, 0)
+        def rfilter(self): return types.SimpleNamespace(is_box_filter=lambda: True)
+
+    class Sensor(Obj):
+        def __init__(self, params): super().__init__("PerspectiveCamera", params); self._film = Film()
+        def film(self): return self._film
+        def sampler(self): return types.SimpleNamespace(sample_count=lambda: 4)
+
+    white = Obj("SmoothDiffuse", {"reflectance.value": [0.8, 0.8, 0.8]})
+    green = Obj("TwoSided", {"brdf_0.reflectance.value": [0.1, 0.9, 0.2]})
+    light_shape = Shape("Rectangle", {"to_world": T().translate([0, 0.99, 0]).rotate([1, 0, 0], 90).scale([0.2, 0.2, 1])}, "light", white)
+    light = Emitter("AreaLight", {"radiance.value": [18.0, 14.0, 7.0]}, light_shape)
+    light_shape._emitter = light
+    tri_v = np.array([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1]], dtype=np.float32)
+    floor = Shape("OBJMesh", {"vertex_positions": tri_v.reshape(-1), "faces": np.array([0, 1, 2, 0, 2, 3], dtype=np.uint32)}, "floor",
+                  green, mesh=True)
+    back = Shape("Rectangle", {"to_world": T().translate([0, 0, -1])}, "back", white)
+    sensor = Sensor({"to_world": T().look_at(origin=[0, 0, 3.9], target=[0, 0, 0], up=[0, 1, 0]), "x_fov": 39.3, "near_clip": 0.01,
+                     "far_clip": 100.0})
+    scene = types.SimpleNamespace(shapes=lambda: [floor, back, light_shape], emitters=lambda: [light], sensors=lambda: [sensor])
+    registered = {}
+    mi = types.ModuleType("mitsuba")
+    mi.traverse = lambda o: o._params
+    mi.variant = lambda: "cuda_ad_rgb"
+    mi.SamplingIntegrator = type("SamplingIntegrator", (), {"__init__": lambda self, props: None})
+    mi.register_integrator = lambda name, factory: registered.__setitem__(name, factory)
+    mi.TensorXf = lambda t: t
+    return mi, scene, sensor, registered
+
+
+def test_mitsuba_adapter_exports_a_scene_the_loader_accepts(mitr, monkeypatch):
+    """mitsuba_adapter.scene_to_dict over a stand-in of the Mitsuba objects it reads (NOT a live Mitsuba: see the
+    module's status note): the exported dictionary loads, and describes the same primitives, BSDFs, emitter, sensor and
+    film as the same scene written as a dictionary by hand."""
+    import sys
+    from mitransient_b200 import mitsuba_adapter as ad
+    mi, scene, sensor, registered = _fake_mitsuba(mitr)
+    monkeypatch.setitem(sys.modules, "mitsuba", mi)
+    assert ad.available()
+    d = ad.scene_to_dict(scene, sensor, {"type": "transient_path", "max_depth": 5})
+    ours = mitr.load_dict(d)
+    T = mitr.ScalarTransform4f
+    hand = mitr.load_dict({
+        "type": "scene", "integrator": {"type": "transient_path", "max_depth": 5},
+        "floor": {"type": "trimesh", "vertices": np.array([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1]], dtype=np.float64),
+                  "faces": np.array([[0, 1, 2], [0, 2, 3]]),
+                  "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.1, 0.9, 0.2]}}}},
+        "back": {"type": "rectangle", "to_world": T().translate([0, 0, -1]),
+                 "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.8, 0.8, 0.8]}}},
+        "light": {"type": "rectangle", "to_world": T().translate([0, 0.99, 0]).rotate([1, 0, 0], 90).scale([0.2, 0.2, 1]),
+                  "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": [0.8, 0.8, 0.8]}},
+                  "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [18.0, 14.0, 7.0]}}},
+        "sensor": {"type": "perspective", "to_world": T().look_at(origin=[0, 0, 3.9], target=[0, 0, 0], up=[0, 1, 0]), "fov": 39.3,
+                   "near_clip": 0.01, "far_clip": 100.0, "sampler": {"type": "independent", "sample_count": 4},
+                   "film": {"type": "transient_hdr_film", "width": 8, "height": 6, "temporal_bins": 32, "start_opl": 3.5,
+                            "bin_width_opl": 0.25, "rfilter": {"type": "box"}}}})
+    a, b = ours.describe(ours.sensors()[0]), hand.describe(hand.sensors()[0])
+    assert (a.n_prims, a.n_shapes, a.n_bsdfs, a.n_emitters) == (b.n_prims, b.n_shapes, b.n_bsdfs, b.n_emitters) == (3, 3, b.n_bsdfs, 1)
+    assert np.allclose(np.ctypeslib.as_array(a.prim_verts, (a.n_prims * 12,)), np.ctypeslib.as_array(b.prim_verts, (b.n_prims * 12,)))
+    assert list(a.sensor.sample_to_camera) == list(b.sensor.sample_to_camera) and list(a.sensor.to_world) == list(b.sensor.to_world)
+    assert (a.film.width, a.film.height, a.film.temporal_bins, a.film.start_opl) == (8, 6, 32, 3.5)
+    assert list(a.emitters[0].radiance) == list(b.emitters[0].radiance)
+    assert ours.integrator().max_depth == 5
+    # unsupported content is refused, not guessed
+    scene.shapes()[1]._bsdf._kind = "RoughConductor"
+    with pytest.raises(NotImplementedError, match="RoughConductor"):
+        ad.scene_to_dict(scene, sensor, {"type": "transient_path"})
+    scene.shapes()[1]._bsdf._kind = "SmoothDiffuse"
+    assert ad.register(prefix="b200_") == ["b200_transient_path", "b200_transient_nlos_path", "b200_transient_prbvolpath"]
+    integ = registered["b200_transient_path"]({"max_depth": 7})
+    assert integ._impl.max_depth == 7
+    with pytest.raises(Exception, match="develop=True"):
+        integ.render(scene, develop=False)
