@@ -1,7 +1,7 @@
 """Random sweeps of integrator options, BSDFs, media and occluders: the oracle's deposits against the REFERENCE'S OWN
 render() + sample(), executed over refshim (build container only: needs /root/reference).  Test infrastructure.
 
-    python tests/golden/fuzz_reference.py nlos|nlos_scene|path|vol  N  FIRST_SEED
+    python tests/golden/fuzz_reference.py nlos|nlos_scene|path|vol|angular|phasor  N  FIRST_SEED
 """
 import os
 import random
@@ -167,7 +167,59 @@ def fuzz_vol(rng, i):
     if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
     return ok
 
-FUZZERS = {"nlos": fuzz_nlos, "nlos_scene": fuzz_nlos_scene, "path": fuzz_path, "vol": fuzz_vol}
+def fuzz_angular(rng, i):
+    """mitransient's `angulararea` emitter (emitters/angulararea.py) with random cutoff / beam angles inside transient_path."""
+    integ = {"max_depth": rng.choice([2, 3, 5, 8, -1]), "rr_depth": rng.choice([1, 2, 5]), "camera_unwarp": rng.random() < 0.3,
+             "discard_direct_light": rng.random() < 0.2}
+    w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
+    spp = rng.choice([8, 16])
+    cutoff = rng.choice([10.0, 25.0, 45.0, 60.0, 80.0, 89.0])
+    beam = cutoff if rng.random() < 0.25 else round(rng.uniform(0.0, cutoff), 2)
+    d = mitr.cornell_box_config(w, h, 32, spp, max_depth=8, window=(3.5, 12.5))
+    d["integrator"].update(integ)
+    d["light"]["emitter"] = {"type": "angulararea", "radiance": {"type": "rgb", "value": [18.387, 10.9873, 2.75357]},
+                             "cutoff_angle": cutoff, "beam_width": beam}
+    if rng.random() < 0.4:
+        d["large-box"]["bsdf"] = rng.choice(BSDFS[1:])
+    scene = mitr.load_dict(d)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render_angular(scene, props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    ok = cmp("angular", (integ, cutoff, beam, w, h, spp, seed), dep, r)
+    if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
+    return ok
+
+
+def fuzz_phasor(rng, i):
+    """The reference's PhasorHDRFilm (frequency selection + per-deposit cos / sin) filled by its transient_path loop."""
+    integ = {"max_depth": rng.choice([3, 5, 8]), "camera_unwarp": rng.random() < 0.3}
+    w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
+    spp = rng.choice([4, 8])
+    bins = rng.choice([64, 256, 1000])
+    wl_mean, wl_sigma = rng.choice([0.1, 0.2, 0.5, 1.0]), rng.choice([0.05, 0.1, 0.5])
+    mitr.set_variant("llvm_ad_mono")
+    try:
+        d = mitr.cornell_box_config(w, h, bins, spp)
+        d["integrator"].update(integ)
+        d["sensor"]["film"] = {"type": "phasor_hdr_film", "width": w, "height": h, "temporal_bins": bins, "start_opl": 3.5,
+                               "bin_width_opl": 6.0 / bins, "wl_mean": wl_mean, "wl_sigma": wl_sigma}
+        scene = mitr.load_dict(d)
+        props = {k: v for k, v in d["integrator"].items() if k != "type"}
+        seed = rng.randrange(1000)
+        steady, raw, dep = refshim.reference_render(scene, "mitransient.integrators.transientpath", "TransientPath", props, spp=spp,
+                                                    seed=seed, monochromatic=True)
+        r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed)
+    finally:
+        mitr.set_variant("cuda_rgb")
+    ok = raw.shape == r["transient"].shape and np.abs(raw - r["transient"]).max() <= 2e-5 * max(1.0, np.abs(raw).max())
+    print(("OK  " if ok else "FAIL"), "phasor", raw.shape, (integ, w, h, spp, bins, wl_mean, wl_sigma, seed),
+          float(np.abs(raw - r["transient"]).max()) if raw.shape == r["transient"].shape else None, flush=True)
+    return ok
+
+
+FUZZERS = {"nlos": fuzz_nlos, "nlos_scene": fuzz_nlos_scene, "path": fuzz_path, "vol": fuzz_vol, "angular": fuzz_angular,
+           "phasor": fuzz_phasor}
 
 
 def run_one(which, seed):
