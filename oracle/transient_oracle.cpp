@@ -1147,8 +1147,7 @@ V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx
         float h2x = rng.next_1d(), h2y = rng.next_1d();                                       //   are drawn unconditionally (:814)
         float b1 = rng.next_1d(); (void) b1;                                                  // arguments of bsdf.sample (:821)
         float b2x = rng.next_1d(), b2y = rng.next_1d();
-        V3 weight = v3(0, 0, 0), wo = v3(0, 0, 0); float bs_pdf = 0.0f;
-        bool twoside_back = bsdf && (bsdf->flags & TR_BSDF_FLAG_TWOSIDED) && cos_i < 0.0f;
+        V3 weight = v3(0, 0, 0), wo = v3(0, 0, 0); float bs_pdf = 0.0f, bs_eta = 1.0f;
         if (active_next && do_hg && hg_sampling) {                                            // hidden_geometry_sample :638-670
             // DiscreteDistribution.sample_reuse_pmf over shapes :420-423
             float value = h2x * ctx.hg_sum;
@@ -1170,17 +1169,17 @@ V3 trace_nlos_path(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx
             bs_pdf = ppdf * (dist * dist) / fabsf(cos_g);                                     // :662
             act = act && (bs_pdf > kEps);
             if (act) weight = v3(spec.x / bs_pdf, spec.y / bs_pdf, spec.z / bs_pdf);
-        } else if (active_next && !do_hg && smooth) {                                         // bsdf.sample :819-824
-            wo = square_to_cosine_hemisphere(b2x, b2y);
-            bs_pdf = kInvPi * wo.z;
-            float ci = twoside_back ? -cos_i : cos_i;
-            if (ci > 0.0f && bs_pdf > 0.0f) weight = v3(bsdf->reflectance[0], bsdf->reflectance[1], bsdf->reflectance[2]);
-            if (twoside_back) wo.z = -wo.z;
+        } else if (active_next && !do_hg) {                                                   // bsdf.sample :819-824
+            // in the local frame, like the plugins (diffuse: cosine hemisphere; conductor / dielectric: delta lobes; null)
+            V3 wi = v3(-dot(ray.d, si.s), -dot(ray.d, si.tt), -dot(ray.d, si.n));
+            BsdfSampleRec bs = bsdf_sample(*bsdf, wi, b1, b2x, b2y);
+            wo = bs.wo; bs_pdf = bs.pdf; weight = bs.weight; bs_eta = bs.eta;
         }
         // ---- update loop variables :831-841
         L = L + Lr;
         V3 wo_world = fma3(si.n, wo.z, fma3(si.tt, wo.y, si.s * wo.x));
         if (si.valid) ray = spawn_ray(si.p, si.n, wo_world);
+        eta = eta * bs_eta;                                                                   // :833  (hidden-geometry samples: 1)
         V3 bw = beta * weight;
         beta = v3(bw.x / pdf_method, bw.y / pdf_method, bw.z / pdf_method);                   // :834
         // ---- stopping criterion :846-858 (same as transient_path)
@@ -1279,8 +1278,9 @@ V3 vol_sample_emitter(const Scene &sc, Pcg32 &rng, bool from_medium, V3 ref_p, c
     ds.pdf *= pdf_pick;
     *ds_out = ds;
     if (ds.pdf == 0.0f) return v3(0, 0, 0);                                        // :429-431
-    bool nz = emitter_val.x != 0.0f || emitter_val.y != 0.0f || emitter_val.z != 0.0f;
-    if (!nz) return v3(0, 0, 0);                                                   // the walk below only scales emitter_val
+    // A sample that carries no radiance (the light seen from behind: ds.pdf != 0, emitter_val == 0) still walks to the
+    // light: the reference only stops on ds.pdf == 0, and the walk draws one sample per medium segment (:456-457), so
+    // skipping it would shift the path's random stream.
     if (!from_medium && is_medium_transition(sc, si)) medium = target_medium(sc, si, ds.d);   // :434-435
     Ray ray;
     if (from_medium) {                                                             // Interaction::spawn_ray_to (no offset)
@@ -1455,12 +1455,14 @@ V3 trace_volpath(const Scene &sc, const TrRenderParams &rp, Pcg32 &rng, Ray ray,
             active_surface = bs_pdf > 0.0f;                                        // :370
             if (active_surface) {
                 beta = beta * bw;                                                  // :386
+                eta = eta * bs.eta;                                                // :387
                 ray = spawn_ray(si.p, si.n, wo_world);                             // :388-389
                 needs_intersection = true;
                 if (!is_null) {                                                    // non_null_bsdf :392-399
                     depth += 1; last_scatter_p = si.p; last_scatter_direction_pdf = bs_pdf;
-                    specular_chain = false;                                        // :402-405 (diffuse is smooth, never delta)
+                    if (bs.delta) specular_chain = true;                           // :402-403 sampled_type has Delta
                 }
+                if (!is_null && !bs.delta) specular_chain = false;                 // :404-405 sampled_type has Smooth (diffuse lobes)
                 if (is_medium_transition(sc, si)) medium = target_medium(sc, si, ray.d);   // :406-407
             }
         }

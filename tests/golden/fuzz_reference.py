@@ -91,12 +91,15 @@ def fuzz_nlos_scene(rng, i):
     if rng.random() < 0.5:       # a bigger relay wall, shifted sideways
         d["relay_wall"]["to_world"] = T().translate([rng.choice([0.0, 0.2]), 0.0, 0.0]).scale([rng.choice([1.0, 1.5]), rng.choice([1.0, 0.75]), 1.0])
     n_extra = rng.choice([0, 1, 2])
+    specular = rng.random() < 0.35
     for k in range(n_extra):
         kind = rng.choice(["rectangle", "cube"])
         pos = [rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(0.7, 1.4)]
         sc = rng.uniform(0.1, 0.35)
         tw = T().translate(pos).rotate([0, 1, 0], 180.0 if kind == "rectangle" else rng.uniform(0, 90)).scale([sc, sc * rng.uniform(0.5, 1.5), sc])
         d["hidden%d" % k] = {"type": kind, "to_world": tw, "bsdf": diffuse()}
+        if specular and k == 0:      # a mirror / metal / glass object among the hidden geometry: oracle-only, see DESIGN 8.2
+            d["hidden0"]["bsdf"] = rng.choice([BSDFS[1], BSDFS[3], BSDFS[8], BSDFS[2]])
     if rng.random() < 0.4:       # sensor somewhere else than the laser
         d["relay_wall"]["nlos_sensor"]["sensor_origin"] = [rng.uniform(-0.8, 0.8), rng.uniform(-0.3, 0.3), rng.uniform(0.2, 0.6)]
     scene = mitr.load_dict(d)
@@ -158,12 +161,17 @@ def fuzz_vol(rng, i):
         for shape in ("small-box", "large-box"):
             d[shape]["interior"]["sigma_t"] = rng.choice([0.5, 2.0, 5.0, 14.0])
             d[shape]["interior"]["phase"]["g"] = rng.choice([-0.5, 0.0, 0.1, 0.7])
+    spec = {}
+    if rng.random() < 0.4:           # specular walls / a glass or metal box next to (or around) the media: oracle-only, see DESIGN 8.2
+        for shape in rng.sample(["back", "floor", "small-box", "large-box"], rng.choice([1, 2])):
+            b = rng.choice([BSDFS[1], BSDFS[2], BSDFS[3], BSDFS[5], BSDFS[6], BSDFS[8]])
+            d[shape]["bsdf"] = b; spec[shape] = b["type"]
     scene = mitr.load_dict(d)
     props = {k: v for k, v in d["integrator"].items() if k != "type"}
     seed = rng.randrange(1000)
     steady, raw, dep = refshim.reference_render_vol(scene, props, spp=spp, seed=seed)
     r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
-    ok = cmp("vol", (integ, media, w, h, spp, seed), dep, r)
+    ok = cmp("vol", (integ, media, spec, w, h, spp, seed), dep, r)
     if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
     return ok
 
