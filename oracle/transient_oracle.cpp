@@ -1037,7 +1037,15 @@ struct NlosVertex { V3 p, n; float cos_i; const TrBsdfDesc *bsdf; };
 V3 nlos_emitter_nee_sample(const Scene &sc, const TrRenderParams &rp, const NlosCtx &ctx, Pcg32 &rng, const NlosVertex &vx,
                            V3 beta, float &distance, float eta, uint32_t depth, bool active_e, bool focus_laser,
                            float px, float py, float sample_scale, Film &film, uint32_t laser_x = 0, uint32_t laser_y = 0) {
-    if (!active_e) return v3(0, 0, 0);
+    if (!active_e) {
+        // a vertex without a smooth lobe (mirror, glass) asks for no emitter sample, yet ds.dist is filled and :497-498 runs
+        // unmasked: the aliased distance still grows (paths that end here are not affected: nothing reads it afterwards)
+        if ((rp.flags & TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES) && vx.bsdf && !focus_laser) {
+            V3 dd = ctx.em_origin - vx.p;
+            distance += sqrtf(dot(dd, dd)) * eta;
+        }
+        return v3(0, 0, 0);
+    }
     film.cnt->shadow_rays++;
     V3 query = vx.p;
     if (focus_laser && (rp.capture_type == TR_CAPTURE_CONFOCAL || rp.capture_type == TR_CAPTURE_EXHAUSTIVE)) {   // :448-458
