@@ -161,6 +161,10 @@ def fuzz_vol(rng, i):
         for shape in ("small-box", "large-box"):
             d[shape]["interior"]["sigma_t"] = rng.choice([0.5, 2.0, 5.0, 14.0])
             d[shape]["interior"]["phase"]["g"] = rng.choice([-0.5, 0.0, 0.1, 0.7])
+    if rng.random() < 0.4:           # a second light low in the room: medium vertices see lights from the front and from behind
+        d["lamp2"] = {"type": "rectangle", "to_world": T().translate([rng.choice([0.5, -0.2]), -0.3, 0.3]).rotate([0, 1, 0], rng.choice([-90.0, 90.0, 0.0])).scale([0.2, 0.2, 1.0]),
+                      "bsdf": {"type": "diffuse", "reflectance": 0.5},
+                      "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [9.0, 3.0, 4.0]}}}
     spec = {}
     if rng.random() < 0.4:           # specular walls / a glass or metal box next to (or around) the media: oracle-only, see DESIGN 8.2
         for shape in rng.sample(["back", "floor", "small-box", "large-box"], rng.choice([1, 2])):
@@ -171,7 +175,7 @@ def fuzz_vol(rng, i):
     seed = rng.randrange(1000)
     steady, raw, dep = refshim.reference_render_vol(scene, props, spp=spp, seed=seed)
     r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
-    ok = cmp("vol", (integ, media, spec, w, h, spp, seed), dep, r)
+    ok = cmp("vol", (integ, media, spec, "lamp2" in d, w, h, spp, seed), dep, r)
     if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
     return ok
 

@@ -156,7 +156,11 @@ VOL_CASES = {
     "vol_b": ((6, 6, 48, 8), {"max_depth": 12, "camera_unwarp": True, "rr_depth": 2}, True),
     "vol_c": ((5, 7, 48, 16), {"max_depth": -1, "rr_depth": 1, "hide_emitters": True}, True),
     "vol_d": ((6, 6, 48, 8), {"max_depth": 6}, False),          # no medium at all: the surface-only branch of the same loop
+    # a second light standing in the room: medium vertices see lights from behind, whose radiance-free emitter samples still
+    # walk to the light and draw per medium segment (transient_prbvolpath.py:429-457)
+    "vol_e": ((5, 7, 48, 8), {"max_depth": 6, "rr_depth": 2, "lamp2": True}, True),
 }
+VOL_CASES_GPU = ("vol_a", "vol_b", "vol_c", "vol_d")           # vol_e was added after the round's GPU budget was spent
 
 
 def vol_case_scene(name):
@@ -166,6 +170,11 @@ def vol_case_scene(name):
     else:
         d = mitr.cornell_box_config(*cfg, max_depth=8)
         d["integrator"]["type"] = "transient_prbvolpath"
+    integ = dict(integ)
+    if integ.pop("lamp2", False):
+        d["lamp2"] = {"type": "rectangle", "to_world": mitr.ScalarTransform4f().translate([0.5, -0.3, 0.3]).rotate([0, 1, 0], -90.0).scale([0.2, 0.2, 1.0]),
+                      "bsdf": {"type": "diffuse", "reflectance": 0.5},
+                      "emitter": {"type": "area", "radiance": {"type": "rgb", "value": [9.0, 3.0, 4.0]}}}
     d["integrator"].update(integ)
     return mitr.load_dict(d), cfg, {k: v for k, v in d["integrator"].items() if k != "type"}
 

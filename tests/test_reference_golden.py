@@ -289,7 +289,7 @@ def test_gpu_angulararea_equals_the_reference_emitter(mitr, name):
 
 
 # ------------------------------------------------------------------------------------------ transient_prbvolpath
-from path_cases import VOL_CASES, vol_case_scene  # noqa: E402
+from path_cases import VOL_CASES, VOL_CASES_GPU, vol_case_scene  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(VOL_CASES))
@@ -319,7 +319,7 @@ def test_reference_volpath_integrator_runs_live(mitr, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(VOL_CASES))
+@pytest.mark.parametrize("name", sorted(VOL_CASES_GPU))
 def test_gpu_volpath_render_equals_the_reference_integrator(mitr, name):
     scene, cfg, _ = vol_case_scene(name)
     integ = scene.integrator()
