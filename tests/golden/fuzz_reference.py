@@ -131,6 +131,10 @@ def fuzz_path(rng, i):
     for shape in ("small-box", "large-box", "back", "floor"):
         b = rng.choice(BSDFS if shape.endswith("box") else [None, None] + BSDFS[:4] + BSDFS[5:])
         if b is not None: d[shape]["bsdf"] = b; bs[shape] = b["type"] + str(b.get("material", b.get("int_ior", "")))
+    if rng.random() < 0.25:              # a crop window of the film
+        cw, ch = rng.randrange(1, w + 1), rng.randrange(1, h + 1)
+        d["sensor"]["film"].update(crop_width=cw, crop_height=ch, crop_offset_x=rng.randrange(0, w - cw + 1), crop_offset_y=rng.randrange(0, h - ch + 1))
+        bs["crop"] = (cw, ch)
     extra = rng.random() < 0.35          # a second (and third) area light: uniform emitter selection with sample reuse
     if extra:
         d["small-box"]["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": [2.0, 5.0, 1.0]}}
@@ -146,6 +150,8 @@ def fuzz_path(rng, i):
     r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
     ok = cmp("path", (integ, bs, w, h, spp, seed), dep, r)
     if ok and not np.allclose(steady, r["steady"], rtol=3e-7, atol=0): print("FAIL steady", np.abs(steady - r["steady"]).max()); ok = False
+    if ok and not (raw.shape == r["transient"].shape and np.abs(raw - r["transient"]).max() <= 1e-6 * max(1.0, np.abs(raw).max())):
+        print("FAIL film", raw.shape, r["transient"].shape); ok = False
     return ok
 
 def fuzz_vol(rng, i):
