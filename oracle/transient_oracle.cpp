@@ -990,7 +990,8 @@ bool nlos_prepare(const Scene &sc, const TrRenderParams &rp, NlosCtx &ctx, std::
                 Hit h = ray_intersect(sc, Ray{ctx.em_origin, dw, std::numeric_limits<float>::max()});
                 ctx.laser_targets[(size_t) y * lw + x] = h.p; any = any || h.valid;
             }
-            if (!any) { err = "The emitter did not intersect any geometry in the scene."; return false; }
+            // the whole laser-target block sits under `if self.laser_sampling:` (:322): without laser sampling nothing is checked
+            if (!any && (rp.flags & TR_FLAG_NLOS_LASER_SAMPLING)) { err = "The emitter did not intersect any geometry in the scene."; return false; }
         }
     }
     if (rp.capture_type == TR_CAPTURE_SINGLE && (rp.flags & TR_FLAG_NLOS_LASER_SAMPLING) && !hl.valid) { err = "The emitter is not pointing at the scene!"; return false; }

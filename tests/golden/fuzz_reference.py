@@ -55,6 +55,10 @@ def fuzz_nlos(rng, i):
     if cap == "exhaustive":
         f = d["relay_wall"]["nlos_sensor"]["transient_film"]
         f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, w, h
+        if rng.random() < 0.4:       # its own laser grid, scanned through a widened copy of the projector (:349-379)
+            f["laser_scan_width"], f["laser_scan_height"] = rng.choice([(2, 2), (3, 2), (2, 4)])
+            d["integrator"].update(force_equal_illumination_scanning=False, illumination_scan_fov=rng.choice([10.0, 30.0, 50.0]))
+            kw["laser_grid"] = (f["laser_scan_width"], f["laser_scan_height"], d["integrator"]["illumination_scan_fov"])
     scene = mitr.load_dict(d)
     if cap == "single":
         mitr.nlos.focus_emitter_at_relay_wall_pixel((rng.randrange(w), rng.randrange(h)), mitr.PluginSpec(d["relay_wall"]), scene.emitters()[0]["spec"])
