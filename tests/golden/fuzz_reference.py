@@ -1,7 +1,7 @@
 """Random sweeps of integrator options, BSDFs, media and occluders: the oracle's deposits against the REFERENCE'S OWN
 render() + sample(), executed over refshim (build container only: needs /root/reference).  Test infrastructure.
 
-    python tests/golden/fuzz_reference.py nlos|nlos_scene|path|vol|angular|phasor  N  FIRST_SEED
+    python tests/golden/fuzz_reference.py nlos|nlos_scene|nlos_sensor|path|vol|angular|phasor  N  FIRST_SEED
 """
 import os
 import random
@@ -114,6 +114,45 @@ def fuzz_nlos_scene(rng, i):
     steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=spp, seed=seed)
     r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
     return cmp("nlos_scene", (kw, w, h, spp, seed, n_extra), dep, r)
+
+
+def fuzz_nlos_sensor(rng, i):
+    """The other two ways of looking at the relay wall: the 1x1 "confocal" nlos_capture_meter (original_film_width / height)
+    and an ordinary perspective camera driving transient_nlos_path (examples/transient-nlos/nlos-z-simple.xml)."""
+    kw = {"nlos_laser_sampling": rng.random() < 0.7, "nlos_hidden_geometry_sampling": rng.random() < 0.7,
+          "account_first_and_last_bounces": rng.random() < 0.5, "max_depth": rng.choice([4, 6, -1]), "rr_depth": rng.choice([2, 5])}
+    spp = rng.choice([16, 64])
+    if rng.random() < 0.5:
+        ow, oh = rng.choice([(4, 4), (8, 6), (5, 7)])
+        d = mitr.nlos_z_scene(1, 1, 64, spp, capture_type="single", start_opl=0.0, window=16.0, **kw)
+        d["relay_wall"]["nlos_sensor"]["original_film_width"], d["relay_wall"]["nlos_sensor"]["original_film_height"] = ow, oh
+        if not kw["nlos_laser_sampling"]: d["emitter"]["fov"] = 120.0
+        scene = mitr.load_dict(d)
+        mitr.nlos.focus_emitter_at_relay_wall_pixel((rng.randrange(ow), rng.randrange(oh)), mitr.PluginSpec(d["relay_wall"]), scene.emitters()[0]["spec"])
+        tag = ("confocal1x1", ow, oh)
+    else:
+        w, h = rng.choice([(4, 3), (6, 5)])
+        capture = rng.choice(["single", "confocal"])
+        v, f = mitr.letter_z_mesh()
+        cam = T().look_at(origin=[rng.uniform(-1.5, -0.8), rng.uniform(-0.3, 0.3), rng.uniform(1.2, 1.9)], target=[0.0, 0.0, 0.0], up=[0, 1, 0])
+        d = {"type": "scene",
+             "integrator": {"type": "transient_nlos_path", "capture_type": capture, **kw},
+             "sensor": {"type": "perspective", "fov": rng.choice([30.0, 40.0]), "near_clip": 0.1, "far_clip": 100.0, "to_world": cam,
+                        "sampler": {"type": "independent", "sample_count": spp},
+                        "film": {"type": "transient_hdr_film", "width": w, "height": h, "temporal_bins": 64, "start_opl": 0.0,
+                                 "bin_width_opl": 16.0 / 64, "rfilter": {"type": "box"}}},
+             "emitter": {"type": "projector", "irradiance": 100.0, "fov": 0.2 if kw["nlos_laser_sampling"] else 60.0, "to_world": cam},
+             "relay_wall": {"type": "rectangle", "to_world": T().scale([2.0, 2.0, 1.0]),
+                            "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.8}}},
+             "hidden": {"type": "trimesh", "vertices": v, "faces": f, "to_world": T().translate([0.0, 0.0, 1.0]),
+                        "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 1.0}}}}
+        scene = mitr.load_dict(d)
+        tag = ("perspective", capture, w, h)
+    props = {k: v for k, v in d["integrator"].items() if k != "type"}
+    seed = rng.randrange(1000)
+    steady, raw, dep = refshim.reference_render_nlos(scene, props, spp=spp, seed=seed)
+    r = oracle.render(scene, scene.integrator(), spp=spp, seed=seed, log_deposits=1 << 21)
+    return cmp("nlos_sensor", (tag, kw, spp, seed), dep, r)
 
 
 GOLD = {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]}, "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}
@@ -240,7 +279,7 @@ def fuzz_phasor(rng, i):
     return ok
 
 
-FUZZERS = {"nlos": fuzz_nlos, "nlos_scene": fuzz_nlos_scene, "path": fuzz_path, "vol": fuzz_vol, "angular": fuzz_angular,
+FUZZERS = {"nlos": fuzz_nlos, "nlos_scene": fuzz_nlos_scene, "nlos_sensor": fuzz_nlos_sensor, "path": fuzz_path, "vol": fuzz_vol, "angular": fuzz_angular,
            "phasor": fuzz_phasor}
 
 
