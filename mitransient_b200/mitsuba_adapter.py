@@ -11,7 +11,7 @@ STATUS: Mitsuba cannot be installed in the environment this repository is built 
 this module has only been exercised against the small stand-in of tests/test_host.py -- the parameter names it reads
 through ``mi.traverse`` follow the Mitsuba 3.6-3.8 plugin documentation and are NOT verified against a live install.
 It supports what the C2 / C3 benchmark scenes contain -- triangle meshes (``cube``, ``obj``, ``ply``), ``rectangle``,
-``diffuse`` / ``twosided`` BSDFs, ``area`` emitters, a ``projector``, a ``perspective`` sensor or the reference's
+``diffuse`` / ``conductor`` / ``dielectric`` / ``null`` / ``twosided`` BSDFs, ``area`` emitters, a ``projector``, a ``perspective`` sensor or the reference's
 ``nlos_capture_meter`` -- and raises ``NotImplementedError`` for everything else instead of guessing.  The parity path
 of this repository does not depend on it.
 """
@@ -65,13 +65,23 @@ def _bsdf_to_dict(mi, bsdf) -> Dict[str, Any]:
     p = mi.traverse(bsdf)
     if kind == "TwoSided":
         inner = {k[len("brdf_0."):]: p[k] for k in p.keys() if k.startswith("brdf_0.")}
-        if any(k.endswith("reflectance.value") or k == "reflectance" for k in inner):
+        if "eta.value" in inner or ("eta" in inner and "k.value" in inner):
+            return {"type": "twosided", "bsdf": {"type": "conductor", "eta": _colour(inner, "eta"), "k": _colour(inner, "k"),
+                                                 "specular_reflectance": _colour(inner, "specular_reflectance", 1.0)}}
+        if any(k in ("reflectance.value", "reflectance") for k in inner):
             return {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": _colour(inner, "reflectance")}}
-        raise NotImplementedError("twosided: only a nested diffuse BSDF is exported")
+        raise NotImplementedError("twosided: only a nested diffuse or conductor BSDF is exported")
     if kind == "SmoothDiffuse":
         return {"type": "diffuse", "reflectance": _colour(p, "reflectance")}
     if kind == "Null":
         return {"type": "null"}
+    if kind == "SmoothConductor":
+        return {"type": "conductor", "eta": _colour(p, "eta"), "k": _colour(p, "k"),
+                "specular_reflectance": _colour(p, "specular_reflectance", 1.0)}
+    if kind == "SmoothDielectric":     # the plugin exposes the relative index int_ior / ext_ior as `eta`
+        return {"type": "dielectric", "int_ior": float(_np(p["eta"])), "ext_ior": 1.0,
+                "specular_reflectance": _colour(p, "specular_reflectance", 1.0),
+                "specular_transmittance": _colour(p, "specular_transmittance", 1.0)}
     raise NotImplementedError(f"BSDF {kind!r} is not exported by the adapter")
 
 

@@ -388,6 +388,15 @@ def test_mitsuba_adapter_exports_a_scene_the_loader_accepts(mitr, monkeypatch):
     assert (a.film.width, a.film.height, a.film.temporal_bins, a.film.start_opl) == (8, 6, 32, 3.5)
     assert list(a.emitters[0].radiance) == list(b.emitters[0].radiance)
     assert ours.integrator().max_depth == 5
+    # specular BSDFs
+    scene.shapes()[1]._bsdf = type(scene.shapes()[1]._bsdf)("SmoothConductor", {"eta.value": [0.14, 0.37, 1.44], "k.value": [3.98, 2.38, 1.6],
+                                                                                 "specular_reflectance.value": [1.0, 1.0, 1.0]})
+    scene.shapes()[0]._bsdf = type(scene.shapes()[1]._bsdf)("SmoothDielectric", {"eta": 1.5})
+    d2 = ad.scene_to_dict(scene, sensor, {"type": "transient_path"})
+    assert d2["back"]["bsdf"]["type"] == "conductor" and d2["back"]["bsdf"]["k"]["value"] == [3.98, 2.38, 1.6]
+    assert d2["floor"]["bsdf"] == {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0, "specular_reflectance": 1.0, "specular_transmittance": 1.0}
+    s2 = mitr.load_dict(d2)
+    assert s2.describe(s2.sensors()[0]).n_bsdfs >= 3
     # unsupported content is refused, not guessed
     scene.shapes()[1]._bsdf._kind = "RoughConductor"
     with pytest.raises(NotImplementedError, match="RoughConductor"):
