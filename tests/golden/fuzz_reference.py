@@ -19,6 +19,7 @@ import mitransient_b200 as mitr  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 T = mitr.ScalarTransform4f
+SPP_SCALE = int(os.environ.get("FUZZ_SPP_SCALE", "1"))       # more samples per configuration: rarer events per scene
 
 
 def sortrows(a): return a[np.lexsort(a.T[::-1])]
@@ -44,7 +45,7 @@ def fuzz_nlos(rng, i):
     kw["max_depth"] = rng.choice([3, 4, 6, 8, -1]) if "filter_depth" not in kw else rng.choice([5, 6, 8])
     kw["rr_depth"] = rng.choice([1, 2, 5])
     w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
-    spp = rng.choice([4, 8, 16])
+    spp = rng.choice([4, 8, 16]) * SPP_SCALE
     if cap == "exhaustive": spp = 4
     d = mitr.nlos_z_scene(w, h, 48, spp, start_opl=0.0, window=16.0, **kw)
     if not kw["nlos_laser_sampling"]:
@@ -82,7 +83,7 @@ def fuzz_nlos_scene(rng, i):
         kw["nlos_hidden_geometry_sampling_do_rroulette"] = rng.random() < 0.5
         kw["nlos_hidden_geometry_sampling_includes_relay_wall"] = rng.random() < 0.3
     w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
-    spp = rng.choice([8, 16])
+    spp = rng.choice([8, 16]) * SPP_SCALE
     d = mitr.nlos_z_scene(w, h, 48, spp, start_opl=0.0, window=24.0, **kw)
     if not kw["nlos_laser_sampling"]:
         d["emitter"]["fov"] = rng.choice([60.0, 120.0])
@@ -121,7 +122,7 @@ def fuzz_nlos_sensor(rng, i):
     and an ordinary perspective camera driving transient_nlos_path (examples/transient-nlos/nlos-z-simple.xml)."""
     kw = {"nlos_laser_sampling": rng.random() < 0.7, "nlos_hidden_geometry_sampling": rng.random() < 0.7,
           "account_first_and_last_bounces": rng.random() < 0.5, "max_depth": rng.choice([4, 6, -1]), "rr_depth": rng.choice([2, 5])}
-    spp = rng.choice([16, 64])
+    spp = rng.choice([16, 64]) * SPP_SCALE
     if rng.random() < 0.5:
         ow, oh = rng.choice([(4, 4), (8, 6), (5, 7)])
         d = mitr.nlos_z_scene(1, 1, 64, spp, capture_type="single", start_opl=0.0, window=16.0, **kw)
@@ -167,7 +168,7 @@ def fuzz_path(rng, i):
     integ = {"max_depth": rng.choice([2, 3, 5, 8, 12, -1]), "rr_depth": rng.choice([1, 2, 3, 5]),
              "camera_unwarp": rng.random() < 0.4, "discard_direct_light": rng.random() < 0.3}
     w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
-    spp = rng.choice([4, 8])
+    spp = rng.choice([4, 8]) * SPP_SCALE
     d = mitr.cornell_box_config(w, h, 32, spp, max_depth=8)
     d["integrator"].update(integ)
     bs = {}
@@ -201,7 +202,7 @@ def fuzz_vol(rng, i):
     integ = {"max_depth": rng.choice([2, 3, 6, 12, -1]), "rr_depth": rng.choice([1, 2, 5]),
              "camera_unwarp": rng.random() < 0.4, "hide_emitters": rng.random() < 0.3}
     w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
-    spp = rng.choice([4, 8])
+    spp = rng.choice([4, 8]) * SPP_SCALE
     media = rng.random() < 0.8
     d = mitr.cornell_box_volumetric(w, h, 32, spp, max_depth=8) if media else mitr.cornell_box_config(w, h, 32, spp, max_depth=8)
     if not media: d["integrator"] = {"type": "transient_prbvolpath", "temporal_filter": "box"}
@@ -233,7 +234,7 @@ def fuzz_angular(rng, i):
     integ = {"max_depth": rng.choice([2, 3, 5, 8, -1]), "rr_depth": rng.choice([1, 2, 5]), "camera_unwarp": rng.random() < 0.3,
              "discard_direct_light": rng.random() < 0.2}
     w, h = rng.choice([(4, 4), (6, 5), (5, 7)])
-    spp = rng.choice([8, 16])
+    spp = rng.choice([8, 16]) * SPP_SCALE
     cutoff = rng.choice([10.0, 25.0, 45.0, 60.0, 80.0, 89.0])
     beam = cutoff if rng.random() < 0.25 else round(rng.uniform(0.0, cutoff), 2)
     d = mitr.cornell_box_config(w, h, 32, spp, max_depth=8, window=(3.5, 12.5))
@@ -256,7 +257,7 @@ def fuzz_phasor(rng, i):
     """The reference's PhasorHDRFilm (frequency selection + per-deposit cos / sin) filled by its transient_path loop."""
     integ = {"max_depth": rng.choice([3, 5, 8]), "camera_unwarp": rng.random() < 0.3}
     w, h = rng.choice([(3, 3), (4, 3), (5, 4)])
-    spp = rng.choice([4, 8])
+    spp = rng.choice([4, 8]) * SPP_SCALE
     bins = rng.choice([64, 256, 1000])
     wl_mean, wl_sigma = rng.choice([0.1, 0.2, 0.5, 1.0]), rng.choice([0.05, 0.1, 0.5])
     mitr.set_variant("llvm_ad_mono")
