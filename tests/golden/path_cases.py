@@ -159,8 +159,15 @@ VOL_CASES = {
     # a second light standing in the room: medium vertices see lights from behind, whose radiance-free emitter samples still
     # walk to the light and draw per medium segment (transient_prbvolpath.py:429-457)
     "vol_e": ((5, 7, 48, 8), {"max_depth": 6, "rr_depth": 2, "lamp2": True}, True),
+    # mirrors, metals and glass next to (and around) the media: delta lobes, eta-scaled path lengths, specular_chain
+    "vol_f": ((6, 6, 48, 8), {"max_depth": 8, "rr_depth": 2, "bsdfs": {"back": {"type": "conductor", "material": "none"},
+                                                                     "floor": {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0}}}, True),
+    "vol_g": ((5, 7, 48, 8), {"max_depth": -1, "rr_depth": 3, "camera_unwarp": True,
+                              "bsdfs": {"small-box": {"type": "dielectric", "int_ior": 1.33, "ext_ior": 1.0},
+                                        "red-wall": {"type": "twosided", "bsdf": {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]},
+                                                                              "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}}}}, True),
 }
-VOL_CASES_GPU = ("vol_a", "vol_b", "vol_c", "vol_d")           # vol_e was added after the round's GPU budget was spent
+VOL_CASES_GPU = tuple(sorted(VOL_CASES))                      # vol_e, vol_f, vol_g: GPU legs NOT YET RUN (branch next/specular-volpath)
 
 
 def vol_case_scene(name):
@@ -171,6 +178,8 @@ def vol_case_scene(name):
         d = mitr.cornell_box_config(*cfg, max_depth=8)
         d["integrator"]["type"] = "transient_prbvolpath"
     integ = dict(integ)
+    for shape, b in integ.pop("bsdfs", {}).items():
+        d[shape]["bsdf"] = b
     if integ.pop("lamp2", False):
         d["lamp2"] = {"type": "rectangle", "to_world": mitr.ScalarTransform4f().translate([0.5, -0.3, 0.3]).rotate([0, 1, 0], -90.0).scale([0.2, 0.2, 1.0]),
                       "bsdf": {"type": "diffuse", "reflectance": 0.5},
