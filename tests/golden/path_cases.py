@@ -73,6 +73,19 @@ NLOS_CASES = {
     # recorded (symbolic) laser loop, so every laser target starts from the caller's mask (refshim._SymbolicLoopState)
     "nlos_p": ((3, 3, 48, 4), {"capture_type": "exhaustive", "nlos_hidden_geometry_sampling": False, "start_opl": 0.0, "window": 16.0,
                                "max_depth": 6, "rr_depth": 2, "occluder": True}, None, None, True),
+    # a mirror, a metal plate and a glass block among the hidden geometry: delta lobes under transient_nlos_path (no emitter
+    # sample at those vertices, bsdf.sample continues the path, eta scales the path length; with plain emitter sampling the
+    # aliased distance still grows there).  GPU legs NOT YET RUN (branch next/specular-nlos).
+    "nlos_q": ((4, 4, 48, 64), {"start_opl": 0.0, "window": 24.0, "max_depth": 6, "plate": {"type": "conductor", "material": "none"}},
+               None, None, False),
+    "nlos_r": ((4, 4, 48, 64), {"capture_type": "single", "nlos_laser_sampling": False, "nlos_hidden_geometry_sampling": False,
+                                "account_first_and_last_bounces": True, "start_opl": 0.0, "window": 24.0, "max_depth": 6,
+                                "plate": {"type": "twosided", "bsdf": {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]},
+                                                                       "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}}},
+               (2, 1), 120.0, False),
+    "nlos_s": ((4, 4, 48, 64), {"nlos_hidden_geometry_sampling": False, "nlos_hidden_geometry_sampling_do_rroulette": False, "start_opl": 0.0,
+                                "window": 24.0, "max_depth": 8, "rr_depth": 3, "plate": {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0}},
+               None, None, False),
     "nlos_h": ((3, 3, 32, 4), {"capture_type": "exhaustive", "start_opl": 0.0, "window": 8.0}, None, None, True),
     "nlos_i": ((3, 3, 32, 4), {"capture_type": "exhaustive", "nlos_laser_sampling": False, "start_opl": 0.0, "window": 8.0}, None, 60.0, True),
     # 1x1 "confocal" sensor (original_film_width / height): every ray goes to the focused laser point
@@ -114,7 +127,13 @@ def nlos_case_scene(name):
     original = kw.pop("original_film", None)
     laser_grid = kw.pop("laser_grid", None)
     occluder = kw.pop("occluder", False)
+    plate = kw.pop("plate", None)
     d = mitr.nlos_z_scene(*cfg, **kw)
+    if plate is not None:        # a tilted plate (a block for glass) next to the letter
+        glass = plate["type"] == "dielectric"
+        d["plate"] = {"type": "cube" if glass else "rectangle",
+                      "to_world": mitr.ScalarTransform4f().translate([0.5, 0.0, 0.8]).rotate([0, 1, 0], -135.0).scale([0.4, 0.4, 0.1 if glass else 1.0]),
+                      "bsdf": plate}
     if occluder:
         d["occluder"] = {"type": "rectangle", "to_world": mitr.ScalarTransform4f().translate([-0.25, 0.1, 0.5]).scale([0.3, 0.3, 1.0]),
                          "bsdf": {"type": "twosided", "bsdf": {"type": "diffuse", "reflectance": 0.7}}}
@@ -159,8 +178,15 @@ VOL_CASES = {
     # a second light standing in the room: medium vertices see lights from behind, whose radiance-free emitter samples still
     # walk to the light and draw per medium segment (transient_prbvolpath.py:429-457)
     "vol_e": ((5, 7, 48, 8), {"max_depth": 6, "rr_depth": 2, "lamp2": True}, True),
+    # mirrors, metals and glass next to (and around) the media: delta lobes, eta-scaled path lengths, specular_chain
+    "vol_f": ((6, 6, 48, 8), {"max_depth": 8, "rr_depth": 2, "bsdfs": {"back": {"type": "conductor", "material": "none"},
+                                                                     "floor": {"type": "dielectric", "int_ior": 1.5, "ext_ior": 1.0}}}, True),
+    "vol_g": ((5, 7, 48, 8), {"max_depth": -1, "rr_depth": 3, "camera_unwarp": True,
+                              "bsdfs": {"small-box": {"type": "dielectric", "int_ior": 1.33, "ext_ior": 1.0},
+                                        "red-wall": {"type": "twosided", "bsdf": {"type": "conductor", "eta": {"type": "rgb", "value": [0.143, 0.375, 1.442]},
+                                                                              "k": {"type": "rgb", "value": [3.983, 2.386, 1.603]}}}}}, True),
 }
-VOL_CASES_GPU = ("vol_a", "vol_b", "vol_c", "vol_d")           # vol_e was added after the round's GPU budget was spent
+VOL_CASES_GPU = tuple(sorted(VOL_CASES))                      # vol_e, vol_f, vol_g: GPU legs NOT YET RUN (branch next/specular-volpath)
 
 
 def vol_case_scene(name):
@@ -171,6 +197,8 @@ def vol_case_scene(name):
         d = mitr.cornell_box_config(*cfg, max_depth=8)
         d["integrator"]["type"] = "transient_prbvolpath"
     integ = dict(integ)
+    for shape, b in integ.pop("bsdfs", {}).items():
+        d[shape]["bsdf"] = b
     if integ.pop("lamp2", False):
         d["lamp2"] = {"type": "rectangle", "to_world": mitr.ScalarTransform4f().translate([0.5, -0.3, 0.3]).rotate([0, 1, 0], -90.0).scale([0.2, 0.2, 1.0]),
                       "bsdf": {"type": "diffuse", "reflectance": 0.5},
