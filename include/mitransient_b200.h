@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 12
+#define TR_ABI_VERSION 13
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -323,6 +323,13 @@ int tr_peer_alloc(uint64_t bytes, void **dev_ptr, unsigned char *handle /* [TR_P
 int tr_peer_open(const unsigned char *handle /* [TR_PEER_HANDLE_BYTES] */, void **dev_ptr);
 int tr_peer_close(void *dev_ptr);
 int tr_peer_free(void *dev_ptr);
+
+/* ------------------------------------------------------------------ self test of the arithmetic contract
+ * The ray / primitive tests divide through rcp_c(x): the correctly rounded 1/x, which the kernels compute as
+ * MUFU.RCP + one Newton step without nvcc's range guard (DESIGN.md "Arithmetic contract").  This runs that sequence
+ * over EVERY fp32 x with 2^-126 <= |x| < 2^126 on the device and counts the values that differ from the IEEE
+ * division 1.0f / x (expected: 0).  No reference counterpart (the reference delegates intersection to Embree/OptiX). */
+int tr_selftest_rcp(uint64_t *n_checked, uint64_t *n_mismatch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -205,7 +205,15 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
             }
         }
         float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (const H3 &x : verts) {
+        const size_t n_scene_verts = verts.size();
+        // end points of shadow rays that are not scene vertices (oracle: classify_boundary_prims): projector and sensor origins
+        for (uint32_t e = 0; e < desc->n_emitters; ++e)
+            if (desc->emitters[e].type == TR_EMITTER_PROJECTOR)
+                verts.push_back(h3(desc->emitters[e].to_world[3], desc->emitters[e].to_world[7], desc->emitters[e].to_world[11]));
+        if (desc->sensor.type == TR_SENSOR_NLOS_CAPTURE_METER) verts.push_back(h3(desc->sensor.origin[0], desc->sensor.origin[1], desc->sensor.origin[2]));
+        else verts.push_back(h3(desc->sensor.to_world[3], desc->sensor.to_world[7], desc->sensor.to_world[11]));
+        for (size_t vi = 0; vi < n_scene_verts; ++vi) {
+            const H3 &x = verts[vi];
             lo3[0] = fminf(lo3[0], x.x); hi3[0] = fmaxf(hi3[0], x.x);
             lo3[1] = fminf(lo3[1], x.y); hi3[1] = fmaxf(hi3[1], x.y);
             lo3[2] = fminf(lo3[2], x.z); hi3[2] = fmaxf(hi3[2], x.z);
@@ -225,15 +233,50 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
         }
     }
 
+    // ---- contract checks: the kernels' reciprocal (MUFU.RCP + one Newton step) is the correctly rounded 1/x for
+    // 2^-126 <= |x| < 2^126; denominators are N.d / a_k.d with |d| = 1, so plane / dual vectors must stay far below that
+    for (uint32_t i = 0; i < np; ++i) {
+        const DevPrim &t = prims[i];
+        const float *w = t.N;
+        for (int k = 0; k < 12; ++k) if (!(std::fabs(w[k]) < 1.2676506e30f)) { err = "primitive too large or too small for fp32 (|N|, |a_k| must be < 2^100)"; return false; }
+    }
+    // ---- axis-aligned rectangles: their own primitive class (oracle: aa_rect_test).  Detected on the vertices: both
+    // edges run along a coordinate axis exactly.
+    std::vector<int> aa_axis(np, -1);
+    for (uint32_t i = 0; i < np; ++i) {
+        if (desc->prim_types[i] != TR_PRIM_QUAD) continue;
+        const float *v0 = desc->prim_verts + 12 * (size_t) i, *v1 = v0 + 3, *v2 = v0 + 6;
+        int ax1 = -1, ax2 = -1, n1 = 0, n2 = 0;
+        for (int c = 0; c < 3; ++c) { if (v1[c] != v0[c]) { ax1 = c; n1++; } if (v2[c] != v0[c]) { ax2 = c; n2++; } }
+        if (!(n1 == 1 && n2 == 1 && ax1 != ax2)) continue;
+        const int k = 3 - ax1 - ax2;
+        DevPrim &t = prims[i];
+        float lo[2], hi[2];
+        for (int j = 0; j < 2; ++j) {
+            const int a = (k + 1 + j) % 3;
+            lo[j] = fminf(fminf(v0[a], v1[a]), v2[a]); hi[j] = fmaxf(fmaxf(v0[a], v1[a]), v2[a]);
+        }
+        aa_axis[i] = k;
+        t.N[0] = v0[k]; t.N[1] = lo[0]; t.N[2] = hi[0]; t.d0 = lo[1];
+        t.a1[0] = hi[1]; uint32_t ku = (uint32_t) k; memcpy(&t.a1[1], &ku, 4); t.a1[2] = 0.0f; t.c1 = 0.0f;
+        t.a2[0] = t.a2[1] = t.a2[2] = 0.0f; t.c2 = 0.0f;
+        t.lim = t.lim < 0.0f ? -7.0f : 7.0f;
+    }
+
     // ---- acceleration: none for small scenes (the kernel runs a lock-step loop over all primitives, original
     // order); otherwise a median-split BVH, pre-order threaded.  Boxes are padded so that the fp32 slab test is
     // conservative w.r.t. the primitive test: culling never changes the result.
     std::vector<DevNode> nodes;
     std::vector<DevPrim> prims_out;
     uint32_t nn_nodes = 0;
-    uint32_t n_planar = 0;
+    uint32_t n_planar = 0, aa_end[3] = {0, 0, 0}, occ_aa_end[3] = {0, 0, 0};
     if (np <= kBruteForceMaxPrims) {
-        for (uint32_t i = 0; i < np; ++i) if (prims[i].lim != 5.0f) { prims_out.push_back(prims[i]); n_planar++; }
+        // test order of the contract: axis-aligned rectangles by normal axis, other planar primitives, boxes
+        for (int k = 0; k < 3; ++k) {
+            for (uint32_t i = 0; i < np; ++i) if (aa_axis[i] == k) { prims_out.push_back(prims[i]); n_planar++; }
+            aa_end[k] = n_planar;
+        }
+        for (uint32_t i = 0; i < np; ++i) if (prims[i].lim != 5.0f && aa_axis[i] < 0) { prims_out.push_back(prims[i]); n_planar++; }
         for (uint32_t i = 0; i < np; ++i) if (prims[i].lim == 5.0f) prims_out.push_back(prims[i]);
     } else {
         std::vector<BuildNode> bnodes;
@@ -383,11 +426,20 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     if (!box_extra.empty()) memcpy(&out.blob[h.off_box_extra], box_extra.data(), box_extra.size() * sizeof(DevBoxExtra));
     if (nn_nodes == 0) {   // brute-force mode: compact copy of the possible occluders, planar first then boxes
         uint32_t k = 0, kp = 0;
-        for (uint32_t i = 0; i < np; ++i)
+        for (uint32_t i = 0; i < np; ++i) {     // prims_out is in test order already: the axis-aligned groups come first
+            if (i == aa_end[0]) occ_aa_end[0] = kp;
+            if (i == aa_end[1]) occ_aa_end[1] = kp;
+            if (i == aa_end[2]) occ_aa_end[2] = kp;
             if (prims_out[i].lim > 0.0f && prims_out[i].lim != 5.0f) { memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims_out[i], sizeof(DevPrim)); kp++; }
+        }
+        if (np == aa_end[0]) occ_aa_end[0] = kp;
+        if (np == aa_end[1]) occ_aa_end[1] = kp;
+        if (np == aa_end[2]) occ_aa_end[2] = kp;
         for (uint32_t i = 0; i < np; ++i)
             if (prims_out[i].lim == 5.0f) memcpy(&out.blob[h.off_occluders + (k++) * sizeof(DevPrim)], &prims_out[i], sizeof(DevPrim));
-        reinterpret_cast<BlobHeader *>(out.blob.data())->n_occ_planar = kp;
+        BlobHeader *hh = reinterpret_cast<BlobHeader *>(out.blob.data());
+        hh->n_occ_planar = kp;
+        for (int a = 0; a < 3; ++a) { hh->aa_end[a] = aa_end[a]; hh->occ_aa_end[a] = occ_aa_end[a]; }
     }
     out.sensor = desc->sensor; out.film = desc->film; out.n_nodes = nn_nodes; out.n_prims = np;
     out.frequencies.clear();

@@ -12,7 +12,7 @@
 
 namespace tr {
 
-struct BlobHeader {            // 96 bytes
+struct BlobHeader {            // 112 bytes
     uint32_t total_bytes;      // multiple of 16
     uint32_t n_prims, n_nodes, n_shapes, n_bsdfs, n_emitters, n_media;
     uint32_t off_prims, off_nodes, off_shapes, off_bsdfs, off_emitters, off_media, off_sampling;
@@ -24,9 +24,12 @@ struct BlobHeader {            // 96 bytes
     uint32_t n_boxes;
     uint32_t n_planar;         // brute-force order: DevPrim[0, n_planar) planar, [n_planar, n_prims) boxes
     uint32_t n_occ_planar;     // same split inside the occluder list
-    uint32_t _pad[2];
+    // brute-force order inside the planar range: axis-aligned rectangles with normal axis x in [0, aa_end[0]), y in
+    // [aa_end[0], aa_end[1]), z in [aa_end[1], aa_end[2]), the other planar primitives in [aa_end[2], n_planar)
+    uint32_t aa_end[3];
+    uint32_t occ_aa_end[3];    // same split inside the occluder list
 };
-static_assert(sizeof(BlobHeader) == 96, "BlobHeader must be 96 bytes");
+static_assert(sizeof(BlobHeader) == 112, "BlobHeader must be 112 bytes");
 
 // Intersection record of one planar primitive (triangle or parallelogram), 80 bytes = 5 x float4.
 //   N = cross(e1,e2), d0 = dot(N,p0), a1 = cross(e2,N)/|N|^2, c1 = dot(p0,a1), a2 = cross(N,e1)/|N|^2, c2 = dot(p0,a2)
@@ -39,7 +42,9 @@ struct DevPrim {
     float a2[3]; float c2;     // box: a3, c3
     float lim;                 // u + v <= |lim| : 1 for triangles, 3 for parallelograms; NEGATIVE for boundary
                                // primitives (never occlude a shadow ray, see tr_scene.cu classify_boundary);
-                               // 5 marks a TR_PRIM_BOX
+                               // 5 marks a TR_PRIM_BOX; +-7 an axis-aligned rectangle, whose first six words are
+                               // (c, lo_a, hi_a, lo_b | hi_b, k): plane x_k = c (k stored as an integer), extent along
+                               // the in-plane axes a = (k + 1) % 3, b = (k + 2) % 3
     uint32_t shape;
     uint32_t prim;             // original primitive index (tie-break key)
     float area;

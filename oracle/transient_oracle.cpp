@@ -42,8 +42,11 @@
 //      cross(a,b) = ( fmaf(a.y,b.z, -(a.z*b.y)), fmaf(a.z,b.x, -(a.x*b.z)), fmaf(a.x,b.y, -(a.y*b.x)) )
 //      v / s      = v * (1.0f / s)            normalize(v) = v * (1.0f / sqrtf(dot(v,v)))
 //  Ray / primitive intersection (the reference delegates it to Embree/OptiX, whose bits cannot be
-//  reproduced): plane form with per-primitive precomputed duals, see Prim / prim_test below.
-//  sqrt and division are correctly rounded; sin/cos use the Cephes polynomial below.  With
+//  reproduced): plane form with per-primitive precomputed duals, see Prim / prim_test below; the one
+//  division of a ray / primitive test is t = num * rcp_c(den) with rcp_c(x) = the correctly rounded 1/x for
+//  |x| >= 2^-100 and +-inf below (a ray parallel to the plane / slab); axis-aligned rectangles are their own
+//  primitive class (slab arithmetic with the ray's three reciprocals rcp_c(d.x|y|z), aa_rect_test).
+//  Everywhere else sqrt and division are correctly rounded; sin/cos use the Cephes polynomial below.  With
 //  the same PCG32 streams the GPU then walks bit-identical paths; only the order of the fp32
 //  additions into a film bin differs.
 // ===========================================================================================
@@ -190,6 +193,9 @@ struct Prim {
     V3 p0, e1, e2, N, a1, a2, n, s, t; float d0, c1, c2, area; uint32_t shape; bool quad; bool boundary;
     // TR_PRIM_BOX: solid parallelepiped p0 + u e1 + v e2 + w e3; (a1,c1),(a2,c2),(a3,c3) are the duals giving (u,v,w)
     bool box; V3 e3, a3; float c3, inv_len[3], face_area[3];
+    // axis-aligned rectangle (a quad whose two edges run along coordinate axes): normal axis (-1: not one), plane
+    // coordinate, and the extent along the two in-plane axes (aa_axis + 1) % 3, (aa_axis + 2) % 3
+    int aa_axis; float aa_c, aa_lo[2], aa_hi[2];
 };
 struct Shape {
     TrShapeDesc d;
@@ -248,6 +254,12 @@ void classify_boundary_prims(Scene &sc) {
             lo[2] = fminf(lo[2], c[k].z); hi[2] = fmaxf(hi[2], c[k].z);
         }
     }
+    // end points of shadow rays that are not scene vertices: the origin of every emitter that is not attached to a
+    // shape (the projector of transient_nlos_path: emitter_nee_sample tests visibility towards it) and of the sensor
+    for (const TrEmitterDesc &e : sc.emitters)
+        if (e.type == TR_EMITTER_PROJECTOR) verts.push_back(v3(e.to_world[3], e.to_world[7], e.to_world[11]));
+    if (sc.sensor.type == TR_SENSOR_NLOS_CAPTURE_METER) verts.push_back(v3(sc.sensor.origin[0], sc.sensor.origin[1], sc.sensor.origin[2]));
+    else verts.push_back(v3(sc.sensor.to_world[3], sc.sensor.to_world[7], sc.sensor.to_world[11]));
     float extent = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     for (Prim &pr : sc.prims) {
         float tol = 1e-4f * sqrtf(dot(pr.N, pr.N)) * extent;
@@ -302,6 +314,21 @@ bool build_scene(const TrSceneDesc *desc, Scene &sc, std::string &err) {
                 t.a2 = cross(t.N, t.e1) * inv_nn; t.c2 = dot(t.p0, t.a2);
                 t.a3 = v3(0, 0, 0); t.c3 = 0.0f;
             }
+            t.aa_axis = -1; t.aa_c = 0.0f; t.aa_lo[0] = t.aa_lo[1] = t.aa_hi[0] = t.aa_hi[1] = 0.0f;
+            if (t.quad && !t.box) {
+                // both edges along a coordinate axis (exactly): an axis-aligned rectangle
+                const float *v0 = v, *v1 = v + 3, *v2 = v + 6;
+                int ax1 = -1, ax2 = -1, n1 = 0, n2 = 0;
+                for (int c = 0; c < 3; ++c) { if (v1[c] != v0[c]) { ax1 = c; n1++; } if (v2[c] != v0[c]) { ax2 = c; n2++; } }
+                if (n1 == 1 && n2 == 1 && ax1 != ax2) {
+                    const int k = 3 - ax1 - ax2;
+                    t.aa_axis = k; t.aa_c = v0[k];
+                    for (int j = 0; j < 2; ++j) {
+                        const int a = (k + 1 + j) % 3;
+                        t.aa_lo[j] = fminf(fminf(v0[a], v1[a]), v2[a]); t.aa_hi[j] = fmaxf(fmaxf(v0[a], v1[a]), v2[a]);
+                    }
+                }
+            }
             t.shape = si;
             t.area = t.box ? 2.0f * ((t.face_area[2] + t.face_area[0]) + t.face_area[1]) : (t.quad ? len : 0.5f * len);
             area_acc += (double) t.area;
@@ -343,12 +370,18 @@ struct Hit {
     bool valid; float t; V3 p, n, s, tt; uint32_t shape, prim;
 };
 
+// Reciprocal of the arithmetic contract: the correctly rounded 1/x for |x| >= 2^-100; below that (a ray parallel to
+// the plane / slab, up to rounding) +-inf with the sign of x.  (The kernel: MUFU.RCP + one Newton step, which is the
+// correctly rounded reciprocal on that range -- checked exhaustively on the GPU, tests/test_gpu_parity.py.)
+constexpr float kRcpMin = 7.888609052210118e-31f;   // 2^-100
+inline float rcp_c(float x) { return fabsf(x) >= kRcpMin ? 1.0f / x : copysignf(kInf, x); }
+
 // Ray / primitive test of the arithmetic contract: intersect the supporting plane, then read the
 // parallelogram coordinates (u, v) of the hit point off the precomputed dual vectors.
 inline bool prim_test(const Prim &pr, const Ray &r, float *t_out, V3 *p_out) {
     float denom = dot(pr.N, r.d);
     float tnum = fmaf(-pr.N.z, r.o.z, fmaf(-pr.N.y, r.o.y, fmaf(-pr.N.x, r.o.x, pr.d0)));
-    float t = tnum / denom;
+    float t = tnum * rcp_c(denom);
     V3 p = fma3(r.d, t, r.o);
     float u = fmaf(p.z, pr.a1.z, fmaf(p.y, pr.a1.y, fmaf(p.x, pr.a1.x, -pr.c1)));
     float v = fmaf(p.z, pr.a2.z, fmaf(p.y, pr.a2.y, fmaf(p.x, pr.a2.x, -pr.c2)));
@@ -356,6 +389,17 @@ inline bool prim_test(const Prim &pr, const Ray &r, float *t_out, V3 *p_out) {
     bool ok = (u >= 0.0f) && (v >= 0.0f) && inside && (t >= 0.0f) && (t <= r.maxt);
     *t_out = t; *p_out = p;
     return ok;
+}
+
+// Axis-aligned rectangle (normal along axis k, plane x_k = c): slab arithmetic with the ray's reciprocal direction
+// inv_d[k] = rcp_c(d[k]), then the hit point's two in-plane coordinates against the rectangle's extent.
+inline bool aa_rect_test(const Prim &pr, const Ray &r, const float inv_d[3], float *t_out) {
+    const float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+    const int k = pr.aa_axis, a = (k + 1) % 3, b = (k + 2) % 3;
+    float t = (pr.aa_c - o[k]) * inv_d[k];
+    float pa = fmaf(t, d[a], o[a]), pb = fmaf(t, d[b], o[b]);
+    *t_out = t;
+    return (pa >= pr.aa_lo[0]) && (pa <= pr.aa_hi[0]) && (pb >= pr.aa_lo[1]) && (pb <= pr.aa_hi[1]) && (t >= 0.0f) && (t <= r.maxt);
 }
 
 // Ray / box test of the arithmetic contract: three slabs in the parallelepiped's (u, v, w) coordinates.  A ray
@@ -366,7 +410,7 @@ inline bool box_test(const Prim &pr, const Ray &r, float *t_out, int *face) {
     for (int k = 0; k < 3; ++k) {
         float uo = fmaf(a[k].z, r.o.z, fmaf(a[k].y, r.o.y, fmaf(a[k].x, r.o.x, -c[k])));
         ud[k] = dot(a[k], r.d);
-        float inv = 1.0f / ud[k];
+        float inv = rcp_c(ud[k]);
         float t0 = (-uo) * inv, t1 = (1.0f - uo) * inv;
         tmin[k] = fminf(t0, t1); tmax[k] = fmaxf(t0, t1);
     }
@@ -386,16 +430,21 @@ inline V3 box_face_normal(const Prim &pr, int face) {
     return (face & 1) ? a * il : (-a) * il;
 }
 
+// Test order of the contract (the first primitive tested wins a tie in t): axis-aligned rectangles by normal axis
+// (x, then y, then z), then the other planar primitives, then boxes; ascending primitive index inside each class.
+inline int prim_class(const Prim &pr) { return pr.box ? 4 : (pr.aa_axis >= 0 ? pr.aa_axis : 3); }
+
 Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: closest hit, brute force
     Hit h; h.valid = false; h.t = kInf; h.prim = 0xffffffffu; h.shape = 0;
     h.p = v3(0, 0, 0); h.n = v3(0, 0, 0); h.s = h.tt = v3(0, 0, 0);
     int best_face = 0;
-    // planar primitives first, then boxes, each in ascending index; strict '<' == first tested wins ties
-    for (int pass = 0; pass < 2; ++pass)
+    const float inv_d[3] = {rcp_c(r.d.x), rcp_c(r.d.y), rcp_c(r.d.z)};
+    for (int pass = 0; pass < 5; ++pass)
         for (uint32_t i = 0; i < sc.prims.size(); ++i) {
-            if (sc.prims[i].box != (pass == 1)) continue;
+            const Prim &pr = sc.prims[i];
+            if (prim_class(pr) != pass) continue;
             float t; V3 p; int face = 0;
-            bool ok = sc.prims[i].box ? box_test(sc.prims[i], r, &t, &face) : prim_test(sc.prims[i], r, &t, &p);
+            bool ok = pr.box ? box_test(pr, r, &t, &face) : (pr.aa_axis >= 0 ? aa_rect_test(pr, r, inv_d, &t) : prim_test(pr, r, &t, &p));
             if (ok && t < h.t) { h.valid = true; h.t = t; h.prim = i; best_face = face; }
         }
     if (h.valid) {
@@ -409,10 +458,12 @@ Hit ray_intersect(const Scene &sc, const Ray &r) {  // scene.ray_intersect: clos
 }
 
 bool ray_test(const Scene &sc, const Ray &r) {  // scene.ray_test: any hit
+    const float inv_d[3] = {rcp_c(r.d.x), rcp_c(r.d.y), rcp_c(r.d.z)};
     for (uint32_t i = 0; i < sc.prims.size(); ++i) {
-        if (sc.prims[i].boundary) continue;   // see classify_boundary_prims
+        const Prim &pr = sc.prims[i];
+        if (pr.boundary) continue;   // see classify_boundary_prims
         float t; V3 p; int face;
-        if (sc.prims[i].box ? box_test(sc.prims[i], r, &t, &face) : prim_test(sc.prims[i], r, &t, &p)) return true;
+        if (pr.box ? box_test(pr, r, &t, &face) : (pr.aa_axis >= 0 ? aa_rect_test(pr, r, inv_d, &t) : prim_test(pr, r, &t, &p))) return true;
     }
     return false;
 }

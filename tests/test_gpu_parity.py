@@ -258,3 +258,15 @@ def test_multi_pass_accumulation(mitr, oracle):
     err = film_l1(raw, ref_film)
     assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL, err
     np.testing.assert_allclose(film.steady_storage.cpu().numpy(), ref_steady, rtol=1e-4, atol=1e-6)
+
+
+def test_contract_reciprocal_is_correctly_rounded(mitr):
+    """The ray / primitive tests divide through rcp_c(x) = the correctly rounded 1/x (oracle: rcp_c).  The kernels compute
+    it as MUFU.RCP + one Newton step without nvcc's range guard: checked here against the IEEE division over EVERY fp32
+    x with 2^-126 <= |x| < 2^126 (tr_selftest_rcp), so the oracle's `1.0f / x` and the kernels agree bit for bit."""
+    import ctypes as C
+    from mitransient_b200 import _lib
+    n, bad = C.c_uint64(0), C.c_uint64(0)
+    _lib.check(_lib.load().tr_selftest_rcp(C.byref(n), C.byref(bad), _lib.current_stream_ptr()))
+    assert n.value == 2 * 252 * (1 << 23), n.value
+    assert bad.value == 0, f"{bad.value} of {n.value} reciprocals differ from 1.0f / x"
