@@ -267,6 +267,10 @@ const char *tr_last_error(void);
  * mitransient/integrators/transientpath.py:134-231).                                      */
 int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene);
 void tr_scene_destroy(TrScene *scene);
+/* Upload the packed scene again (host -> device, asynchronous on `stream`, from page-locked host memory): the
+ * per-render input transfer of a caller that keeps its scene on the host between renders (Dr.Jit re-uploads the
+ * scene parameters it traced; mi.render on a CPU variant owns no device state).  Used by bench.py's e2e leg.     */
+int tr_scene_refresh(TrScene *scene, void *stream);
 /* bytes of the packed scene blob, number of BVH nodes (introspection for tests)           */
 int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_prims);
 

@@ -110,6 +110,6 @@ class TrDeposit(C.Structure):
 EXPORTED_SYMBOLS = (
     "tr_device_check", "tr_abi_version", "tr_last_error", "tr_scene_create", "tr_scene_destroy",
     "tr_scene_info", "tr_render", "tr_render_to_host", "tr_owned_pixels", "tr_film_scatter_add", "tr_film_develop",
-    "tr_peer_alloc", "tr_peer_open", "tr_peer_close", "tr_peer_free", "tr_selftest_rcp",
+    "tr_peer_alloc", "tr_peer_open", "tr_peer_close", "tr_peer_free", "tr_selftest_rcp", "tr_scene_refresh",
 )
 TR_PEER_HANDLE_BYTES = 64

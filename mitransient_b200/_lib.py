@@ -50,6 +50,8 @@ def load() -> C.CDLL:
         lib.tr_scene_create.argtypes = [C.POINTER(_abi.TrSceneDesc), C.POINTER(vp)]
         lib.tr_scene_destroy.restype = None
         lib.tr_scene_destroy.argtypes = [vp]
+        lib.tr_scene_refresh.restype = C.c_int
+        lib.tr_scene_refresh.argtypes = [vp, vp]
         lib.tr_scene_info.restype = C.c_int
         lib.tr_scene_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.tr_render.restype = C.c_int

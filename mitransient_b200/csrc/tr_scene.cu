@@ -476,6 +476,8 @@ int tr_scene_create(const TrSceneDesc *desc, TrScene **out_scene) {
     TR_CUDA_OR(cudaMemcpy(s->impl.d_blob, s->impl.blob.data(), s->impl.blob.size(), cudaMemcpyHostToDevice),
                { cudaFree(s->impl.d_blob); delete s; });
     TR_CUDA_OR(cudaMalloc(&s->impl.d_scratch, 4096), { cudaFree(s->impl.d_blob); delete s; });
+    TR_CUDA_OR(cudaHostAlloc(&s->impl.h_pinned, s->impl.blob.size(), cudaHostAllocDefault), { cudaFree(s->impl.d_scratch); cudaFree(s->impl.d_blob); delete s; });
+    memcpy(s->impl.h_pinned, s->impl.blob.data(), s->impl.blob.size());
     if (!s->impl.frequencies.empty()) {
         const size_t fb = s->impl.frequencies.size() * sizeof(float);
         TR_CUDA_OR(cudaMalloc(&s->impl.d_freqs, fb), { cudaFree(s->impl.d_scratch); cudaFree(s->impl.d_blob); delete s; });
@@ -493,7 +495,15 @@ void tr_scene_destroy(TrScene *scene) {
     if (scene->impl.d_scratch) cudaFree(scene->impl.d_scratch);
     if (scene->impl.d_nlos) cudaFree(scene->impl.d_nlos);
     if (scene->impl.d_freqs) cudaFree(scene->impl.d_freqs);
+    if (scene->impl.h_pinned) cudaFreeHost(scene->impl.h_pinned);
     delete scene;
+}
+
+int tr_scene_refresh(TrScene *scene, void *stream) {
+    if (!scene) return tr::fail(TR_ERR_INVALID_ARGUMENT, "scene is NULL");
+    TR_CUDA(cudaMemcpyAsync(scene->impl.d_blob, scene->impl.h_pinned, scene->impl.blob.size(), cudaMemcpyHostToDevice,
+                            (cudaStream_t) stream));
+    return TR_OK;
 }
 
 int tr_scene_info(const TrScene *scene, uint64_t *blob_bytes, uint32_t *n_nodes, uint32_t *n_prims) {

@@ -101,6 +101,7 @@ struct DevMedium { float sigma_t[3]; float g; float albedo[3]; float scale; };  
 struct SceneImpl {
     std::vector<unsigned char> blob;     // host copy
     void *d_blob = nullptr;              // device copy
+    void *h_pinned = nullptr;            // page-locked host copy (tr_scene_refresh uploads from it)
     TrSensorDesc sensor;
     TrFilmDesc film;
     uint32_t n_nodes = 0, n_prims = 0;

@@ -76,7 +76,12 @@ class PeerFilm:
     films and reducing them, each rank's render kernel flushes its finished pixel histograms STRAIGHT INTO the
     destination rank's film with 128-bit stores over NVLink: the transfer is fused into the kernel's flush and
     overlaps the path tracing; no reduce, no memset, no N-fold film memory.  One tiny NCCL all-reduce at the end
-    orders the remote stores before ``dst`` reads the film."""
+    orders the remote stores before ``dst`` reads the film.
+
+    Contract when the film is REUSED: there is one buffer and no double buffering, so a new render may only start once
+    ``dst`` has finished reading the previous film.  :func:`render_distributed_peer` fences on entry as well (the entry
+    fence is enqueued on ``dst``'s stream after its reads); callers that launch ``tr_render`` themselves (bench.py)
+    must do the same whenever something reads the film between two renders."""
 
     def __init__(self, shape_film, shape_steady, dst: int = 0):
         import ctypes as C
@@ -103,7 +108,8 @@ class PeerFilm:
         self._ptr = ptr.value
         self.film = _DeviceArray(self._ptr, shape_film)
         self.steady = _DeviceArray(self._ptr + self._film_bytes, shape_steady)
-        self._flag = torch.zeros(1, device="cuda")
+        self._nccl = dist.get_backend() == "nccl"
+        self._flag = torch.zeros(1, device="cuda" if self._nccl else "cpu")
 
     def tensors(self):
         """(steady, film) as torch tensors -- only meaningful on ``dst`` (the memory lives on its device)."""
@@ -117,8 +123,12 @@ class PeerFilm:
 
     def fence(self):
         """Stream-ordered after this rank's render kernel: when it completes on ``dst``, every rank's stores have
-        been issued and completed (kernel completion flushes them) before anything enqueued later reads the film."""
+        been issued and completed (kernel completion flushes them) before anything enqueued later reads the film.
+        (On a non-NCCL backend -- the two-ranks-on-one-GPU test -- the stream is drained on the host first.)"""
+        import torch
         import torch.distributed as dist
+        if not self._nccl:
+            torch.cuda.current_stream().synchronize()
         dist.all_reduce(self._flag)
 
 
@@ -145,6 +155,10 @@ def render_distributed_peer(scene, peer: PeerFilm, sensor=0, seed: int = 0, spp:
     params = integ.make_params(spp, spp, (int(seed) + sampler.base_seed) & 0xFFFFFFFF, rank=rank, world=world,
                                film_channels=int(peer.film.shape[-1]))
     integ.fill_params_(params, scene, s)
+    # The film is ONE buffer that every rank overwrites: order this render after whatever `dst` enqueued on its stream to
+    # read the previous one (develop, device->host copy) -- without this fence another rank's kernel could store into the
+    # film while `dst` is still reading it (write-after-read).
+    peer.fence()
     _lib.check(_lib.load().tr_render(dev.handle, C.byref(params), peer.film.data_ptr(), peer.steady.data_ptr(), None,
                                      torch.cuda.current_stream().cuda_stream))
     peer.fence()

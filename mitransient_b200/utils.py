@@ -71,6 +71,36 @@ def cornell_box_config(width, height, temporal_bins, spp, max_depth=8, window=(3
     return d
 
 
+def _unit_mesh(kind):
+    """Explicit triangles of Mitsuba's unit `rectangle` ([-1,1]^2 in z = 0, normal +z) or `cube` ([-1,1]^3, outward
+    normals): (vertices, faces)."""
+    from .scene import _CUBE_FACES
+    quads = [((-1, -1, 0), (2, 0, 0), (0, 2, 0))] if kind == "rectangle" else _CUBE_FACES
+    verts, faces = [], []
+    for o, u, v in quads:
+        p = [tuple(float(o[i]) for i in range(3)), tuple(float(o[i] + u[i]) for i in range(3)),
+             tuple(float(o[i] + u[i] + v[i]) for i in range(3)), tuple(float(o[i] + v[i]) for i in range(3))]
+        k = len(verts)
+        verts += p
+        faces += [(k, k + 1, k + 2), (k, k + 2, k + 3)]
+    return verts, faces
+
+
+def cornell_box_mesh_config(width, height, temporal_bins, spp, max_depth=8, window=(3.5, 9.5)):
+    """The Cornell box of :func:`cornell_box_config` with every rectangle and cube given as an explicit triangle
+    mesh (36 triangles; the light is a mesh area emitter) -- the mesh flavour of the benchmark scene, like the
+    reference's examples/transient/cornell-box/cbox_diffuse.xml builds its box from OBJ files.  It exercises the mesh
+    pipeline: coplanar triangle pairs -> parallelograms, mesh position sampling by the area CDF, no box primitives."""
+    d = cornell_box_config(width, height, temporal_bins, spp, max_depth, window)
+    for key, val in list(d.items()):
+        if isinstance(val, dict) and val.get("type") in ("rectangle", "cube"):
+            v, f = _unit_mesh(val["type"])
+            mesh = {k: x for k, x in val.items() if k != "type"}
+            mesh.update({"type": "trimesh", "vertices": v, "faces": f})
+            d[key] = mesh
+    return d
+
+
 def indent(obj, amount=2):
     lines = str(obj).splitlines(keepends=True)
     if len(lines) <= 1:

@@ -124,3 +124,88 @@ def xml_to_dict(path: str, **params) -> Dict[str, Any]:
 def load_file(path: str, **params):
     """``mi.load_file(path, **params)``: parse the XML, resolve mesh file names relative to it, build the scene."""
     return load_dict(xml_to_dict(path, **params), base_dir=os.path.dirname(os.path.abspath(path)))
+
+
+# ------------------------------------------------------------------------------------ dictionary -> XML
+_TAG_OF_TYPE = {
+    **{t: "integrator" for t in ("transient_path", "transient_nlos_path", "transient_prbvolpath", "path", "volpath")},
+    **{t: "sensor" for t in ("perspective", "nlos_capture_meter")},
+    **{t: "sampler" for t in ("independent",)},
+    **{t: "film" for t in ("transient_hdr_film", "phasor_hdr_film", "hdrfilm")},
+    **{t: "rfilter" for t in ("box", "gaussian", "tent")},
+    **{t: "bsdf" for t in ("diffuse", "conductor", "dielectric", "twosided", "null", "plastic", "roughplastic",
+                           "roughconductor", "bumpmap")},
+    **{t: "shape" for t in ("rectangle", "cube", "obj", "ply", "trimesh")},
+    **{t: "emitter" for t in ("area", "projector", "angulararea")},
+    **{t: "medium" for t in ("homogeneous",)},
+    **{t: "phase" for t in ("hg", "isotropic")},
+}
+
+
+def _emit(parent, name, val, mesh_dir, mesh_prefix, counter):
+    if isinstance(val, dict) and "type" in val:
+        t = val["type"]
+        if t == "ref":
+            ET.SubElement(parent, "ref", {"id": str(val["id"]), **({"name": name} if name and not name.startswith("_ref") else {})})
+            return
+        if t == "rgb":
+            v = list(val["value"]) if not isinstance(val["value"], (int, float)) else [val["value"]] * 3
+            ET.SubElement(parent, "rgb", {"name": name, "value": ", ".join(repr(float(x)) for x in v)})
+            return
+        tag = _TAG_OF_TYPE.get(t)
+        if tag is None:
+            raise ValueError(f"dict_to_xml: unknown plugin type {t!r}")
+        attrib = {"type": "obj" if t == "trimesh" else t}
+        if parent.tag == "scene":
+            attrib["id"] = name
+        elif name and not name.startswith("_") and tag not in ("film", "sampler", "rfilter", "phase"):
+            attrib["name"] = name
+        el = ET.SubElement(parent, tag, attrib)
+        for k, v in val.items():
+            if k in ("type", "vertices", "faces"):
+                continue
+            _emit(el, k, v, mesh_dir, mesh_prefix, counter)
+        if t == "trimesh":                       # in-memory mesh -> Wavefront OBJ next to the scene file
+            counter[0] += 1
+            fn = f"{mesh_prefix}_{counter[0]}_{name}.obj"
+            v = np.asarray(val["vertices"], dtype=np.float64).reshape(-1, 3)
+            f = np.asarray(val["faces"], dtype=np.int64).reshape(-1, 3)
+            with open(os.path.join(mesh_dir, fn), "w") as fh:
+                for p in v:
+                    fh.write("v " + " ".join(repr(float(x)) for x in p) + "\n")
+                for tri in f:
+                    fh.write("f " + " ".join(str(int(i) + 1) for i in tri) + "\n")
+            ET.SubElement(el, "string", {"name": "filename", "value": fn})
+        return
+    if isinstance(val, ScalarTransform4f):
+        tr = ET.SubElement(parent, "transform", {"name": name})
+        ET.SubElement(tr, "matrix", {"value": " ".join(repr(float(x)) for x in np.asarray(val.matrix, dtype=np.float64).reshape(-1))})
+    elif isinstance(val, bool):
+        ET.SubElement(parent, "boolean", {"name": name, "value": "true" if val else "false"})
+    elif isinstance(val, (int, np.integer)):
+        ET.SubElement(parent, "integer", {"name": name, "value": str(int(val))})
+    elif isinstance(val, (float, np.floating)):
+        ET.SubElement(parent, "float", {"name": name, "value": repr(float(val))})
+    elif isinstance(val, str):
+        ET.SubElement(parent, "string", {"name": name, "value": val})
+    elif isinstance(val, (list, tuple, np.ndarray)) and len(val) == 3:
+        ET.SubElement(parent, "vector", {"name": name, "x": repr(float(val[0])), "y": repr(float(val[1])), "z": repr(float(val[2]))})
+    else:
+        raise ValueError(f"dict_to_xml: cannot write property {name!r} = {val!r}")
+
+
+def dict_to_xml(scene: Dict[str, Any], path: str) -> str:
+    """Write a scene dictionary as a Mitsuba 3 XML file (``trimesh`` shapes become OBJ files next to it) -- the inverse of
+    :func:`xml_to_dict` for the supported subset: ``load_file(dict_to_xml(d, path))`` builds the same scene as
+    ``load_dict(d)``.  Transforms are written as ``<matrix>`` blocks, floats with full precision."""
+    root = ET.Element("scene", {"version": "3.0.0"})
+    mesh_dir = os.path.dirname(os.path.abspath(path))
+    prefix = os.path.splitext(os.path.basename(path))[0]
+    counter = [0]
+    for key, val in scene.items():
+        if key == "type":
+            continue
+        _emit(root, key, val, mesh_dir, prefix, counter)
+    ET.indent(root)
+    ET.ElementTree(root).write(path, encoding="utf-8", xml_declaration=False)
+    return path

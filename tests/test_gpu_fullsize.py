@@ -1,0 +1,78 @@
+"""GPU-vs-oracle parity at the film sizes BASELINE.json quotes (parity was only checked at toy sizes), with
+the scene read from a Mitsuba XML file through ``load_file`` (the "on-disk format either side of the path" row of
+SURVEY 8f: ``dict_to_xml`` writes the file -- the reference's own example files do not exist on the GPU box):
+
+  C2    Cornell box, transient_path, 512 x 512 x 1024 bins (13 histogram slots per CTA, 4 GiB film, 64-bit cell index)
+  C2m   the same box as 36 mesh triangles (OBJ files; cbox_diffuse.xml's flavour), 512 x 512 x 1024
+  C3    NLOS letter Z, transient_nlos_path confocal, 256 x 256 x 4096 bins (64 KiB slots, 3 per CTA)
+  C4i   volumetric Cornell box, transient_prbvolpath, 256 x 384 x 512 bins
+
+The samples per pixel are reduced so that the CPU oracle finishes in seconds; the film dimensions -- which decide the
+kernel's slot layout, interleave and index arithmetic -- are the full ones.  The full 256-spp C2 job is compared by
+bench.py (`parity`).  Bar: equal integer work counters, whole-film relative L1 <= 1e-5, per-time-bin <= 1e-4."""
+import os
+
+import numpy as np
+import pytest
+
+from parity_utils import film_l1_device
+
+pytestmark = pytest.mark.gpu
+WHOLE_TOL, PER_BIN_TOL = 1e-5, 1e-4
+
+
+def _through_xml(mitr, d, tmp_path, name):
+    from mitransient_b200.xml import dict_to_xml
+    return mitr.load_file(dict_to_xml(d, os.path.join(str(tmp_path), name + ".xml")))
+
+
+def _check(mitr, oracle, scene, spp, dims, seed=0):
+    import torch
+    w, h, t = dims
+    integ, sensor = scene.integrator(), scene.sensors()[0]
+    integ.collect_counters = True
+    steady, transient = integ.render(scene, seed=seed, spp=spp)
+    counted = dict(integ.last_counters)
+    assert tuple(transient.shape) == (h, w, t, 3)
+    del transient
+    raw = sensor.film().develop(raw=True)[1]
+    assert tuple(raw.shape) == (h, w, t, 4)
+    ref = oracle.render(scene, integ, seed=seed, spp=spp)
+    assert counted == ref["counters"], (counted, ref["counters"])
+    assert counted["paths"] == w * h * spp and counted["deposits_in_range"] > 0
+    err = film_l1_device(raw, ref["transient"])
+    assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
+    np.testing.assert_allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
+    # the plain (counter-free, 768-thread) instantiation -- the one the bench times -- renders the same film
+    integ.collect_counters = False
+    integ.render(scene, seed=seed, spp=spp)
+    raw2 = sensor.film().develop(raw=True)[1]
+    err2 = film_l1_device(raw2, ref["transient"])
+    assert err2["zero_bins_mismatch"] == 0 and err2["whole"] <= WHOLE_TOL and err2["max_t"] <= PER_BIN_TOL, err2
+    del raw, raw2, ref
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(900)
+def test_c2_cornell_full_film(mitr, oracle, tmp_path):
+    scene = _through_xml(mitr, mitr.cornell_box_config(512, 512, 1024, 4), tmp_path, "c2")
+    _check(mitr, oracle, scene, 4, (512, 512, 1024))
+
+
+@pytest.mark.timeout(900)
+def test_c2_mesh_cornell_full_film(mitr, oracle, tmp_path):
+    scene = _through_xml(mitr, mitr.cornell_box_mesh_config(512, 512, 1024, 2), tmp_path, "c2mesh")
+    assert scene.describe(scene.sensors()[0]).n_prims == 18            # 36 triangles -> 18 parallelograms
+    _check(mitr, oracle, scene, 2, (512, 512, 1024), seed=3)
+
+
+@pytest.mark.timeout(900)
+def test_c3_nlos_confocal_full_film(mitr, oracle, tmp_path):
+    scene = _through_xml(mitr, mitr.nlos_z_scene(256, 256, 4096, 16), tmp_path, "c3")
+    _check(mitr, oracle, scene, 16, (256, 256, 4096))
+
+
+@pytest.mark.timeout(900)
+def test_c4i_volumetric_cornell_full_film(mitr, oracle, tmp_path):
+    scene = _through_xml(mitr, mitr.cornell_box_volumetric(256, 384, 512, 8), tmp_path, "c4i")
+    _check(mitr, oracle, scene, 8, (256, 384, 512), seed=1)

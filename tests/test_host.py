@@ -407,3 +407,26 @@ def test_mitsuba_adapter_exports_a_scene_the_loader_accepts(mitr, monkeypatch):
     assert integ._impl.max_depth == 7
     with pytest.raises(Exception, match="develop=True"):
         integ.render(scene, develop=False)
+
+
+def test_dict_to_xml_round_trip(mitr, tmp_path):
+    """`dict_to_xml` writes what `load_file` reads: the same flat scene descriptor (vertices, sensor, film) and the same
+    integrator as `load_dict` of the dictionary -- for the four benchmark scenes, meshes going through OBJ files."""
+    import ctypes as C
+    from mitransient_b200.xml import dict_to_xml
+
+    def flat(scene):
+        d = scene.describe(scene.sensors()[0])
+        v = np.ctypeslib.as_array(C.cast(d.prim_verts, C.POINTER(C.c_float)), shape=(d.n_prims, 12)).copy()
+        return v, bytes(d.sensor), bytes(d.film), d.n_shapes, d.n_bsdfs, d.n_emitters, d.n_media
+
+    cases = {"c2": lambda: mitr.cornell_box_config(32, 32, 64, 4), "vol": lambda: mitr.cornell_box_volumetric(16, 24, 32, 4),
+             "nlos": lambda: mitr.nlos_z_scene(16, 16, 64, 4), "mesh": lambda: mitr.cornell_box_mesh_config(16, 16, 32, 4)}
+    for name, make in cases.items():          # (load_dict consumes its dictionary: build a fresh one per use)
+        s0 = mitr.load_dict(make())
+        a = flat(s0)
+        s1 = mitr.load_file(dict_to_xml(make(), str(tmp_path / (name + ".xml"))))
+        b = flat(s1)
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], name
+        assert s1.integrator().__dict__ == s0.integrator().__dict__
+    assert (tmp_path / "mesh_1_light.obj").exists() or any(p.suffix == ".obj" for p in tmp_path.iterdir())
