@@ -27,7 +27,7 @@ if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256
     a.spp = 1024 if a.spp == 256 else a.spp
     scene = mitr.load_dict(mitr.nlos_z_scene(a.width, a.height, a.bins, a.spp))
 elif a.scene == "vol":         # BASELINE config C4(i): volumetric Cornell box 256x384 x 512 bins
-    a.width, a.height, a.bins, a.spp = 256, 384, 512, 64
+    a.width, a.height, a.bins, a.spp = 256, 384, 512, 256
     scene = mitr.load_dict(mitr.cornell_box_volumetric(a.width, a.height, a.bins, a.spp))
 else:
     scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
