@@ -61,7 +61,9 @@ class TransientADIntegrator:
         passes = []
         for i in range(num_passes):
             u = independent_sampler_first_float(seed, i)
-            seed_i = int(u * 2.0 ** 32) & 0xFFFFFFFF                               # common.py:72
+            # common.py:72 draws the seed, :80 hands it to a fresh clone of the sensor's sampler, whose seed() adds the
+            # sampler's own `seed` property again (independent.cpp) -- like the single-pass seed above
+            seed_i = (int(u * 2.0 ** 32) + sampler.base_seed) & 0xFFFFFFFF
             spp_i = spp % spp_per_pass if (needs_remainder and i == num_passes - 1) else spp_per_pass
             passes.append((seed_i, spp_i))
         return passes

@@ -96,6 +96,11 @@ def _shape_to_dict(mi, shape) -> Dict[str, Any]:
     else:
         raise NotImplementedError(f"shape {_kind(shape)!r} is not exported by the adapter")
     d["bsdf"] = _bsdf_to_dict(mi, shape.bsdf())
+    for side in ("interior", "exterior"):        # media are not exported yet: refuse instead of rendering empty space
+        med = getattr(shape, side + "_medium")()
+        if med is not None:
+            raise NotImplementedError(f"shape {shape.id()!r} has an {side} medium: participating media are not exported "
+                                      "by the adapter (build the scene with mitransient_b200.load_file / load_dict)")
     em = shape.emitter()
     if em is not None:
         if _kind(em) != "AreaLight":
@@ -132,6 +137,10 @@ def scene_to_dict(mi_scene, sensor, integrator: Dict[str, Any]) -> Dict[str, Any
                                 "sensor_origin": [float(v) for v in _np(sensor.world_transform().translation()).reshape(3)]}
             if getattr(sensor, "is_confocal", False):
                 d["nlos_sensor"].update(original_film_width=int(sensor.film_size[0]), original_film_height=int(sensor.film_size[1]))
+                # runtime parameters of the 1x1 confocal meter (nloscapturemeter.py:219-228)
+                d["nlos_sensor"]["laser_target"] = [float(v) for v in _np(sensor.laser_target).reshape(3)]
+                if hasattr(sensor, "laser_bounce_opl"):
+                    d["nlos_sensor"]["laser_bounce_opl"] = float(_np(sensor.laser_bounce_opl).reshape(-1)[0])
         out[shape.id() or f"shape{i}"] = d
     if wall is None:
         sp = mi.traverse(sensor)
@@ -147,6 +156,19 @@ def scene_to_dict(mi_scene, sensor, integrator: Dict[str, Any]) -> Dict[str, Any
         out[em.id() or f"emitter{i}"] = {"type": "projector", "to_world": _matrix(ep["to_world"]), "fov": float(_np(ep["x_fov"])),
                                          "fov_axis": "x", "irradiance": _colour(ep, "irradiance")}
     return out
+
+
+def _scene_stamp(mi, mi_scene, sensor) -> bytes:
+    """Bytes of every transform an update() can edit after the scene was loaded (cache key of the exported scene)."""
+    parts = []
+    for obj in list(mi_scene.emitters()) + [sensor]:
+        p = mi.traverse(obj)
+        for k in p.keys():
+            if k.endswith("to_world"):
+                parts.append(_matrix(p[k]).tobytes())
+    if getattr(sensor, "is_confocal", False):
+        parts.append(_np(sensor.laser_target).tobytes())
+    return b"".join(parts)
 
 
 def _make_integrator_class(mi, plugin: str):
@@ -167,9 +189,12 @@ def _make_integrator_class(mi, plugin: str):
                 raise Exception("develop=True must be specified when invoking AD integrators")       # common.py:130-132
             if isinstance(sensor, int):
                 sensor = scene.sensors()[sensor]
-            if self._cache is None or self._cache[0] is not scene or self._cache[1] is not sensor:
+            # the exported scene is cached per (scene, sensor) AND the values mi.traverse(...).update() can change between
+            # renders (emitter / sensor transforms: mitransient.nlos.focus_emitter_at_relay_wall_*, laser_target)
+            stamp = _scene_stamp(mi, scene, sensor)
+            if self._cache is None or self._cache[0] is not scene or self._cache[1] is not sensor or self._cache[3] != stamp:
                 ours = mitr.load_dict(scene_to_dict(scene, sensor, {"type": plugin, **self._props}))
-                self._cache = (scene, sensor, ours)
+                self._cache = (scene, sensor, ours, stamp)
             ours = self._cache[2]
             steady, transient = self._impl.render(ours, sensor=0, seed=seed, spp=spp, develop=True, evaluate=evaluate,
                                                   progress_callback=progress_callback)

@@ -316,6 +316,8 @@ def _fake_mitsuba(mitr):
         def is_mesh(self): return self._mesh
         def bsdf(self): return self._bsdf
         def emitter(self): return self._emitter
+        def interior_medium(self): return None
+        def exterior_medium(self): return None
 
     class Emitter(Obj):
         def __init__(self, kind, params, shape=None): super().__init__(kind, params); self._shape = shape
@@ -430,3 +432,20 @@ def test_dict_to_xml_round_trip(mitr, tmp_path):
         assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], name
         assert s1.integrator().__dict__ == s0.integrator().__dict__
     assert (tmp_path / "mesh_1_light.obj").exists() or any(p.suffix == ".obj" for p in tmp_path.iterdir())
+
+
+def test_multi_pass_seeds_include_the_sampler_seed(mitr, monkeypatch):
+    """common.py:70-80: per-pass seeds are drawn from a sampler seeded with `seed` (+ the sampler's own `seed` property)
+    and handed to fresh clones of the sensor's sampler, whose seed() adds that property again."""
+    from mitransient_b200.films.transient_hdr_film import TransientHDRFilm
+    from mitransient_b200.sampler import independent_sampler_first_float
+    monkeypatch.setattr(TransientHDRFilm, "prepare", lambda self, aovs=(): 4)
+    for base in (0, 7):
+        d = mitr.cornell_box_config(512, 512, 2, 4)
+        d["sensor"]["sampler"]["seed"] = base
+        scene = mitr.load_dict(d)
+        passes = scene.integrator().prepare(scene, scene.sensors()[0], 3, 2 ** 15)
+        assert len(passes) == 129
+        for i, (seed_i, _) in enumerate(passes[:5]):
+            u = independent_sampler_first_float((3 + base) & 0xFFFFFFFF, i)
+            assert seed_i == (int(u * 2.0 ** 32) + base) & 0xFFFFFFFF
