@@ -16,7 +16,10 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "latest"
 wl = sys.argv[2] if len(sys.argv) > 2 else "C2"
 rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
 cmd = sys.argv[4] if len(sys.argv) > 4 else None
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+if rep.endswith(".csv"):          # already converted on the GPU box (ncu -i ... --page raw --csv), see scripts/gpu_profile.sh
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keep = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
