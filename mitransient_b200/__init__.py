@@ -27,7 +27,7 @@ from .scene import PluginSpec, Properties, ScalarColor3d, ScalarColor3f, Scene, 
 from .sensors.nloscapturemeter import NLOSCaptureMeter
 from .transforms import ScalarTransform4f
 from .xml import load_file, xml_to_dict
-from .utils import (cornell_box, cornell_box_config, cornell_box_mesh_config, cornell_box_volumetric, letter_z_mesh, nlos_z_scene,
+from .utils import (cornell_box, cornell_box_config, cornell_box_mesh_config, cornell_box_sphere_config, cornell_box_volumetric, icosphere, letter_z_mesh, nlos_z_scene,
                     speed_of_light)
 
 __version__ = "0.1.0"

@@ -27,10 +27,18 @@ inline H3 hxf_vector(const float *m, H3 v) {
 struct BuildTri { float lo[3], hi[3], c[3]; uint32_t idx; };
 struct BuildNode { float lo[3], hi[3]; int left = -1, right = -1; uint32_t first = 0, count = 0; };
 
-constexpr uint32_t kLeafSize = 2;
+constexpr uint32_t kLeafMax = 4;                // primitives per BVH leaf (the leaf code holds up to 15)
 constexpr uint32_t kBruteForceMaxPrims = 64;   // up to this many primitives: no BVH, lock-step loop in the kernel
+constexpr int kSahBins = 16;
+constexpr int kSahMaxDepth = 40;               // deeper than this the build switches to median splits: bounds the traversal stack
 
-int build_rec(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32_t begin, uint32_t end) {
+inline float half_area(const float *lo, const float *hi) {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Binned surface-area-heuristic build (16 bins per axis, all three axes), leaves of up to kLeafMax primitives.
+int build_rec(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32_t begin, uint32_t end, int depth, int &max_depth) {
     BuildNode nd;
     float clo[3], chi[3];
     for (int a = 0; a < 3; ++a) { nd.lo[a] = clo[a] = INFINITY; nd.hi[a] = chi[a] = -INFINITY; }
@@ -41,26 +49,67 @@ int build_rec(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32
         }
     int me = (int) nodes.size();
     nodes.push_back(nd);
-    uint32_t n = end - begin;
-    int axis = 0;
-    for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
-    if (n <= kLeafSize || !(chi[axis] - clo[axis] > 0.0f)) {
-        if (n > 15) {  // degenerate cluster (identical centroids): split by index so leaves stay <= 15
-            uint32_t mid = begin + n / 2;
-            int l = build_rec(nodes, tris, begin, mid), r = build_rec(nodes, tris, mid, end);
-            nodes[me].left = l; nodes[me].right = r;
-            return me;
+    max_depth = std::max(max_depth, depth);
+    const uint32_t n = end - begin;
+    if (n <= 2) { nodes[me].first = begin; nodes[me].count = n; return me; }
+    uint32_t mid = 0;
+    bool split = false;
+    if (depth < kSahMaxDepth) {
+        float best_cost = INFINITY; int best_axis = -1, best_bin = -1;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = chi[a] - clo[a];
+            if (!(ext > 0.0f)) continue;
+            uint32_t cnt[kSahBins] = {0};
+            float blo[kSahBins][3], bhi[kSahBins][3];
+            for (int b = 0; b < kSahBins; ++b) for (int k = 0; k < 3; ++k) { blo[b][k] = INFINITY; bhi[b][k] = -INFINITY; }
+            const float scale = (float) kSahBins / ext;
+            for (uint32_t i = begin; i < end; ++i) {
+                int b = std::min(kSahBins - 1, std::max(0, (int) ((tris[i].c[a] - clo[a]) * scale)));
+                cnt[b]++;
+                for (int k = 0; k < 3; ++k) { blo[b][k] = std::min(blo[b][k], tris[i].lo[k]); bhi[b][k] = std::max(bhi[b][k], tris[i].hi[k]); }
+            }
+            float ra[kSahBins]; uint32_t rn[kSahBins];          // right-side sweeps
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; uint32_t c = 0;
+            for (int b = kSahBins - 1; b > 0; --b) {
+                for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], blo[b][k]); hi[k] = std::max(hi[k], bhi[b][k]); }
+                c += cnt[b]; rn[b] = c; ra[b] = c ? half_area(lo, hi) : 0.0f;
+            }
+            for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+            c = 0;
+            for (int b = 0; b < kSahBins - 1; ++b) {            // split between bin b and b + 1
+                for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], blo[b][k]); hi[k] = std::max(hi[k], bhi[b][k]); }
+                c += cnt[b];
+                if (c == 0 || rn[b + 1] == 0) continue;
+                float cost = half_area(lo, hi) * (float) c + ra[b + 1] * (float) rn[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+            }
         }
-        nodes[me].first = begin; nodes[me].count = n;
-        return me;
+        // leaf when splitting does not pay (cost model: one box test ~ one primitive test) and the leaf is small enough
+        const float leaf_cost = half_area(nd.lo, nd.hi) * (float) n;
+        if (n <= kLeafMax && !(best_cost + half_area(nd.lo, nd.hi) < leaf_cost)) { nodes[me].first = begin; nodes[me].count = n; return me; }
+        if (best_axis >= 0) {
+            const float scale = (float) kSahBins / (chi[best_axis] - clo[best_axis]);
+            const float c0 = clo[best_axis];
+            auto it = std::stable_partition(tris.begin() + begin, tris.begin() + end, [=](const BuildTri &t) {
+                int b = std::min(kSahBins - 1, std::max(0, (int) ((t.c[best_axis] - c0) * scale)));
+                return b <= best_bin;
+            });
+            mid = (uint32_t) (it - tris.begin());
+            split = mid > begin && mid < end;
+        }
     }
-    uint32_t mid = begin + n / 2;
-    std::nth_element(tris.begin() + begin, tris.begin() + mid, tris.begin() + end,
-                     [axis](const BuildTri &a, const BuildTri &b) {
-                         return a.c[axis] < b.c[axis] || (a.c[axis] == b.c[axis] && a.idx < b.idx);
-                     });
-    int l = build_rec(nodes, tris, begin, mid);
-    int r = build_rec(nodes, tris, mid, end);
+    if (!split) {   // identical centroids, or too deep: median split along the widest axis (by index when degenerate)
+        int axis = 0;
+        for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+        if (n <= kLeafMax && !(chi[axis] - clo[axis] > 0.0f)) { nodes[me].first = begin; nodes[me].count = n; return me; }
+        mid = begin + n / 2;
+        std::nth_element(tris.begin() + begin, tris.begin() + mid, tris.begin() + end,
+                         [axis](const BuildTri &a, const BuildTri &b) {
+                             return a.c[axis] < b.c[axis] || (a.c[axis] == b.c[axis] && a.idx < b.idx);
+                         });
+    }
+    int l = build_rec(nodes, tris, begin, mid, depth + 1, max_depth);
+    int r = build_rec(nodes, tris, mid, end, depth + 1, max_depth);
     nodes[me].left = l; nodes[me].right = r;
     return me;
 }
@@ -281,31 +330,39 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     } else {
         std::vector<BuildNode> bnodes;
         bnodes.reserve(2 * np);
-        build_rec(bnodes, bprims, 0, np);
+        int max_depth = 0;
+        build_rec(bnodes, bprims, 0, np, 0, max_depth);
+        if (max_depth >= 60) { err = "internal: BVH deeper than the traversal stack"; return false; }
         float extent = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
         float absmax = 0.0f;
         for (int a = 0; a < 3; ++a) absmax = std::max(absmax, std::max(std::fabs(slo[a]), std::fabs(shi[a])));
         const float pad = 1e-4f * std::max(extent, absmax) + 1e-6f;
-        nn_nodes = (uint32_t) bnodes.size();
-        nodes.resize(nn_nodes);
-        std::vector<uint32_t> skip(nn_nodes, nn_nodes);   // next node in pre-order that is not a descendant
-        {
-            struct Item { int node; uint32_t skip; };
-            std::vector<Item> st; st.push_back({0, nn_nodes});
-            while (!st.empty()) {
-                Item it = st.back(); st.pop_back();
-                skip[it.node] = it.skip;
-                const BuildNode &b = bnodes[it.node];
-                if (b.left >= 0) { st.push_back({b.left, (uint32_t) b.right}); st.push_back({b.right, it.skip}); }
-            }
-        }
         prims_out.resize(np);
         for (uint32_t i = 0; i < np; ++i) prims_out[i] = prims[bprims[i].idx];
+        // device nodes: one 64-byte record per INNER node holding the padded boxes of both children, breadth-first
+        // (the top of the tree is contiguous at the start of the array).  Child code: inner node index, or
+        // 0x80000000 | first << 4 | count for a leaf.
+        std::vector<int> order; order.reserve(bnodes.size());          // inner build nodes in BFS order
+        std::vector<uint32_t> dev_index(bnodes.size(), 0xffffffffu);
+        if (bnodes[0].left < 0) { err = "internal: BVH root is a leaf"; return false; }
+        order.push_back(0); dev_index[0] = 0;
+        for (size_t h = 0; h < order.size(); ++h) {
+            const BuildNode &b = bnodes[order[h]];
+            for (int ch : {b.left, b.right})
+                if (bnodes[ch].left >= 0) { dev_index[ch] = (uint32_t) order.size(); order.push_back(ch); }
+        }
+        nn_nodes = (uint32_t) order.size();
+        nodes.resize(nn_nodes);
+        auto code = [&](int ch) -> uint32_t {
+            const BuildNode &c = bnodes[ch];
+            return c.left >= 0 ? dev_index[ch] : (0x80000000u | (c.first << 4) | c.count);
+        };
         for (uint32_t i = 0; i < nn_nodes; ++i) {
-            const BuildNode &b = bnodes[i];
-            for (int a = 0; a < 3; ++a) { nodes[i].lo[a] = b.lo[a] - pad; nodes[i].hi[a] = b.hi[a] + pad; }
-            nodes[i].skip = skip[i];
-            nodes[i].leaf = b.count ? ((b.first << 4) | b.count) : 0u;
+            const BuildNode &b = bnodes[order[i]];
+            const BuildNode &c0 = bnodes[b.left], &c1 = bnodes[b.right];
+            DevNode &d = nodes[i];
+            for (int a = 0; a < 3; ++a) { d.lo0[a] = c0.lo[a] - pad; d.hi0[a] = c0.hi[a] + pad; d.lo1[a] = c1.lo[a] - pad; d.hi1[a] = c1.hi[a] + pad; }
+            d.child0 = code(b.left); d.child1 = code(b.right); d._r0 = d._r1 = 0;
         }
     }
 

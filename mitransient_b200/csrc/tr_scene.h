@@ -69,11 +69,13 @@ struct DevBoxExtra {           // 80 bytes: what sampling a point on a box needs
 };
 static_assert(sizeof(DevBoxExtra) == 80, "DevBoxExtra must be 80 bytes");
 
-struct DevNode {               // 32 bytes = 2 x float4, pre-order threaded BVH
-    float lo[3]; uint32_t skip;   // node to visit when this one is missed / finished
-    float hi[3]; uint32_t leaf;   // 0 for inner nodes, else (first_prim << 4) | count
+struct DevNode {               // 64 bytes = 4 x float4: one INNER node of the BVH with the (padded) boxes of both children,
+    float lo0[3], hi0[3];      // breadth-first order.  Words: lo0.xyz hi0.x | hi0.yz lo1.xy | lo1.z hi1.xyz | child0 child1 - -
+    float lo1[3], hi1[3];
+    uint32_t child0, child1;   // inner node index, or 0x80000000 | first_prim << 4 | count for a leaf
+    uint32_t _r0, _r1;
 };
-static_assert(sizeof(DevNode) == 32, "DevNode must be 32 bytes");
+static_assert(sizeof(DevNode) == 64, "DevNode must be 64 bytes");
 
 struct DevShape {              // 128 bytes
     int32_t type, bsdf, emitter, flags;

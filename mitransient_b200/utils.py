@@ -101,6 +101,42 @@ def cornell_box_mesh_config(width, height, temporal_bins, spp, max_depth=8, wind
     return d
 
 
+def icosphere(subdivisions=2):
+    """Unit sphere as a subdivided icosahedron: (vertices (N,3), faces (M,3)); 20 * 4^subdivisions triangles."""
+    import numpy as np
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(int(subdivisions)):
+        mid, nf = {}, []
+
+        def midpoint(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in mid:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                mid[key] = len(v) - 1
+            return mid[key]
+        for a, b, c in f:
+            ab, bc, ca = midpoint(a, b), midpoint(b, c), midpoint(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return np.array(v), np.array(f, dtype=np.int64)
+
+
+def cornell_box_sphere_config(width, height, temporal_bins, spp, subdivisions=3, max_depth=8, window=(3.5, 9.5)):
+    """The Cornell box with the small box replaced by a triangulated sphere (20 * 4^subdivisions triangles: 320 at 2,
+    1280 at 3, 5120 at 4): the scene the BVH path is measured on (more than 64 primitives -> no lock-step loop)."""
+    d = cornell_box_config(width, height, temporal_bins, spp, max_depth, window)
+    v, f = icosphere(subdivisions)
+    d["small-box"] = {"type": "trimesh", "vertices": v, "faces": f, "merge_quads": False,
+                      "to_world": T().translate([0.335, -0.7, 0.38]).scale(0.3), "bsdf": {"type": "ref", "id": "white"}}
+    return d
+
+
 def indent(obj, amount=2):
     lines = str(obj).splitlines(keepends=True)
     if len(lines) <= 1:

@@ -18,7 +18,7 @@ ap.add_argument("--bins", type=int, default=1024)
 ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol"])
+ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol", "mesh", "sphere2", "sphere3", "sphere4"])
 ap.add_argument("--world", type=int, default=1, help="render only the tiles of rank 0 of `world` ranks (the per-GPU share of an N-GPU job)")
 a = ap.parse_args()
 if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256 x 4096 bins, 1024 spp
@@ -29,6 +29,12 @@ if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256
 elif a.scene == "vol":         # BASELINE config C4(i): volumetric Cornell box 256x384 x 512 bins
     a.width, a.height, a.bins, a.spp = 256, 384, 512, 256
     scene = mitr.load_dict(mitr.cornell_box_volumetric(a.width, a.height, a.bins, a.spp))
+elif a.scene == "mesh":        # the Cornell box as 36 mesh triangles (18 parallelograms, brute-force loop)
+    a.spp = 64 if a.spp == 256 else a.spp
+    scene = mitr.load_dict(mitr.cornell_box_mesh_config(a.width, a.height, a.bins, a.spp, a.depth))
+elif a.scene.startswith("sphere"):   # Cornell box + icosphere: the BVH path (320 / 1280 / 5120 triangles)
+    a.spp = 32 if a.spp == 256 else a.spp
+    scene = mitr.load_dict(mitr.cornell_box_sphere_config(a.width, a.height, a.bins, a.spp, int(a.scene[-1]), a.depth))
 else:
     scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
 integ, sensor = scene.integrator(), scene.sensors()[0]
