@@ -99,7 +99,7 @@ def _worker_one_gpu(rank, world, port, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(600)
+@pytest.mark.timeout(180)
 def test_two_ranks_on_one_gpu_assemble_the_film_through_ipc(tmp_path):
     """KAT-7 on the 1-GPU test box: a film assembled by two ranks (tile sharding, peer film through CUDA IPC) equals the
     single-rank film; the sample streams are indexed globally, so only the fp32 add order inside a bin may differ."""
