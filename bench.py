@@ -451,8 +451,14 @@ def run_ours(args):
             ingest = (n - 1) / n * (16.0 * W * H * T) / (s_ms * 1e-3) / 1e9
             multi["strong_" + m] = {"spp": C2["spp"], "ms_per_step": s_ms, "kernel_ms_per_rank": [round(x, 3) for x in s_pr],
                                     "value": W * H * C2["spp"] / (s_ms * 1e-3) / 1e6, "rank0_ingest_GBps": ingest,
-                                    "speedup_vs_1gpu_kernel": None,
                                     "what": "C2 at 256 spp split over N ranks; ms_per_step includes the film assembly on rank 0"}
+            if m == "reduce":
+                # the same kernels without any assembly: every rank keeps its own tiles in its own HBM (the device-resident
+                # default when the consumer is sharded too -- the layout tr_render_to_host with world > 1 copies out)
+                multi["strong_sharded"] = {"spp": C2["spp"], "ms_per_step": s_k, "kernel_ms_per_rank": [round(x, 3) for x in s_pr],
+                                           "value": W * H * C2["spp"] / (s_k * 1e-3) / 1e6,
+                                           "what": "C2 at 256 spp split over N ranks, film left sharded (no assembly): the slowest "
+                                                   "rank's kernel time of the reduce-mode steps"}
         if n == 8:                                             # BASELINE config 5 as written: 4096 spp over 8 GPUs
             p5 = integ.make_params(4096, 4096, 0, rank=rank, world=n, film_channels=4)
             for m in ([mode] + ([other] if other else [])):
