@@ -33,7 +33,6 @@ elif a.scene == "mesh":        # the Cornell box as 36 mesh triangles (18 parall
     a.spp = 64 if a.spp == 256 else a.spp
     scene = mitr.load_dict(mitr.cornell_box_mesh_config(a.width, a.height, a.bins, a.spp, a.depth))
 elif a.scene.startswith("sphere"):   # Cornell box + icosphere: the BVH path (320 / 1280 / 5120 triangles)
-    a.spp = 32 if a.spp == 256 else a.spp
     scene = mitr.load_dict(mitr.cornell_box_sphere_config(a.width, a.height, a.bins, a.spp, int(a.scene[-1]), a.depth))
 else:
     scene = mitr.load_dict(mitr.cornell_box_config(a.width, a.height, a.bins, a.spp, a.depth))
