@@ -567,9 +567,13 @@ def run_ours(args):
                     "max_depth 16", "C4i", lambda s: mitr.cornell_box_volumetric(256, 384, 512, s), 256, 384, 512, 256, 16, 16,
                     xs, peak, peak_src, clk))
                 extra.append(extra_workload(
-                    torch, mitr, lib, _lib, C, oracle, "C2-mesh cornell box as 38 triangles (cbox_diffuse.xml geometry) "
-                    "transient_path 512x512x1024, 64 spp", "C2mesh", lambda s: mitr.cornell_box_mesh_config(512, 512, 1024, s), 512, 512,
-                    1024, 64, 4, 4, xs, peak, peak_src, clk))
+                    torch, mitr, lib, _lib, C, oracle, "C2-mesh cornell box as 36 mesh triangles (the flavour of cbox_diffuse.xml: 18 "
+                    "parallelograms, lock-step loop) transient_path 512x512x1024, 256 spp", "C2mesh",
+                    lambda s: mitr.cornell_box_mesh_config(512, 512, 1024, s), 512, 512, 1024, 256, 4, 4, xs, peak, peak_src, clk))
+                extra.append(extra_workload(
+                    torch, mitr, lib, _lib, C, oracle, "C2-bvh cornell box + 1280-triangle icosphere (1287 primitives, SAH BVH path) "
+                    "transient_path 512x512x1024, 256 spp", "C2bvh",
+                    lambda s: mitr.cornell_box_sphere_config(512, 512, 1024, s, 3), 512, 512, 1024, 256, 1, 1, 3, peak, peak_src, clk))
         except Exception as exc:
             import traceback
             traceback.print_exc(file=sys.stderr)
