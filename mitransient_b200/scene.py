@@ -246,6 +246,45 @@ def merge_quads(tris: np.ndarray, rel_eps: float = 1e-6):
     return (np.array(prims, dtype=np.float64).reshape(-1, 3, 3), np.array(types, dtype=np.uint8))
 
 
+def merge_box(prims: np.ndarray, types: np.ndarray, rel_eps: float = 1e-6):
+    """Six outward-facing parallelograms that are the faces of ONE parallelepiped (an OBJ / PLY cube after
+    :func:`merge_quads`, like the boxes of the reference's examples/transient/cornell-box/meshes) -> one TR_PRIM_BOX
+    primitive (corner + three edges), which a ray tests with three slab intervals instead of six plane tests.
+    Returns ``(box [1,4,3], types [1])`` or ``None`` when the primitives are anything else."""
+    if len(prims) != 6 or not np.all(types == _abi.TR_PRIM_QUAD):
+        return None
+    q = prims[:, :3, :]
+    corners = np.concatenate([q, (q[:, 1] + q[:, 2] - q[:, 0])[:, None, :]], axis=1).reshape(-1, 3)      # 24 corners
+    eps = rel_eps * max(1e-30, float(np.abs(corners).max()))
+    keys = np.round(corners / eps).astype(np.int64)
+    uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
+    if len(uniq) != 8:
+        return None
+    pts = np.array([corners[inverse == i].mean(axis=0) for i in range(8)])
+    # the corner with the smallest key and its three neighbours (the corners it shares a face edge with)
+    adj = {i: set() for i in range(8)}
+    idx = inverse.reshape(6, 4)                       # per face: p0, p1, p2, p3 = p1 + p2 - p0  -> edges p0p1, p0p2, p1p3, p2p3
+    for f in idx:
+        for a, b in ((0, 1), (0, 2), (1, 3), (2, 3)):
+            adj[f[a]].add(f[b]); adj[f[b]].add(f[a])
+    if any(len(v) != 3 for v in adj.values()):
+        return None
+    p0 = pts[0]
+    e = [pts[j] - p0 for j in sorted(adj[0])]
+    if np.linalg.det(np.array(e)) < 0:
+        e[1], e[2] = e[2], e[1]
+    want = np.array([p0 + a * e[0] + b * e[1] + c * e[2] for a in (0, 1) for b in (0, 1) for c in (0, 1)])
+    if any(np.abs(want - p).max(axis=1).min() > 4 * eps for p in pts):
+        return None                                   # not a parallelepiped
+    centre = pts.mean(axis=0)
+    for f in q:                                       # every face must look outwards (a room built from a cube stays a mesh)
+        n = np.cross(f[1] - f[0], f[2] - f[0])
+        if np.dot(n, (f[1] + f[2]) * 0.5 - centre) <= 0:
+            return None
+    box = np.array([[p0, p0 + e[0], p0 + e[1], p0 + e[2]]], dtype=np.float64)
+    return box, np.full(1, _abi.TR_PRIM_BOX, dtype=np.uint8)
+
+
 def _apply(to_world: ScalarTransform4f, prims: np.ndarray, flip: bool) -> np.ndarray:
     m = to_world.matrix
     out = prims @ m[:3, :3].T + m[:3, 3]
@@ -643,6 +682,13 @@ def load_dict(d: Dict[str, Any], base_dir: Optional[str] = None) -> Any:
                 ptypes = np.full(len(base), _abi.TR_PRIM_TRIANGLE, dtype=np.uint8)
             if t in ("obj", "ply", "trimesh") and bool(val.get("merge_quads", True)) and len(base) > 1:
                 base, ptypes = merge_quads(base)     # coplanar triangle pairs -> parallelogram primitives
+                # a closed parallelepiped (six such quads) -> one box primitive, like `cube`; not for emitters (their
+                # position sampling follows the mesh's primitive list) and not when normals are flipped
+                is_emitter = any(_type_of(cv) in ("area", "angulararea") for cv in val.values())
+                if bool(val.get("box_primitive", True)) and not flip and not is_emitter:
+                    as_box = merge_box(base, ptypes)
+                    if as_box is not None:
+                        base, ptypes = as_box
             if base.shape[1] == 3:
                 base = _with_p3(base, ptypes)
             for ck, cv in val.items():      # every nested plugin of a shape must be one this build understands

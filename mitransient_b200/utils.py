@@ -86,17 +86,19 @@ def _unit_mesh(kind):
     return verts, faces
 
 
-def cornell_box_mesh_config(width, height, temporal_bins, spp, max_depth=8, window=(3.5, 9.5)):
+def cornell_box_mesh_config(width, height, temporal_bins, spp, max_depth=8, window=(3.5, 9.5), merge_boxes=False):
     """The Cornell box of :func:`cornell_box_config` with every rectangle and cube given as an explicit triangle
     mesh (36 triangles; the light is a mesh area emitter) -- the mesh flavour of the benchmark scene, like the
     reference's examples/transient/cornell-box/cbox_diffuse.xml builds its box from OBJ files.  It exercises the mesh
-    pipeline: coplanar triangle pairs -> parallelograms, mesh position sampling by the area CDF, no box primitives."""
+    pipeline: coplanar triangle pairs -> parallelograms, mesh position sampling by the area CDF; with ``merge_boxes``
+    the loader may also turn the two closed cubes back into box primitives (``scene.merge_box``), without it the scene
+    keeps its 18 parallelograms."""
     d = cornell_box_config(width, height, temporal_bins, spp, max_depth, window)
     for key, val in list(d.items()):
         if isinstance(val, dict) and val.get("type") in ("rectangle", "cube"):
             v, f = _unit_mesh(val["type"])
             mesh = {k: x for k, x in val.items() if k != "type"}
-            mesh.update({"type": "trimesh", "vertices": v, "faces": f})
+            mesh.update({"type": "trimesh", "vertices": v, "faces": f, "box_primitive": bool(merge_boxes)})
             d[key] = mesh
     return d
 

@@ -449,3 +449,20 @@ def test_multi_pass_seeds_include_the_sampler_seed(mitr, monkeypatch):
         for i, (seed_i, _) in enumerate(passes[:5]):
             u = independent_sampler_first_float((3 + base) & 0xFFFFFFFF, i)
             assert seed_i == (int(u * 2.0 ** 32) + base) & 0xFFFFFFFF
+
+
+def test_closed_mesh_cubes_become_box_primitives(mitr):
+    """`merge_box`: six outward parallelograms of one parallelepiped (an OBJ cube after `merge_quads`) -> one box primitive;
+    emitters, open or inward-facing meshes and `box_primitive=False` keep their parallelograms."""
+    from mitransient_b200.scene import merge_box, merge_quads
+    s18 = mitr.load_dict(mitr.cornell_box_mesh_config(8, 8, 4, 1))
+    assert s18.describe(s18.sensors()[0]).n_prims == 18
+    s8 = mitr.load_dict(mitr.cornell_box_mesh_config(8, 8, 4, 1, merge_boxes=True))
+    assert s8.describe(s8.sensors()[0]).n_prims == 8
+    v, f = mitr.utils._unit_mesh("cube")
+    tris = np.array(v)[np.array(f)]
+    q, t = merge_quads(tris)
+    box, bt = merge_box(q, t)
+    assert box.shape == (1, 4, 3) and abs(abs(np.linalg.det(box[0, 1:] - box[0, 0])) - 8.0) < 1e-9
+    assert merge_box(q[:, [0, 2, 1]], t) is None          # inward-facing faces: a room, not a solid
+    assert merge_box(q[:5], t[:5]) is None                # open
