@@ -270,3 +270,54 @@ def test_contract_reciprocal_is_correctly_rounded(mitr):
     _lib.check(_lib.load().tr_selftest_rcp(C.byref(n), C.byref(bad), _lib.current_stream_ptr()))
     assert n.value == 2 * 252 * (1 << 23), n.value
     assert bad.value == 0, f"{bad.value} of {n.value} reciprocals differ from 1.0f / x"
+
+
+@pytest.mark.parametrize("subdiv,in_smem", [(1, True), (3, False)])
+def test_bvh_icosphere_parity(mitr, oracle, subdiv, in_smem):
+    """The SAH BVH path on both sides of the 48 KB blob limit: 87 primitives (whole blob staged in shared memory) and
+    1287 primitives (blob in global memory, the breadth-first top of the tree staged by the TMA copy) must give the
+    oracle's brute-force hits -- closest hits AND shadow rays: equal counters, film relative L1 <= 1e-5."""
+    scene = mitr.load_dict(mitr.cornell_box_sphere_config(40, 32, 160, 8, subdiv))
+    integ = scene.integrator()
+    integ.collect_counters = True
+    steady, transient = integ.render(scene, seed=6, spp=8)
+    info = integ.device_scene(scene, scene.sensors()[0]).info()
+    assert info["bvh_nodes"] > 0 and (info["blob_bytes"] <= 48 * 1024) == in_smem, info
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = oracle.render(scene, integ, seed=6, spp=8)
+    assert integ.last_counters == ref["counters"], (integ.last_counters, ref["counters"])
+    err = film_l1(raw, ref["transient"])
+    assert err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL, err
+    integ.collect_counters = False                          # the plain 768-thread instantiation
+    integ.render(scene, seed=6, spp=8)
+    raw2 = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    assert film_l1(raw2, ref["transient"])["whole"] <= WHOLE_TOL
+
+
+def test_mesh_cubes_as_box_primitives_parity(mitr, oracle):
+    """`merge_box` at ingestion: the mesh Cornell box with its closed cubes turned into box primitives (8 primitives)
+    renders like the oracle on the same descriptor."""
+    scene = mitr.load_dict(mitr.cornell_box_mesh_config(40, 32, 160, 8, merge_boxes=True))
+    assert scene.describe(scene.sensors()[0]).n_prims == 8
+    integ = scene.integrator()
+    integ.collect_counters = True
+    integ.render(scene, seed=2, spp=8)
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = oracle.render(scene, integ, seed=2, spp=8)
+    assert integ.last_counters == ref["counters"]
+    assert film_l1(raw, ref["transient"])["whole"] <= WHOLE_TOL
+
+
+def test_scene_refresh_reuploads_the_same_scene(mitr):
+    """tr_scene_refresh (the e2e leg's per-step H2D input): a render after it equals the render before it."""
+    import ctypes as C
+    import torch
+    from mitransient_b200 import _lib
+    scene = mitr.load_dict(mitr.cornell_box_config(24, 16, 64, 4))
+    integ, sensor = scene.integrator(), scene.sensors()[0]
+    _, t0 = integ.render(scene, seed=1, spp=4)
+    t0 = t0.clone()
+    dev = integ.device_scene(scene, sensor)
+    _lib.check(_lib.load().tr_scene_refresh(dev.handle, _lib.current_stream_ptr()))
+    _, t1 = integ.render(scene, seed=1, spp=4)
+    assert torch.equal(t0, t1)
