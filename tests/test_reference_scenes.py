@@ -53,6 +53,39 @@ def test_example_scene_loads_and_renders_with_the_oracle(mitr, oracle, rel):
         mitr.set_variant("cuda_rgb")
 
 
+FIXTURES = {"cbox_diffuse": ("transient/cornell-box/cbox_diffuse.xml", {"res": 64, "spp": 16}),
+            "cbox_volumetric": ("transient/cornell-box/cbox_volumetric.xml", {"res": 64, "spp": 16}),
+            "nlos_Z": ("transient-nlos/nlos_Z.xml", {})}
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_scene_fixture_equals_the_reference_file(mitr, name):
+    """tests/golden/scenes/<name>.xml (written by make_scene_fixtures.py with OUR exporter, for the GPU box) builds the
+    same flat scene descriptor as the reference's own file: primitives, shapes, BSDFs, emitters, media, sensor, film,
+    integrator."""
+    import ctypes as C
+    import warnings
+    rel, params = FIXTURES[name]
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scenes", name + ".xml")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a, b = mitr.load_file(os.path.join(EXAMPLES, rel), **params), mitr.load_file(here)
+    da, db = a.describe(a.sensors()[0]), b.describe(b.sensors()[0])
+    assert da.n_prims == db.n_prims and da.n_shapes == db.n_shapes and da.n_bsdfs == db.n_bsdfs
+    assert da.n_emitters == db.n_emitters and da.n_media == db.n_media
+    va = np.ctypeslib.as_array(C.cast(da.prim_verts, C.POINTER(C.c_float)), shape=(da.n_prims, 12))
+    vb = np.ctypeslib.as_array(C.cast(db.prim_verts, C.POINTER(C.c_float)), shape=(db.n_prims, 12))
+    assert np.array_equal(va, vb)
+    assert bytes(da.sensor) == bytes(db.sensor) and bytes(da.film) == bytes(db.film)
+    for i in range(da.n_bsdfs):
+        assert bytes(da.bsdfs[i]) == bytes(db.bsdfs[i])
+    for i in range(da.n_emitters):
+        assert bytes(da.emitters[i]) == bytes(db.emitters[i])
+    for i in range(da.n_media):
+        assert bytes(da.media[i]) == bytes(db.media[i])
+    assert a.integrator().__dict__ == b.integrator().__dict__
+
+
 @pytest.mark.parametrize("rel,needle", sorted(UNSUPPORTED.items()))
 def test_unsupported_example_scene_fails_loudly(mitr, rel, needle):
     with pytest.raises((ValueError, NotImplementedError)) as e:
