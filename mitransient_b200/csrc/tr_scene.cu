@@ -3,6 +3,7 @@
 // for the integrator (scene services used at mitransient/integrators/transientpath.py:134-231).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tr_common.h"
@@ -319,7 +320,8 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     std::vector<DevPrim> prims_out;
     uint32_t nn_nodes = 0;
     uint32_t n_planar = 0, aa_end[3] = {0, 0, 0}, occ_aa_end[3] = {0, 0, 0};
-    if (np <= kBruteForceMaxPrims) {
+    static const uint32_t brute_max = getenv("TR_BRUTE_MAX") ? (uint32_t) atoi(getenv("TR_BRUTE_MAX")) : kBruteForceMaxPrims;   // experiment knob
+    if (np <= brute_max) {
         // test order of the contract: axis-aligned rectangles by normal axis, other planar primitives, boxes
         for (int k = 0; k < 3; ++k) {
             for (uint32_t i = 0; i < np; ++i) if (aa_axis[i] == k) { prims_out.push_back(prims[i]); n_planar++; }

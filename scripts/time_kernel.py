@@ -18,7 +18,7 @@ ap.add_argument("--bins", type=int, default=1024)
 ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol", "mesh", "sphere2", "sphere3", "sphere4"])
+ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol", "mesh", "sphere0", "sphere1", "sphere2", "sphere3", "sphere4"])
 ap.add_argument("--world", type=int, default=1, help="render only the tiles of rank 0 of `world` ranks (the per-GPU share of an N-GPU job)")
 a = ap.parse_args()
 if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256 x 4096 bins, 1024 spp
