@@ -169,7 +169,7 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))
-    side = pick_cpu_sample(mitr, oracle, target_s=4.0)
+    side = pick_cpu_sample(mitr, oracle, target_s=8.0)      # the full 512x512 job on a box that renders it in <= ~8 s per step
     for _ in range(args.warmup):
         oracle_rate(mitr, oracle, side, side, C2["temporal_bins"], C2["spp"], C2["max_depth"])
     t_total, paths = 0.0, 0
@@ -183,7 +183,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 cornell_box transient_path 512x512x1024 256spp depth8 (bounded CPU sample)",
+        "config": {"workload": "C2 cornell_box transient_path 512x512x1024 256spp depth8" + ("" if side == C2["width"] else " (bounded CPU sample)"),
                    "note": "mitsuba/drjit not installable here: CPU oracle port of the reference path, scalar C++"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
