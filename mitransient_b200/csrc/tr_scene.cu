@@ -29,7 +29,8 @@ struct BuildTri { float lo[3], hi[3], c[3]; uint32_t idx; };
 struct BuildNode { float lo[3], hi[3]; int left = -1, right = -1; uint32_t first = 0, count = 0; };
 
 constexpr uint32_t kLeafMax = 4;                // primitives per BVH leaf (the leaf code holds up to 15)
-constexpr uint32_t kBruteForceMaxPrims = 64;   // up to this many primitives: no BVH, lock-step loop in the kernel
+constexpr uint32_t kBruteForceMaxPrims = 40;   // up to this many primitives: no BVH, lock-step loop in the kernel.  Measured (round 2, 256 spp):
+                                               // 27 primitives 27.5 ms lock-step; 87 primitives 69.3 ms lock-step vs 39.6 ms BVH; 18: 9.8 vs 18.3 ms
 constexpr int kSahBins = 16;
 constexpr int kSahMaxDepth = 40;               // deeper than this the build switches to median splits: bounds the traversal stack
 
@@ -320,8 +321,7 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     std::vector<DevPrim> prims_out;
     uint32_t nn_nodes = 0;
     uint32_t n_planar = 0, aa_end[3] = {0, 0, 0}, occ_aa_end[3] = {0, 0, 0};
-    static const uint32_t brute_max = getenv("TR_BRUTE_MAX") ? (uint32_t) atoi(getenv("TR_BRUTE_MAX")) : kBruteForceMaxPrims;   // experiment knob
-    if (np <= brute_max) {
+    if (np <= kBruteForceMaxPrims) {
         // test order of the contract: axis-aligned rectangles by normal axis, other planar primitives, boxes
         for (int k = 0; k < 3; ++k) {
             for (uint32_t i = 0; i < np; ++i) if (aa_axis[i] == k) { prims_out.push_back(prims[i]); n_planar++; }

@@ -131,7 +131,7 @@ def icosphere(subdivisions=2):
 
 def cornell_box_sphere_config(width, height, temporal_bins, spp, subdivisions=3, max_depth=8, window=(3.5, 9.5)):
     """The Cornell box with the small box replaced by a triangulated sphere (20 * 4^subdivisions triangles: 320 at 2,
-    1280 at 3, 5120 at 4): the scene the BVH path is measured on (more than 64 primitives -> no lock-step loop)."""
+    1280 at 3, 5120 at 4): the scene the BVH path is measured on (more primitives than the lock-step limit of 40)."""
     d = cornell_box_config(width, height, temporal_bins, spp, max_depth, window)
     v, f = icosphere(subdivisions)
     d["small-box"] = {"type": "trimesh", "vertices": v, "faces": f, "merge_quads": False,

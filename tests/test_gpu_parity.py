@@ -87,7 +87,7 @@ def _uv_sphere(n_lat, n_lon, radius, center):
 
 
 def test_bvh_mesh_scene_parity(mitr, oracle, tmp_path):
-    """> 64 primitives: the threaded-BVH traversal must give the oracle's brute-force hits; the light is an
+    """More primitives than the lock-step limit (40): the BVH traversal must give the oracle's brute-force hits; the light is an
     OBJ mesh (two triangles), which exercises Mesh::sample_position (area CDF + triangle warp)."""
     sv, sf = _uv_sphere(10, 16, 0.35, (0.3, -0.65, 0.2))
     _write_obj(tmp_path / "sphere.obj", sv, sf)
