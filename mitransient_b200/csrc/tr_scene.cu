@@ -315,7 +315,7 @@ bool pack_scene(const TrSceneDesc *desc, SceneImpl &out, std::string &err) {
     }
 
     // ---- acceleration: none for small scenes (the kernel runs a lock-step loop over all primitives, original
-    // order); otherwise a median-split BVH, pre-order threaded.  Boxes are padded so that the fp32 slab test is
+    // order: the contract's test order); otherwise a binned-SAH BVH, breadth-first child-pair nodes.  Boxes are padded so that the fp32 slab test is
     // conservative w.r.t. the primitive test: culling never changes the result.
     std::vector<DevNode> nodes;
     std::vector<DevPrim> prims_out;
