@@ -127,7 +127,28 @@ def cfg_nlos(rng, kind):
     return d, spp, focus
 
 
-KINDS = {"path": cfg_path, "mesh": cfg_path, "bvh": cfg_path, "mats": cfg_path, "vol": cfg_vol, "nlos": cfg_nlos}
+def cfg_exhaustive(rng, kind):
+    """Exhaustive NLOS capture into an `exhaustive_scan` film (global vector reductions instead of the shared-memory
+    histograms), with the sensor's grid or the film's own laser grid."""
+    kw = {"capture_type": "exhaustive", "nlos_laser_sampling": rng.random() < 0.7,
+          "nlos_hidden_geometry_sampling": rng.random() < 0.6, "account_first_and_last_bounces": rng.random() < 0.5,
+          "max_depth": rng.choice([3, 4, 6]), "rr_depth": rng.choice([2, 5])}
+    w, h = rng.choice([(2, 2), (3, 4), (5, 4)])
+    t = rng.choice([32, 96, 400])
+    spp = rng.choice([2, 4, 8])
+    d = mitr.nlos_z_scene(w, h, t, spp, start_opl=0.0, window=rng.choice([8.0, 16.0]), **kw)
+    if not kw["nlos_laser_sampling"]:
+        d["emitter"]["fov"] = rng.choice([60.0, 120.0])
+    f = d["relay_wall"]["nlos_sensor"]["transient_film"]
+    f["exhaustive_scan"], f["laser_scan_width"], f["laser_scan_height"] = True, w, h
+    if kw["nlos_laser_sampling"] and rng.random() < 0.4:       # its own laser grid (transientnlospath.py:349-379)
+        f["laser_scan_width"], f["laser_scan_height"] = rng.choice([(2, 2), (3, 2), (2, 4)])
+        d["integrator"].update(force_equal_illumination_scanning=False, illumination_scan_fov=rng.choice([10.0, 30.0, 50.0]))
+    return d, spp, None
+
+
+KINDS = {"path": cfg_path, "mesh": cfg_path, "bvh": cfg_path, "mats": cfg_path, "vol": cfg_vol, "nlos": cfg_nlos,
+         "exh": cfg_exhaustive}
 
 
 def one(rng, kind):
@@ -139,22 +160,41 @@ def one(rng, kind):
     integ, sensor = scene.integrator(), scene.sensors()[0]
     if os.environ.get("FUZZ_DRY"):          # generator check on a box without a GPU: the oracle alone
         integ.check_transient_(scene, sensor); integ.check_scene_(scene, sensor)
-        ref = oracle.render(scene, integ, seed=seed, spp=spp)
-        print("DRY ", kind, ref["counters"], flush=True)
+        try:
+            ref = oracle.render(scene, integ, seed=seed, spp=spp)
+            print("DRY ", kind, ref["counters"], flush=True)
+        except RuntimeError as exc:
+            print("DRY ", kind, "oracle refuses:", exc, flush=True)
         return True
     integ.collect_counters = True
-    steady, _ = integ.render(scene, seed=seed, spp=spp)
+    try:
+        steady, _ = integ.render(scene, seed=seed, spp=spp)
+    except (mitr.TransientError, ValueError, AssertionError) as exc:
+        # a configuration the reference refuses (e.g. a laser grid that misses the scene): the oracle must refuse it too
+        try:
+            oracle.render(scene, integ, seed=seed, spp=spp)
+        except RuntimeError as oexc:
+            print("OK  ", kind, "both refuse:", str(exc)[:60], "|", str(oexc)[:60], flush=True)
+            return True
+        print("FAIL", kind, "only the GPU path refuses:", exc, flush=True)
+        return False
     counted = dict(integ.last_counters)
     raw = sensor.film().develop(raw=True)[1].cpu().numpy()
     ref = oracle.render(scene, integ, seed=seed, spp=spp)
     ok = counted == ref["counters"]
-    err = film_l1(raw, ref["transient"])
+
+    def l1(a, b):           # exhaustive_scan films are (H, W, Lh, Lw, T, C): fold the laser grid into the pixel axis
+        if a.ndim == 6:
+            a, b = a.reshape(a.shape[0], -1, a.shape[4], a.shape[5]), b.reshape(b.shape[0], -1, b.shape[4], b.shape[5])
+        return film_l1(a, b)
+    err = l1(raw, ref["transient"])
     ok = ok and err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL
-    ok = ok and np.allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
+    if kind != "exh":       # (an exhaustive film's develop() returns the channel mean as "steady", transient_hdr_film.py:213-214)
+        ok = ok and np.allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
     integ.collect_counters = False
     integ.render(scene, seed=seed, spp=spp)
     raw2 = sensor.film().develop(raw=True)[1].cpu().numpy()
-    err2 = film_l1(raw2, ref["transient"])
+    err2 = l1(raw2, ref["transient"])
     ok = ok and err2["zero_bins_mismatch"] == 0 and err2["whole"] <= WHOLE_TOL
     info = integ.device_scene(scene, sensor).info()
     film = sensor.film()
