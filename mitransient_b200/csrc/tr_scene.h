@@ -121,6 +121,7 @@ struct SceneImpl {
     std::vector<float> frequencies; void *d_freqs = nullptr;   // phasor film: host / device copy of TrFilmDesc.frequencies
     void *d_nlos = nullptr;              // float4 targets[H*W + 1] | float hg_table[2 * n_shapes]
     uint32_t nlos_key = 0xffffffffu; float hg_sum = 0.f, hg_norm = 0.f;
+    int nlos_grid_valid = 1;             // does the film's own laser grid (Exhaustive capture) hit the scene anywhere? (:370-377)
     int nlos_laser_valid = -1;           // does the laser axis hit the scene? (-1: not computed yet; transientnlospath.py:335)
     std::mutex mu;                       // tr_render mutates the caches above: one render call per scene at a time
     size_t nlos_capacity = 0; uint32_t nlos_grid = 0; float nlos_s2c[16] = {0};   // laser grid of an Exhaustive capture with its own fov

@@ -129,3 +129,21 @@ def test_mono_transient_film_is_luminance(mitr, oracle, mono):
     assert (raw[..., 0] == raw[..., 1]).all() and (raw[..., 1] == raw[..., 2]).all()
     ref = oracle.render(scene, it, spp=8)
     assert rel_l1(raw, ref["transient"]) <= TOL
+
+
+def test_exhaustive_own_laser_grid_that_misses_the_scene_is_refused(mitr, oracle):
+    """transientnlospath.py:370-377: with laser sampling, an Exhaustive capture's own laser grid must hit the scene
+    somewhere ("The emitter did not intersect any geometry in the scene").  The oracle and tr_render refuse alike -- on
+    the first render AND on a second one that finds the cached laser targets (the check is cached with them)."""
+    d = exhaustive_scene(mitr, 3, 32, 2)
+    f = d["relay_wall"]["nlos_sensor"]["transient_film"]
+    f["laser_scan_width"], f["laser_scan_height"] = 2, 2
+    d["integrator"].update(force_equal_illumination_scanning=False, illumination_scan_fov=10.0)
+    d["emitter"]["to_world"] = mitr.ScalarTransform4f().look_at(origin=[-0.5, 0.0, 0.25], target=[-10.0, 0.0, 0.25], up=[0, 1, 0])
+    scene = mitr.load_dict(d)
+    it = scene.integrator()
+    with pytest.raises(RuntimeError, match="did not intersect any geometry"):
+        oracle.render(scene, it, spp=2, seed=0)
+    for _ in range(2):
+        with pytest.raises(mitr.TransientError, match="did not intersect any geometry"):
+            it.render(scene, spp=2, seed=0)
