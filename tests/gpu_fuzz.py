@@ -147,11 +147,34 @@ def cfg_exhaustive(rng, kind):
     return d, spp, None
 
 
+def cfg_phasor(rng, kind):
+    """phasor_hdr_film (monochromatic variant) under transient_path on Cornell variants or transient_nlos_path."""
+    spp = rng.choice([2, 8, 16])
+    if rng.random() < 0.5:
+        w, h = rng.choice([(8, 8), (17, 9), (24, 16)])
+        bins = rng.choice([64, 256, 1024])
+        d = mitr.cornell_box_config(w, h, bins, spp, rng.choice([3, 8]))
+        wl = rng.choice([(0.5, 0.5), (0.2, 0.1), (1.0, 0.3)])
+        d["sensor"]["film"] = {"type": "phasor_hdr_film", "width": w, "height": h, "temporal_bins": bins, "start_opl": 3.5,
+                               "bin_width_opl": 6.0 / bins, "wl_mean": wl[0], "wl_sigma": wl[1], "rfilter": {"type": "box"}}
+    else:
+        w, h = rng.choice([(4, 4), (9, 7), (16, 16)])
+        bins = rng.choice([100, 300])
+        d = mitr.nlos_z_scene(w, h, bins, spp, nlos_hidden_geometry_sampling=rng.random() < 0.6,
+                              account_first_and_last_bounces=rng.random() < 0.5)
+        wl = rng.choice([(0.06, 0.06), (0.1, 0.03)])
+        d["relay_wall"]["nlos_sensor"]["transient_film"] = {
+            "type": "phasor_hdr_film", "width": w, "height": h, "temporal_bins": bins, "start_opl": 1.85,
+            "bin_width_opl": 1.8 / bins, "wl_mean": wl[0], "wl_sigma": wl[1], "rfilter": {"type": "box"}}
+    return d, spp, None
+
+
 KINDS = {"path": cfg_path, "mesh": cfg_path, "bvh": cfg_path, "mats": cfg_path, "vol": cfg_vol, "nlos": cfg_nlos,
-         "exh": cfg_exhaustive}
+         "exh": cfg_exhaustive, "phasor": cfg_phasor}
 
 
 def one(rng, kind):
+    mitr.set_variant("cuda_mono" if kind == "phasor" else "cuda_rgb")
     d, spp, focus = KINDS[kind](rng, kind)
     seed = rng.randrange(1000)
     scene = mitr.load_dict(d)
@@ -184,12 +207,17 @@ def one(rng, kind):
     ok = counted == ref["counters"]
 
     def l1(a, b):           # exhaustive_scan films are (H, W, Lh, Lw, T, C): fold the laser grid into the pixel axis
+        if a.ndim == 3:     # phasor film (H, W, 2F + 1): one "time bin" per stored component
+            a, b = a[:, :, :, None], b[:, :, :, None]
         if a.ndim == 6:
             a, b = a.reshape(a.shape[0], -1, a.shape[4], a.shape[5]), b.reshape(b.shape[0], -1, b.shape[4], b.shape[5])
         return film_l1(a, b)
     err = l1(raw, ref["transient"])
     ok = ok and err["zero_bins_mismatch"] == 0 and err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL
-    if kind != "exh":       # (an exhaustive film's develop() returns the channel mean as "steady", transient_hdr_film.py:213-214)
+    if kind == "phasor":    # every finite deposit counts (no time window): compare component-wise too
+        ok = ok and np.allclose(raw, ref["transient"], rtol=1e-4, atol=1e-6)
+        ok = ok and np.allclose(steady.cpu().numpy()[..., 0], ref["steady"][..., 0], rtol=1e-4, atol=1e-6)
+    elif kind != "exh":     # (an exhaustive film's develop() returns the channel mean as "steady", transient_hdr_film.py:213-214)
         ok = ok and np.allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
     integ.collect_counters = False
     integ.render(scene, seed=seed, spp=spp)
