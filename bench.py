@@ -253,7 +253,7 @@ def extra_workload(torch, mitr, lib, _lib, C, oracle, name, tag, make_scene, W, 
     cnt = counters_dict(counters.cpu().tolist())
     ms = time_render(torch, lib, _lib, C, dev, params, film, steady, stream, steps, 3)
     out = {"workload": name, "paths_per_step": W * H * spp, "kernel_ms": ms, "value": W * H * spp / ms / 1e3, "unit": UNIT,
-           "steps": steps, "counters": cnt,
+           "steps": steps, "counters": cnt, "kernel": integ.last_render_info(),
            "roofline": roofline_block(cnt["vertices"], W, H, T, ms, peak, peak_src, clocks, ncu_summary(tag))}
     if oracle is not None:
         # parity at the full film size with fewer samples per pixel (the oracle has to finish in seconds)
@@ -408,6 +408,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     headline_launches = launches[0]
     value = paths_total / (ms_per_step * 1e-3) / 1e6
+    render_info = integ.last_render_info()          # which histogram path / CTA shape the timed launches used
 
     # ---- N > 1: the assembled film against a single-GPU render of the same job, then the other multi-GPU records
     parity = None
@@ -589,6 +590,9 @@ def run_ours(args):
                                   ("kernel flushes into rank 0's film over NVLink peer memory + all-reduce fence)"
                                    if mode == "peer" else "NCCL reduce of film+steady to rank 0)") if n > 1 else ""),
                    "paths_per_step": paths_total, "film_bytes": W * H * T * 16,
+                   "kernel": dict(render_info, note="histogram_path global = red.global.add.v4.f32 into the film, which a "
+                                  "cudaMemsetAsync inside the timed step zeroes (counted in ms_per_step and roofline.kernel_ms, "
+                                  "not in gpu_launches); shared = shared-memory slots flushed once per pixel"),
                    "l2": "no flush needed: each step writes the 4 GiB film (>> 126 MB L2); the scene lives in shared memory",
                    "parallelism": f"pixel-tile x{n}"},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": headline_launches,

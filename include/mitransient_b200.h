@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TR_ABI_VERSION 13
+#define TR_ABI_VERSION 14
 
 /* ------------------------------------------------------------------ status codes */
 typedef enum TrStatus {
@@ -198,6 +198,7 @@ enum { TR_FLAG_CAMERA_UNWARP = 1,          /* common.py:25                      
        TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES = 128,
        TR_FLAG_DISCARD_DIRECT_PATHS = 256 };
 
+enum { TR_HIST_AUTO = 0, TR_HIST_SHARED = 1, TR_HIST_GLOBAL = 2 };
 enum { TR_CAPTURE_SINGLE = 0, TR_CAPTURE_CONFOCAL = 1, TR_CAPTURE_EXHAUSTIVE = 2 };
 
 typedef struct TrRenderParams {
@@ -229,7 +230,12 @@ typedef struct TrRenderParams {
        perspective_projection(1x1, fov, 1e-4, 1e4)), row-major 4x4.                                        */
     int32_t force_equal_grids;
     float laser_scan_sample_to_camera[16];
-    uint32_t _reserved[6];  /* (the `single` laser target and the per-pixel sensor targets,
+    /* Where the kernel accumulates a pixel's (time x RGBW) histogram -- a device-side choice with no counterpart in
+       the reference; both give the same film (the same deposits, summed in a different order).  AUTO picks by
+       measured cost ("Two histogram paths"); SHARED / GLOBAL state a preference, honoured whenever that
+       path can serve the call (tr_last_render_info tells which one ran).                                  */
+    uint32_t histogram_path; /* TR_HIST_*                                                    */
+    uint32_t _reserved[5];  /* (the `single` laser target and the per-pixel sensor targets,
                                transientnlospath.py:295-339, are traced on the device)      */
 } TrRenderParams;
 
@@ -333,6 +339,12 @@ int tr_peer_free(void *dev_ptr);
  * MUFU.RCP + one Newton step without nvcc's range guard (DESIGN.md "Arithmetic contract").  This runs that sequence
  * over EVERY fp32 x with 2^-126 <= |x| < 2^126 on the device and counts the values that differ from the IEEE
  * division 1.0f / x (expected: 0).  No reference counterpart (the reference delegates intersection to Embree/OptiX). */
+/* What the last tr_render / tr_render_sharded / tr_render_to_host launch of THIS host thread used (introspection for
+ * tests and bench.py): the histogram path that ran (TR_HIST_SHARED or TR_HIST_GLOBAL), its shared-memory histogram
+ * slots per CTA, threads per CTA, dynamic shared memory per CTA in bytes.  All zero before the first launch.        */
+typedef struct TrRenderInfo { uint32_t histogram_path, slots, threads, smem_bytes; } TrRenderInfo;
+void tr_last_render_info(TrRenderInfo *out);
+
 int tr_selftest_rcp(uint64_t *n_checked, uint64_t *n_mismatch, void *stream);
 
 #ifdef __cplusplus

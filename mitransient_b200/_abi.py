@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-TR_ABI_VERSION = 13
+TR_ABI_VERSION = 14
 
 TR_OK = 0
 TR_ERR_INVALID_ARGUMENT = -1
@@ -30,6 +30,8 @@ TR_FLAG_NLOS_HG_SAMPLING_DO_RROULETTE = 32
 TR_FLAG_NLOS_HG_SAMPLING_INCLUDES_RELAY_WALL = 64
 TR_FLAG_ACCOUNT_FIRST_AND_LAST_BOUNCES = 128
 TR_FLAG_DISCARD_DIRECT_PATHS = 256
+TR_HIST_AUTO, TR_HIST_SHARED, TR_HIST_GLOBAL = 0, 1, 2
+HIST_NAMES = {"auto": TR_HIST_AUTO, "shared": TR_HIST_SHARED, "global": TR_HIST_GLOBAL}
 
 TR_CAPTURE_SINGLE, TR_CAPTURE_CONFOCAL, TR_CAPTURE_EXHAUSTIVE = 0, 1, 2
 TR_FILM_TRANSIENT_HDR, TR_FILM_PHASOR_HDR = 0, 1
@@ -88,7 +90,11 @@ class TrRenderParams(C.Structure):
                 ("tile_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32),
                 ("film_channels", C.c_int32), ("accumulate", C.c_int32),
                 ("capture_type", C.c_int32), ("filter_depth", C.c_int32), ("force_equal_grids", C.c_int32),
-                ("laser_scan_sample_to_camera", C.c_float * 16), ("_reserved", C.c_uint32 * 6)]
+                ("laser_scan_sample_to_camera", C.c_float * 16), ("histogram_path", C.c_uint32), ("_reserved", C.c_uint32 * 5)]
+
+
+class TrRenderInfo(C.Structure):
+    _fields_ = [("histogram_path", C.c_uint32), ("slots", C.c_uint32), ("threads", C.c_uint32), ("smem_bytes", C.c_uint32)]
 
 
 class TrCounters(C.Structure):
@@ -110,6 +116,6 @@ class TrDeposit(C.Structure):
 EXPORTED_SYMBOLS = (
     "tr_device_check", "tr_abi_version", "tr_last_error", "tr_scene_create", "tr_scene_destroy",
     "tr_scene_info", "tr_render", "tr_render_to_host", "tr_owned_pixels", "tr_film_scatter_add", "tr_film_develop",
-    "tr_peer_alloc", "tr_peer_open", "tr_peer_close", "tr_peer_free", "tr_selftest_rcp", "tr_scene_refresh",
+    "tr_peer_alloc", "tr_peer_open", "tr_peer_close", "tr_peer_free", "tr_selftest_rcp", "tr_scene_refresh", "tr_last_render_info",
 )
 TR_PEER_HANDLE_BYTES = 64

@@ -64,6 +64,8 @@ def load() -> C.CDLL:
         lib.tr_film_scatter_add.argtypes = [vp, C.POINTER(_abi.TrFilmDesc), C.c_int32, vp, C.c_uint64, vp]
         lib.tr_film_develop.restype = C.c_int
         lib.tr_film_develop.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp]
+        lib.tr_last_render_info.restype = None
+        lib.tr_last_render_info.argtypes = [C.POINTER(_abi.TrRenderInfo)]
         lib.tr_selftest_rcp.restype = C.c_int
         lib.tr_selftest_rcp.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
         lib.tr_peer_alloc.restype = C.c_int

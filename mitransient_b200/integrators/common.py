@@ -8,6 +8,7 @@ Only the primal render is in scope; render_forward / render_backward (common.py:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 from .. import _abi, _lib
@@ -35,6 +36,9 @@ class TransientADIntegrator:
         props.get("block_size", 0)             # documented, never read (transientpath.py:68-71)
         self.last_counters: Optional[dict] = None
         self.collect_counters = False
+        # where the kernel accumulates a pixel's histogram: "auto" | "shared" | "global" (TrRenderParams.histogram_path;
+        # no counterpart in the reference, not a plugin property -- the film is the same either way)
+        self.histogram_path = os.environ.get("MITRANSIENT_B200_HISTOGRAM_PATH", "auto")
 
     # ---- common.py:32-85
     def prepare(self, scene: Scene, sensor, seed: int, spp: int, aovs=()) -> List[Tuple[int, int]]:
@@ -97,7 +101,16 @@ class TransientADIntegrator:
         p.tile_size, p.rank, p.world = tile_size, rank, world
         p.film_channels, p.accumulate = film_channels, int(accumulate)
         p.capture_type, p.filter_depth, p.force_equal_grids = 0, -1, 1
+        p.histogram_path = _abi.HIST_NAMES[self.histogram_path]
         return p
+
+    @staticmethod
+    def last_render_info() -> dict:
+        """What the last kernel launch of this thread used (tr_last_render_info): histogram path, slots, threads."""
+        info = _abi.TrRenderInfo()
+        _lib.load().tr_last_render_info(info)
+        return {"histogram_path": {0: None, _abi.TR_HIST_SHARED: "shared", _abi.TR_HIST_GLOBAL: "global"}[info.histogram_path],
+                "slots": int(info.slots), "threads": int(info.threads), "smem_bytes": int(info.smem_bytes)}
 
     def device_scene(self, scene: Scene, sensor) -> _lib.DeviceScene:
         key = scene.description_key(sensor)

@@ -19,6 +19,7 @@ ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--scene", default="cornell", choices=["cornell", "nlos", "vol", "mesh", "sphere0", "sphere1", "sphere2", "sphere3", "sphere4"])
+ap.add_argument("--hist", default="auto", choices=["auto", "shared", "global"], help="TrRenderParams.histogram_path")
 ap.add_argument("--world", type=int, default=1, help="render only the tiles of rank 0 of `world` ranks (the per-GPU share of an N-GPU job)")
 a = ap.parse_args()
 if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256 x 4096 bins, 1024 spp
@@ -27,7 +28,7 @@ if a.scene == "nlos":          # BASELINE config C3: letter Z, confocal, 256x256
     a.spp = 1024 if a.spp == 256 else a.spp
     scene = mitr.load_dict(mitr.nlos_z_scene(a.width, a.height, a.bins, a.spp))
 elif a.scene == "vol":         # BASELINE config C4(i): volumetric Cornell box 256x384 x 512 bins
-    a.width, a.height, a.bins, a.spp = 256, 384, 512, 256
+    a.width, a.height, a.bins = 256, 384, 512
     scene = mitr.load_dict(mitr.cornell_box_volumetric(a.width, a.height, a.bins, a.spp))
 elif a.scene == "mesh":        # the Cornell box as 36 mesh triangles (18 parallelograms, brute-force loop)
     a.spp = 64 if a.spp == 256 else a.spp
@@ -43,6 +44,7 @@ film = torch.zeros((a.height, a.width, a.bins, 4), dtype=torch.float32, device="
 steady = torch.zeros((a.height, a.width, 3), dtype=torch.float32, device="cuda")
 params = integ.make_params(a.spp, a.spp, 0, rank=0, world=a.world)
 integ.fill_params_(params, scene, sensor)
+params.histogram_path = {"auto": 0, "shared": 1, "global": 2}[a.hist]
 st = torch.cuda.current_stream()
 for _ in range(3):
     _lib.check(lib.tr_render(dev.handle, C.byref(params), film.data_ptr(), steady.data_ptr(), None, st.cuda_stream))

@@ -24,3 +24,17 @@ def oracle():
 def mitr():
     import mitransient_b200
     return mitransient_b200
+
+
+# Every GPU test runs three times: with the library's own choice of histogram path (TR_HIST_AUTO) and with each of the
+# two paths preferred (shared-memory slots / global reductions), so that toy-size inputs cover both kernels' code.
+def pytest_generate_tests(metafunc):
+    if metafunc.definition.get_closest_marker("gpu") is not None:
+        metafunc.parametrize("hist_path", ["auto", "shared", "global"], indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def hist_path(request, monkeypatch):
+    which = getattr(request, "param", "auto")
+    monkeypatch.setenv("MITRANSIENT_B200_HISTOGRAM_PATH", which)   # read by every integrator built during the test
+    return which

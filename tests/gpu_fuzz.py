@@ -190,6 +190,10 @@ def one(rng, kind):
             print("DRY ", kind, "oracle refuses:", exc, flush=True)
         return True
     integ.collect_counters = True
+    # the counting render prefers one histogram path, the plain render below the other (honoured where the scene / film
+    # allow both, tr_last_render_info says what ran)
+    prefs = ("shared", "global") if seed % 2 else ("global", "shared")
+    integ.histogram_path = prefs[0]
     try:
         steady, _ = integ.render(scene, seed=seed, spp=spp)
     except (mitr.TransientError, ValueError, AssertionError) as exc:
@@ -202,6 +206,7 @@ def one(rng, kind):
         print("FAIL", kind, "only the GPU path refuses:", exc, flush=True)
         return False
     counted = dict(integ.last_counters)
+    ran = integ.last_render_info()["histogram_path"][0]
     raw = sensor.film().develop(raw=True)[1].cpu().numpy()
     ref = oracle.render(scene, integ, seed=seed, spp=spp)
     ok = counted == ref["counters"]
@@ -220,7 +225,9 @@ def one(rng, kind):
     elif kind != "exh":     # (an exhaustive film's develop() returns the channel mean as "steady", transient_hdr_film.py:213-214)
         ok = ok and np.allclose(steady.cpu().numpy(), ref["steady"], rtol=1e-4, atol=1e-6)
     integ.collect_counters = False
+    integ.histogram_path = prefs[1]
     integ.render(scene, seed=seed, spp=spp)
+    ran += integ.last_render_info()["histogram_path"][0]
     raw2 = sensor.film().develop(raw=True)[1].cpu().numpy()
     err2 = l1(raw2, ref["transient"])
     ok = ok and err2["zero_bins_mismatch"] == 0 and err2["whole"] <= WHOLE_TOL
@@ -229,7 +236,7 @@ def one(rng, kind):
     fw, fh = film.size()
     print(("OK  " if ok else "FAIL"), kind, f"prims={info['primitives']} nodes={info['bvh_nodes']} film={fw}x{fh}x{film.temporal_bins} spp={spp} "
           f"seed={seed} depth={integ.max_depth if integ.max_depth < 1 << 31 else -1} vertices={counted['vertices']} deposits={counted['deposits_in_range']} "
-          f"L1={err['whole']:.1e}/{err2['whole']:.1e}", flush=True)
+          f"L1={err['whole']:.1e}/{err2['whole']:.1e} hist={ran}", flush=True)
     if not ok:
         print("     counters gpu", counted, "\n     counters ref", ref["counters"], "\n     err", err, err2, flush=True)
     return ok

@@ -321,3 +321,27 @@ def test_scene_refresh_reuploads_the_same_scene(mitr):
     _lib.check(_lib.load().tr_scene_refresh(dev.handle, _lib.current_stream_ptr()))
     _, t1 = integ.render(scene, seed=1, spp=4)
     assert torch.equal(t0, t1)
+
+
+def test_histogram_path_preference_is_honoured_and_reported(mitr, oracle, hist_path):
+    """TrRenderParams.histogram_path: the diffuse Cornell box can run on either path (tr_last_render_info says which
+    one did); a scene with a mirror only has the shared-memory instantiation, whatever the preference."""
+    scene = mitr.load_dict(mitr.cornell_box_config(16, 16, 64, 8))
+    integ = scene.integrator()
+    assert integ.histogram_path == hist_path
+    integ.collect_counters = True
+    integ.render(scene, seed=1, spp=8)
+    info = integ.last_render_info()
+    assert info["histogram_path"] == {"auto": "global", "shared": "shared", "global": "global"}[hist_path], info
+    assert info["threads"] == 512 and (info["slots"] >= 2) == (info["histogram_path"] == "shared")
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = oracle.render(scene, integ, seed=1, spp=8)
+    assert integ.last_counters == ref["counters"]
+    err = film_l1(raw, ref["transient"])
+    assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL and err["zero_bins_mismatch"] == 0, err
+
+    d = mitr.cornell_box_config(16, 16, 64, 8)
+    d["large-box"]["bsdf"] = {"type": "conductor"}
+    scene = mitr.load_dict(d)
+    scene.integrator().render(scene, seed=1, spp=8)
+    assert scene.integrator().last_render_info()["histogram_path"] == "shared"
