@@ -194,20 +194,30 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------- roofline
-def roofline_block(n_v, W, H, T, kernel_ms, peak, peak_src, clocks, ncu):
+def film_passes(integ, info=None):
+    """DRAM passes over the film of the last launch: 3 on the global-reduction path behind a memset, else 1."""
+    info = info or integ.last_render_info()
+    volumetric = type(integ).__name__ == "TransientPRBVolpathIntegrator"      # zeroes its film inside the kernel (kZero)
+    return 3 if info["histogram_path"] == "global" and not volumetric else 1
+
+
+def roofline_block(n_v, W, H, T, kernel_ms, peak, peak_src, clocks, ncu, film_passes=1):
     """SURVEY 8(d) byte model next to what the kernel really does: its DRAM traffic is the film written once (path state
     lives in registers), its ceiling is instruction issue."""
     b_alg = 128.0 * n_v + 16.0 * W * H * T + 12.0 * W * H
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
-    film_bytes = 16.0 * W * H * T + 12.0 * W * H
+    # DRAM traffic model: the shared-memory histogram path (and the volumetric kernel, which zeroes its own film in the L2)
+    # writes the film once; the global-reduction path behind a memset writes it (memset), reads it back and writes it again
+    film_bytes = film_passes * 16.0 * W * H * T + 12.0 * W * H
     r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
          "traffic": ncu["dram_bytes"] if ncu else None, "peak_source": peak_src,
          "kernel": "render_transient_path_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes": b_alg,
          "live_path_vertices": n_v,
          "model": "SURVEY 8d: 128 B x N_v + 16 B x H*W*T + 12 B x H*W (wavefront byte model).  This kernel keeps path state "
-                  "in registers: its real DRAM traffic is the film written once (dram_frac), its ceiling is instruction issue",
+                  "in registers: its real DRAM traffic is the film (dram_frac: written once by the shared-memory histogram path; memset + "
+                  "read + write = 3 passes by the global-reduction path), its ceiling is instruction issue",
          "dram_frac": film_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
-         "dram_bytes_model": film_bytes}
+         "dram_bytes_model": film_bytes, "film_passes": film_passes}
     if ncu:
         f_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         slots = N_SM * 4 * f_mhz * 1e6 * kernel_ms * 1e-3
@@ -254,7 +264,7 @@ def extra_workload(torch, mitr, lib, _lib, C, oracle, name, tag, make_scene, W, 
     ms = time_render(torch, lib, _lib, C, dev, params, film, steady, stream, steps, 3)
     out = {"workload": name, "paths_per_step": W * H * spp, "kernel_ms": ms, "value": W * H * spp / ms / 1e3, "unit": UNIT,
            "steps": steps, "counters": cnt, "kernel": integ.last_render_info(),
-           "roofline": roofline_block(cnt["vertices"], W, H, T, ms, peak, peak_src, clocks, ncu_summary(tag))}
+           "roofline": roofline_block(cnt["vertices"], W, H, T, ms, peak, peak_src, clocks, ncu_summary(tag), film_passes(integ))}
     if oracle is not None:
         # parity at the full film size with fewer samples per pixel (the oracle has to finish in seconds)
         sp = mitr.load_dict(make_scene(parity_spp))
@@ -524,7 +534,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant (only) kernel: render_transient_path_kernel
     peak, peak_src = measured_peak_hbm()
-    roofline = roofline_block(n_v / n, W, H / n, T, kern_ms, peak, peak_src, clk, ncu_summary("C2") if n == 1 else None)
+    roofline = roofline_block(n_v / n, W, H / n, T, kern_ms, peak, peak_src, clk, ncu_summary("C2") if n == 1 else None,
+                              film_passes(integ, render_info))
     roofline["kernel_ms_per_rank"] = [round(x, 3) for x in kern_ms_per_rank]
 
     # ---- CPU baseline (oracle port), rank 0, N = 1 only: the FULL C2 render when the host finishes it in ~20 s -- then it
