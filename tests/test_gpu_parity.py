@@ -325,7 +325,7 @@ def test_scene_refresh_reuploads_the_same_scene(mitr):
 
 def test_histogram_path_preference_is_honoured_and_reported(mitr, oracle, hist_path):
     """TrRenderParams.histogram_path: the diffuse Cornell box can run on either path (tr_last_render_info says which
-    one did); a scene with a mirror only has the shared-memory instantiation, whatever the preference."""
+    one did), with or without specular materials."""
     scene = mitr.load_dict(mitr.cornell_box_config(16, 16, 64, 8))
     integ = scene.integrator()
     assert integ.histogram_path == hist_path
@@ -340,8 +340,16 @@ def test_histogram_path_preference_is_honoured_and_reported(mitr, oracle, hist_p
     err = film_l1(raw, ref["transient"])
     assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL and err["zero_bins_mismatch"] == 0, err
 
+    # a mirror box: the general-material kernels exist for both paths too
     d = mitr.cornell_box_config(16, 16, 64, 8)
     d["large-box"]["bsdf"] = {"type": "conductor"}
     scene = mitr.load_dict(d)
-    scene.integrator().render(scene, seed=1, spp=8)
-    assert scene.integrator().last_render_info()["histogram_path"] == "shared"
+    integ = scene.integrator()
+    integ.collect_counters = True
+    integ.render(scene, seed=1, spp=8)
+    assert integ.last_render_info()["histogram_path"] == info["histogram_path"]
+    raw = scene.sensors()[0].film().develop(raw=True)[1].cpu().numpy()
+    ref = oracle.render(scene, integ, seed=1, spp=8)
+    assert integ.last_counters == ref["counters"]
+    err = film_l1(raw, ref["transient"])
+    assert err["whole"] <= WHOLE_TOL and err["max_t"] <= PER_BIN_TOL and err["zero_bins_mismatch"] == 0, err
