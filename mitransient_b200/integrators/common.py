@@ -101,6 +101,8 @@ class TransientADIntegrator:
         p.tile_size, p.rank, p.world = tile_size, rank, world
         p.film_channels, p.accumulate = film_channels, int(accumulate)
         p.capture_type, p.filter_depth, p.force_equal_grids = 0, -1, 1
+        if self.histogram_path not in _abi.HIST_NAMES:
+            raise ValueError(f'histogram_path must be one of {sorted(_abi.HIST_NAMES)}, not {self.histogram_path!r}')
         p.histogram_path = _abi.HIST_NAMES[self.histogram_path]
         return p
 

@@ -1,4 +1,5 @@
 """Host-side logic (no GPU): scene ingestion, plugin parameters and the reference's accept/reject behaviour."""
+import ctypes as C
 import math
 
 import numpy as np
@@ -466,3 +467,21 @@ def test_closed_mesh_cubes_become_box_primitives(mitr):
     assert box.shape == (1, 4, 3) and abs(abs(np.linalg.det(box[0, 1:] - box[0, 0])) - 8.0) < 1e-9
     assert merge_box(q[:, [0, 2, 1]], t) is None          # inward-facing faces: a room, not a solid
     assert merge_box(q[:5], t[:5]) is None                # open
+
+
+def test_histogram_path_is_a_host_side_attribute_not_a_plugin_property(mitr, monkeypatch):
+    """TrRenderParams.histogram_path: "auto" unless the integrator attribute (or MITRANSIENT_B200_HISTOGRAM_PATH, which the
+    GPU tests use to run every test on both device paths) says otherwise; never read from the plugin dictionary."""
+    from mitransient_b200 import _abi
+    monkeypatch.delenv("MITRANSIENT_B200_HISTOGRAM_PATH", raising=False)
+    integ = mitr.load_dict(mitr.cornell_box_config(4, 4, 8, 1)).integrator()
+    assert integ.histogram_path == "auto" and integ.make_params(1, 1, 0).histogram_path == _abi.TR_HIST_AUTO
+    for name, value in (("shared", _abi.TR_HIST_SHARED), ("global", _abi.TR_HIST_GLOBAL)):
+        integ.histogram_path = name
+        assert integ.make_params(1, 1, 0).histogram_path == value
+    integ.histogram_path = "registers"
+    with pytest.raises(ValueError):
+        integ.make_params(1, 1, 0)
+    monkeypatch.setenv("MITRANSIENT_B200_HISTOGRAM_PATH", "global")
+    assert mitr.load_dict(mitr.cornell_box_config(4, 4, 8, 1)).integrator().histogram_path == "global"
+    assert C.sizeof(_abi.TrRenderInfo) == 16
