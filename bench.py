@@ -61,7 +61,7 @@ def ncu_summary(tag):
         return {"warp_inst": float(d["smsp__inst_executed.sum"]["value"]), "dram_bytes": float(d["dram_bytes_per_launch"]),
                 "lanes_per_inst": float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]["value"]),
                 "kernel_ms_under_ncu": float(d["gpu__time_duration.sum"]["value"]), "source": os.path.relpath(p, ROOT),
-                "kernel_version": d.get("kernel_version")}
+                "kernel_version": d.get("kernel_version"), "note": d.get("note")}
     except Exception:
         return None
 
@@ -225,7 +225,7 @@ def roofline_block(n_v, W, H, T, kernel_ms, peak, peak_src, clocks, ncu, film_pa
                       "sm_mhz": f_mhz, "issue_slots": slots,
                       "what": "executed warp instructions (ncu capture of the same workload, committed) / (148 SMs x 4 "
                               "schedulers x SM clock x kernel time of THIS run)", "source": ncu["source"],
-                      "kernel_version": ncu.get("kernel_version")}
+                      "kernel_version": ncu.get("kernel_version"), "note": ncu.get("note")}
         r["traffic_source"] = ncu["source"] + " (ncu --set full of the same command; not re-measured in this run)"
     else:
         r["issue"] = None
